@@ -1,0 +1,94 @@
+/*
+ * timbre_trap_b200 - C ABI of the B200 (sm_100a) hot path of sony/timbre-trap.
+ *
+ * The reference has no FFI: its boundary for this path is the Python class API of
+ * timbre_trap.framework (reference: timbre_trap/framework/__init__.py:1-4).  The Python host
+ * side of this repo (timbre_trap_b200/framework) mirrors those classes and binds the entry
+ * points below with ctypes; each entry point cites the reference method it replaces.
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - every function returns 0 (TT_OK) on success, non-zero otherwise; tt_last_error() gives
+ *     the message of the last failure on the calling thread.  Nothing throws.
+ *   - no ownership transfer: callers own every buffer except the plan's private scratch.
+ *   - calls are asynchronous on `stream`; a plan (it owns scratch) must be used from one
+ *     stream at a time.
+ *
+ * Layouts
+ *   audio         (B, n_blocks * L)            fp32, L = block_length
+ *   coefficients  (B, F, n_blocks * M, 2)      fp32 interleaved (re, im) - i.e. exactly the memory
+ *                                              behind the reference's (B, 2, F, T) `to_real` view
+ *                                              (cqtwrapper.py:91-95): channels-last
+ */
+#ifndef TIMBRE_TRAP_B200_H
+#define TIMBRE_TRAP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tt_cqt_plan tt_cqt_plan;
+
+/* library / error plumbing */
+const char* tt_last_error(void);
+int tt_version(void);
+
+/*
+ * Replaces cqt_pytorch.CQT.__init__ as called from cqtwrapper.py:31-35 (the window / index /
+ * dual tables).  All table pointers are HOST arrays in the packed form documented in
+ * oracle/nsgt_ref.py::NSGTTables: per bin k, `length[k]` non-zero taps that start at crop
+ * index `first[k]` and at spectrum index `start[k]`; `offset[k]` is the prefix sum.
+ * `max_blocks_per_launch` bounds the plan's scratch (blocks are processed in groups).
+ */
+int tt_cqt_plan_create(tt_cqt_plan** plan, int block_length, int n_bins, int max_window_length,
+                       const int32_t* start, const int32_t* length, const int32_t* first, const int32_t* offset,
+                       const float* win_packed, const float* dual_packed, int n_taps,
+                       int max_blocks_per_launch);
+int tt_cqt_plan_destroy(tt_cqt_plan* plan);
+/* bytes of device scratch held by the plan */
+int64_t tt_cqt_plan_scratch_bytes(const tt_cqt_plan* plan);
+
+/*
+ * CQT.forward / encode + to_real  (cqtwrapper.py:50-97).
+ *   audio   (batch, n_blocks * L) fp32
+ *   coeffs  (batch, F, n_blocks * M, 2) fp32
+ */
+int tt_cqt_forward(tt_cqt_plan* plan, const float* audio, int batch, int n_blocks, float* coeffs, void* stream);
+
+/*
+ * CQT.decode  (cqtwrapper.py:184-213): to_complex + synthesis + global infinity-norm normalise.
+ *   coeffs     (batch, F, n_blocks * M, 2) fp32
+ *   audio      (batch, n_blocks * L) fp32
+ *   peak       device scalar (fp32, >= 0): receives max|audio| BEFORE normalisation; must be
+ *              zero-initialised by the caller OR pass accumulate_peak = 0 to have it reset here.
+ *   normalise  0: leave audio un-normalised (peak still written) - the sharded path all-reduces
+ *              `peak` across ranks and then calls tt_scale_by_peak;
+ *              1: divide by the peak when it is non-zero (reference semantics).
+ */
+int tt_cqt_inverse(tt_cqt_plan* plan, const float* coeffs, int batch, int n_blocks, float* audio,
+                   float* peak, int normalise, void* stream);
+
+/* audio[i] /= *peak when *peak != 0  (cqtwrapper.py:209-211) */
+int tt_scale_by_peak(float* audio, int64_t n, const float* peak, void* stream);
+
+/*
+ * TimbreTrap.to_activations (modules.py:271-289) = tanh(CQT.to_magnitude) (cqtwrapper.py:122-141)
+ *   coeffs (rows, 2) interleaved -> out (rows);  apply_tanh = 0 gives the plain magnitude
+ */
+int tt_magnitude(const float* coeffs, int64_t n, int apply_tanh, float* out, void* stream);
+
+/*
+ * CQT.to_decibels (cqtwrapper.py:143-182): per batch item 20*log10(max(x,1e-10)), floored at the
+ * item's max - 80 dB; if rescale: shifted to a 0 dB ceiling and mapped to [0,1].
+ *   magnitude, out  (batch, per_item)
+ *   item_max        device scratch of `batch` floats
+ */
+int tt_to_decibels(const float* magnitude, int batch, int64_t per_item, int rescale, float* out,
+                   float* item_max, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,121 @@
+"""
+GPU parity of the CQT kernels (through the C ABI, via timbre_trap_b200.framework.CQT) against the
+CPU oracle (oracle/nsgt_ref.py, complex128).  Tolerance: 1e-4 norm-relative, fp32
+(BASELINE.json north_star; SURVEY.md section 8c defines "relative" as max-abs / max|ref| and l2 / ||ref||).
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.helpers import rel_err, tonal_clip
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+BASE = (9, 60, 22050, 3)
+SMALL = (6, 12, 8000, 0.5)
+
+
+def _mods(cfg):
+    from oracle.model_ref import CQTRef
+    from timbre_trap_b200.framework import CQT
+    return CQT(*cfg), CQTRef(*cfg)
+
+
+@pytest.mark.parametrize('cfg,batch,blocks', [(BASE, 2, 1), (BASE, 1, 3), (SMALL, 3, 2), ((8, 24, 16000, 1.0), 2, 2)])
+def test_forward_matches_oracle(cfg, batch, blocks):
+    cqt, ref = _mods(cfg)
+    audio = tonal_clip(blocks * ref.block_length, cfg[2], seed=7, n_batch=batch)
+    noise = torch.from_numpy(np.random.default_rng(1).uniform(-1, 1, audio.shape).astype(np.float32))
+    for x in (audio, noise):
+        got = cqt(x.cuda())
+        want = ref(x)
+        assert got.shape == want.shape == (batch, 2, ref.n_bins, blocks * ref.max_window_length)
+        assert tuple(got.stride()) == tuple(want.stride())          # same channels-last view as the reference
+        emax, el2 = rel_err(got.cpu().numpy(), want.numpy())
+        assert emax < TOL and el2 < TOL, (emax, el2)
+        # per bin as well: low bins are ~60 dB below the loudest ones
+        g, w = got.cpu().numpy(), want.numpy()
+        for k in range(0, ref.n_bins, 7):
+            e, _ = rel_err(g[:, :, k], w[:, :, k])
+            assert e < 5 * TOL, (k, e)
+
+
+def test_encode_complex_and_layout_helpers():
+    cqt, ref = _mods(SMALL)
+    x = tonal_clip(2 * ref.block_length, SMALL[2], seed=3, n_batch=2)
+    c = cqt.encode(x.cuda())
+    assert c.is_complex() and c.shape == (2, 1, ref.n_bins, 2 * ref.max_window_length)
+    r = cqt.to_real(c)
+    assert torch.equal(r, cqt(x.cuda()))
+    assert torch.equal(cqt.to_complex(r), c.squeeze(1))
+
+
+@pytest.mark.parametrize('cfg,batch,blocks', [(BASE, 2, 2), (SMALL, 3, 2)])
+def test_inverse_matches_oracle(cfg, batch, blocks):
+    cqt, ref = _mods(cfg)
+    rng = np.random.default_rng(5)
+    # (a) consistent coefficients (a real signal's transform), (b) arbitrary coefficients
+    audio = tonal_clip(blocks * ref.block_length, cfg[2], seed=9, n_batch=batch)
+    consistent = ref(audio).contiguous()
+    arbitrary = torch.from_numpy(rng.standard_normal(tuple(consistent.shape)).astype(np.float32))
+    for c in (consistent, arbitrary):
+        raw, peak = cqt.decode_raw(c.cuda())
+        want_raw = ref.decode_raw(c)
+        emax, el2 = rel_err(raw.cpu().numpy(), want_raw.numpy())
+        assert emax < TOL and el2 < TOL, (emax, el2)
+        assert abs(float(peak) - float(want_raw.abs().max())) <= TOL * float(want_raw.abs().max())
+        got = cqt.decode(c.cuda())
+        want = ref.decode(c)
+        emax, el2 = rel_err(got.cpu().numpy(), want.numpy())
+        assert emax < TOL and el2 < TOL, (emax, el2)
+        assert abs(float(got.abs().max()) - 1.0) < 1e-6
+    # complex input path (cqtwrapper.py:200) and the all-zero case (no divide, cqtwrapper.py:209)
+    cc = cqt.to_complex(consistent.cuda()).unsqueeze(-3)
+    assert torch.allclose(cqt.decode(cc), cqt.decode(consistent.cuda()), atol=1e-6)
+    z = cqt.decode(torch.zeros_like(consistent).cuda())
+    assert torch.count_nonzero(z) == 0 and torch.isfinite(z).all()
+
+
+def test_round_trip_and_linearity_large():
+    """Size-independent properties at a size the oracle is not run at (64 blocks)."""
+    cqt, ref = _mods(BASE)
+    x = tonal_clip(8 * ref.block_length, 22050, seed=13, n_batch=8).cuda()
+    y = torch.roll(x, 1234, dims=-1) * 0.5
+    cx, cy = cqt(x), cqt(y)
+    cxy = cqt(2.0 * x - 3.0 * y)
+    emax, el2 = rel_err(cxy.cpu().numpy(), (2.0 * cx - 3.0 * cy).cpu().numpy())
+    assert emax < TOL and el2 < TOL
+    # block independence: transforming the blocks one by one gives the same rows
+    one = cqt(x[:1, :, ref.block_length:2 * ref.block_length])
+    assert torch.equal(one[0], cx[0, :, :, ref.max_window_length:2 * ref.max_window_length])
+    # round trip: decode(encode(x)) == x / max|x| up to the transform's own coverage (>= 60 dB on tonal input)
+    back = cqt.decode(cx)
+    xn = x / x.abs().max()
+    snr = 10 * torch.log10((xn ** 2).sum() / ((xn - back) ** 2).sum())
+    assert float(snr) > 50.0, float(snr)   # the oracle itself gives 52.3 dB on this clip (70 uncovered rfft bins)
+
+
+def test_magnitude_and_decibels():
+    from oracle.model_ref import to_decibels_ref
+    cqt, ref = _mods(SMALL)
+    x = tonal_clip(2 * ref.block_length, SMALL[2], seed=21, n_batch=3)
+    c = ref(x)
+    mag = cqt.to_magnitude(c.cuda())
+    assert rel_err(mag.cpu().numpy(), ref.to_magnitude(c).numpy())[0] < 1e-6
+    db = cqt.to_decibels(mag)
+    want = to_decibels_ref(ref.to_magnitude(c))
+    assert float((db.cpu() - want).abs().max()) < 1e-5
+    db_raw = cqt.to_decibels(mag, rescale=False)
+    assert float((db_raw.cpu() - to_decibels_ref(ref.to_magnitude(c), rescale=False)).abs().max()) < 1e-3
+
+
+def test_rejects_cpu_and_ragged_inputs():
+    from timbre_trap_b200._lib import TimbreTrapB200Error
+    cqt, ref = _mods(SMALL)
+    with pytest.raises(TimbreTrapB200Error):
+        cqt(torch.zeros(1, 1, ref.block_length))
+    with pytest.raises(ValueError):
+        cqt(torch.zeros(1, 1, ref.block_length + 1).cuda())
+    empty = cqt(torch.zeros(0, 1, ref.block_length).cuda())
+    assert empty.shape == (0, 2, ref.n_bins, ref.max_window_length)

@@ -1,0 +1,66 @@
+"""
+ctypes binding of libtimbretrap_b200.so (include/timbre_trap_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, an
+exception is raised.  Build it with `python -c "import __graft_entry__ as g; g.build()"`
+(or `python -m timbre_trap_b200.build`).
+"""
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libtimbretrap_b200.so')
+
+_lib = None
+
+c_void_p, c_int, c_int64, c_float_p, c_int32_p = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                 ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int32))
+
+# name -> (restype, argtypes); every symbol include/timbre_trap_b200.h declares
+SIGNATURES = {
+    'tt_last_error': (ctypes.c_char_p, []),
+    'tt_version': (c_int, []),
+    'tt_cqt_plan_create': (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int32_p, c_int32_p, c_int32_p,
+                                   c_int32_p, c_float_p, c_float_p, c_int, c_int]),
+    'tt_cqt_plan_destroy': (c_int, [c_void_p]),
+    'tt_cqt_plan_scratch_bytes': (c_int64, [c_void_p]),
+    'tt_cqt_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'tt_cqt_inverse': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    'tt_scale_by_peak': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    'tt_magnitude': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    'tt_to_decibels': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+}
+
+
+class TimbreTrapB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded shared library (loads on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TimbreTrapB200Error(
+                f'{LIB_PATH} is missing - the CUDA extension has not been built (run __graft_entry__.build()). '
+                'timbre_trap_b200 has no CPU or PyTorch fallback.')
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)      # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != 0:
+        msg = lib().tt_last_error()
+        raise TimbreTrapB200Error(f'timbre_trap_b200 call failed (status {status}): {msg.decode() if msg else "?"}')
+
+
+def require_cuda(tensor, what):
+    if not tensor.is_cuda:
+        raise TimbreTrapB200Error(f'{what} must be a CUDA tensor: timbre_trap_b200 has no CPU path '
+                                  '(the CPU oracle lives in oracle/ and is test-only).')
