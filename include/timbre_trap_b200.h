@@ -88,6 +88,13 @@ int tt_magnitude(const float* coeffs, int64_t n, int apply_tanh, float* out, voi
 int tt_to_decibels(const float* magnitude, int batch, int64_t per_item, int rescale, float* out,
                    float* item_max, void* stream);
 
+/*
+ * Self-test of the tcgen05 / TMEM plumbing the conv kernels are built on (no reference counterpart):
+ * D (128 x n, fp32) = A (128 x k, bf16, row-major) * B (n x k, bf16, row-major)^T on one CTA.
+ * swap_lbo_sbo = 1 encodes the shared-memory descriptors with the two stride fields exchanged (must FAIL).
+ */
+int tt_umma_probe(const void* a_bf16, const void* b_bf16, float* d, int n, int k, int swap_lbo_sbo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,27 @@
+"""tcgen05 / TMEM plumbing self-test (GPU): a one-CTA bf16 GEMM through umma.cuh against torch fp32."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(n, k, swap):
+    from timbre_trap_b200 import _lib
+    g = torch.Generator(device='cuda').manual_seed(n * 1000 + k)
+    a = torch.randn((128, k), device='cuda', generator=g).bfloat16()
+    b = torch.randn((n, k), device='cuda', generator=g).bfloat16()
+    d = torch.full((128, n), float('nan'), device='cuda')
+    _lib.check(_lib.lib().tt_umma_probe(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+                                        ctypes.c_void_p(d.data_ptr()), n, k, swap,
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    want = a.float() @ b.float().t()
+    return float((d - want).abs().max()), float(want.abs().max())
+
+
+@pytest.mark.parametrize('n,k', [(16, 16), (16, 32), (32, 64), (64, 128), (128, 256), (256, 64)])
+def test_probe_gemm(n, k):
+    err, scale = _run(n, k, 0)
+    assert err <= 1e-3 * scale, (err, scale)

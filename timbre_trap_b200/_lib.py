@@ -29,6 +29,7 @@ SIGNATURES = {
     'tt_cqt_inverse': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
     'tt_scale_by_peak': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'tt_magnitude': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
+    'tt_umma_probe': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'tt_to_decibels': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }
 

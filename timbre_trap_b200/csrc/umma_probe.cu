@@ -1,0 +1,79 @@
+// Self-test of the tcgen05 plumbing in umma.cuh: D (128 x N, fp32) = A (128 x K, bf16) * B (N x K, bf16)^T on one
+// CTA, operands staged by plain loads into the SWIZZLE_NONE K-major canonical layout.  The GPU test suite runs it
+// before any conv kernel so that a descriptor-encoding mistake shows up as a GEMM mismatch, not as a wrong model.
+#include "../../include/timbre_trap_b200.h"
+#include "tt_common.cuh"
+#include "umma.cuh"
+
+namespace tt {
+
+// smem layout: core matrix (row-group g, k-group kg) of an R-row operand at  kg * (R * 16) + g * 128  bytes
+//   -> SBO (8-row groups) = 128 B, LBO (k-groups) = R * 16 B
+__global__ void __launch_bounds__(128) umma_probe_kernel(const __nv_bfloat16* __restrict__ A,
+                                                         const __nv_bfloat16* __restrict__ Bm, float* __restrict__ D,
+                                                         int N, int K, int swap_lbo_sbo) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + (size_t)(K / 8) * 128 * 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    for (int i = tid; i < 128 * (K / 8); i += 128) {
+        const int row = i % 128, kg = i / 128;
+        *reinterpret_cast<uint4*>(sA + (size_t)kg * 128 * 16 + row * 16) =
+            *reinterpret_cast<const uint4*>(A + (size_t)row * K + kg * 8);
+    }
+    for (int i = tid; i < N * (K / 8); i += 128) {
+        const int row = i % N, kg = i / N;
+        *reinterpret_cast<uint4*>(sB + (size_t)kg * N * 16 + row * 16) =
+            *reinterpret_cast<const uint4*>(Bm + (size_t)row * K + kg * 8);
+    }
+    if (warp == 0) umma::tmem_alloc(&tmem_base, 256);
+    if (tid == 0) {
+        umma::mbar_init(&bar, 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = tmem_base;
+
+    if (tid == 0) {
+        const uint32_t idesc = umma::make_idesc_bf16(128, N);
+        const uint32_t a0 = umma::smem_u32(sA), b0 = umma::smem_u32(sB);
+        for (int k = 0; k < K / 16; ++k) {
+            const uint32_t lbo_a = 128 * 16, lbo_b = N * 16, sbo = 128;
+            uint64_t da = swap_lbo_sbo ? umma::make_desc(a0 + k * 2 * lbo_a, sbo, lbo_a) : umma::make_desc(a0 + k * 2 * lbo_a, lbo_a, sbo);
+            uint64_t db = swap_lbo_sbo ? umma::make_desc(b0 + k * 2 * lbo_b, sbo, lbo_b) : umma::make_desc(b0 + k * 2 * lbo_b, lbo_b, sbo);
+            umma::mma_bf16(tmem, da, db, idesc, k > 0);
+        }
+        umma::commit(&bar);
+    }
+    umma::mbar_wait(&bar, 0);
+    umma::fence_after_sync();
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        umma::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) D[(size_t)(warp * 32 + lane) * N + c + i] = v[i];
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, 256);
+}
+
+}  // namespace tt
+
+extern "C" int tt_umma_probe(const void* a_bf16, const void* b_bf16, float* d, int n, int k, int swap_lbo_sbo, void* stream) {
+    TT_REQUIRE(a_bf16 && b_bf16 && d, "null argument");
+    TT_REQUIRE(n % 16 == 0 && n >= 16 && n <= 256 && k % 16 == 0 && k >= 16 && k <= 256, "probe supports N,K in [16,256], multiples of 16");
+    const size_t smem = (size_t)(k / 8) * (128 + n) * 16;
+    TT_CUDA_CHECK(cudaFuncSetAttribute(tt::umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tt::umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16, d, n, k,
+                                                                   swap_lbo_sbo);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
