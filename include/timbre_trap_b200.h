@@ -89,6 +89,30 @@ int tt_to_decibels(const float* magnitude, int batch, int64_t per_item, int resc
                    float* item_max, void* stream);
 
 /*
+ * ---- conv autoencoder (modules.py:396-777), bf16 tensor-core implicit GEMMs --------------------------------
+ * Activations: "C8 planar" bf16  [B][ceil(C/8)][H][T][8]  (channel counts below are the PADDED counts, multiples of 8).
+ * Weights: pre-packed bf16 in the tcgen05 B-operand layout [K/8][N][8]; K order and zero padding are documented at
+ * timbre_trap_b200/framework/packing.py (one function per entry point).  Biases: fp32, padded to N.
+ */
+
+/* ResidualConv2dBlock.forward (modules.py:743-777), fused: y = x + ELU(W2 * ELU(W1 (*)_dilation x + b1) + b2) */
+int tt_res_block(const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
+                 int B, int C, int H, int T, int dilation, void* stream);
+/* EncoderBlock.sconv + ELU (modules.py:626-629): Conv2d(Cin, Cout, (4,1), stride (2,1)); Hout = (Hin-4)/2 + 1 */
+int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int T, void* stream);
+/* DecoderBlock.tconv + ELU (modules.py:685-688): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding); Hout = 2 Hin + 2 + out_pad */
+int tt_conv_up(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int out_pad, int T, void* stream);
+/* Encoder.convlat (modules.py:446,478): Conv2d(C4, latent, (H4,1)), no activation; lat is C8 planar with H = 1 */
+int tt_conv_lat(const void* x, void* lat, const void* w, const float* bias, int B, int C4, int H4, int NL, int T, void* stream);
+/* Decoder.convin + ELU (modules.py:533-536) with TimbreTrap.decode's indicator channel (modules.py:139-142) folded into
+ * the per-row bias table bias[H0][C0] (one table per switch setting) */
+int tt_deconv_in(const void* lat, void* y, const void* w, const float* bias, int B, int Clat, int C0, int H0, int T, void* stream);
+/* Encoder.convin + ELU (modules.py:430-433): fp32 interleaved coefficients (B,F,T,2) -> C8 planar; w fp32 [C0][2][3][3] */
+int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, int B, int C0, int H, int T, void* stream);
+/* Decoder.convout (modules.py:543): C8 planar -> fp32 interleaved coefficients (B,F,T,2); w fp32 [2][C][3][3] */
+int tt_conv_out(const void* x, float* coeffs, const float* w, const float* bias, int B, int C, int H, int T, void* stream);
+
+/*
  * Self-test of the tcgen05 / TMEM plumbing the conv kernels are built on (no reference counterpart):
  * D (128 x n, fp32) = A (128 x k, bf16, row-major) * B (n x k, bf16, row-major)^T on one CTA.
  * swap_lbo_sbo = 1 encodes the shared-memory descriptors with the two stride fields exchanged (must FAIL).

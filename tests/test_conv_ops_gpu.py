@@ -1,0 +1,105 @@
+"""
+GPU parity of every conv entry point of the C ABI against torch fp32 convs of the same bf16-rounded inputs and
+weights (the kernels compute bf16 x bf16 -> fp32 and round activations to bf16 between layers; tolerance is the
+bf16 output rounding, 2^-8 relative, plus fp32 accumulation noise).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _assert_close(got, want, tol=1.2e-2):
+    err = float((got - want).abs().max())
+    ref = float(want.abs().max())
+    assert err <= tol * ref, (err, ref)
+
+
+@pytest.mark.parametrize('C,H,T,d,B', [(4, 37, 256, 1, 2), (8, 30, 128, 2, 1), (8, 19, 384, 3, 2), (16, 33, 256, 1, 2),
+                                         (16, 21, 128, 3, 1), (32, 65, 256, 2, 1), (32, 17, 128, 3, 2), (2, 20, 200, 1, 1)])
+def test_res_block(C, H, T, d, B):
+    from timbre_trap_b200.framework import ops, packing as P
+    x = _bf(_rand((B, C, H, T), 1))
+    w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
+    w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
+    mid = _bf(F.elu(F.conv2d(x, w1, b1, padding=d, dilation=d)))
+    want = x + F.elu(F.conv2d(mid, w2, b2))
+    n = max(16, P.pad8(C))
+    y = ops.res_block(P.to_c8(x.cuda()), P.pack_res3x3(w1.cuda()), P.pad_vec(b1.cuda(), n), P.pack_res1x1(w2.cuda()),
+                      P.pad_vec(b2.cuda(), n), d)
+    got = P.from_c8(y, C).cpu()
+    _assert_close(got, want)
+    if P.pad8(C) != C:   # padded channels stay exactly zero
+        assert float(y.float().permute(0, 1, 4, 2, 3).reshape(B, -1, H, T)[:, C:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('Cin,Cout,H,T,B', [(4, 8, 40, 256, 2), (8, 16, 27, 128, 1), (16, 32, 33, 256, 2), (32, 64, 65, 128, 1),
+                                              (2, 4, 20, 100, 1)])
+def test_conv_down(Cin, Cout, H, T, B):
+    from timbre_trap_b200.framework import ops, packing as P
+    x = _bf(_rand((B, Cin, H, T), 11))
+    w, b = _bf(_rand((Cout, Cin, 4, 1), 12, 0.3)), _rand((Cout,), 13, 0.3)
+    want = F.elu(F.conv2d(x, w, b, stride=(2, 1)))
+    n = max(16, P.pad8(Cout))
+    y = ops.conv_down(P.to_c8(x.cuda()), P.pack_down(w.cuda()), P.pad_vec(b.cuda(), n), P.pad8(Cout))
+    assert y.shape[2] == want.shape[2]
+    _assert_close(P.from_c8(y, Cout).cpu(), want)
+
+
+@pytest.mark.parametrize('Cin,Cout,H,T,op,B', [(64, 32, 31, 128, 1, 2), (32, 16, 65, 256, 1, 1), (16, 8, 33, 128, 1, 2),
+                                                 (8, 4, 29, 256, 0, 1), (4, 2, 9, 100, 1, 1), (16, 8, 5, 128, 0, 1)])
+def test_conv_up(Cin, Cout, H, T, op, B):
+    from timbre_trap_b200.framework import ops, packing as P
+    x = _bf(_rand((B, Cin, H, T), 21))
+    w, b = _bf(_rand((Cin, Cout, 4, 1), 22, 0.3)), _rand((Cout,), 23, 0.3)
+    want = F.elu(F.conv_transpose2d(x, w, b, stride=(2, 1), output_padding=(op, 0)))
+    y = ops.conv_up(P.to_c8(x.cuda()), P.pack_up(w.cuda()), P.pack_up_bias(b.cuda(), Cout), P.pad8(Cout), op)
+    assert y.shape[2] == want.shape[2]
+    _assert_close(P.from_c8(y, Cout).cpu(), want)
+
+
+@pytest.mark.parametrize('C4,H4,D,T,B', [(64, 31, 128, 256, 2), (32, 2, 32, 128, 1), (64, 2, 24, 100, 2)])
+def test_conv_lat_and_deconv_in(C4, H4, D, T, B):
+    from timbre_trap_b200.framework import ops, packing as P
+    Dp = (D + 15) // 16 * 16
+    x = _bf(_rand((B, C4, H4, T), 31))
+    w, b = _bf(_rand((D, C4, H4, 1), 32, 0.05)), _rand((D,), 33, 0.3)
+    want = F.conv2d(x, w, b)
+    lat = ops.conv_lat(P.to_c8(x.cuda()), P.pack_lat(w.cuda(), Dp), P.pad_vec(b.cuda(), Dp), Dp)
+    _assert_close(P.from_c8(lat, D).cpu(), want)
+    # decoder side
+    wd, bd = _bf(_rand((D + 1, C4, H4, 1), 34, 0.1)), _rand((C4,), 35, 0.3)
+    lat_in = _bf(_rand((B, D, 1, T), 36))
+    packed, tables = P.pack_deconv_in(wd.cuda(), bd.cuda(), Dp)
+    for mode, flag in ((0, 0.0), (1, 1.0)):
+        full = torch.cat((lat_in, torch.full((B, 1, 1, T), flag)), dim=1)
+        wantd = F.elu(F.conv_transpose2d(full, wd, bd))
+        y = ops.deconv_in(P.to_c8(lat_in.cuda()) if Dp == P.pad8(D) else P.to_c8(F.pad(lat_in, (0, 0, 0, 0, 0, Dp - D)).cuda()),
+                          packed, tables[mode].contiguous(), P.pad8(C4), H4)
+        _assert_close(P.from_c8(y, C4).cpu(), wantd)
+
+
+@pytest.mark.parametrize('C0,H,T,B', [(4, 60, 300, 2), (2, 33, 128, 1), (8, 17, 64, 1)])
+def test_conv_in_out(C0, H, T, B):
+    from timbre_trap_b200.framework import ops, packing as P
+    x = _rand((B, 2, H, T), 41)
+    w, b = _rand((C0, 2, 3, 3), 42, 0.4), _rand((C0,), 43, 0.3)
+    want = F.elu(F.conv2d(x, w, b, padding=1))
+    y = ops.conv_in(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda().contiguous(), b.cuda(), C0)
+    _assert_close(P.from_c8(y, C0).cpu(), want)
+    xo = _bf(_rand((B, C0, H, T), 44))
+    wo, bo = _rand((2, C0, 3, 3), 45, 0.4), _rand((2,), 46, 0.3)
+    wanto = F.conv2d(xo, wo, bo, padding=1)
+    yo = ops.conv_out(P.to_c8(xo.cuda()), wo.cuda().contiguous(), bo.cuda(), C0)
+    _assert_close(yo.permute(0, 3, 1, 2).cpu(), wanto, tol=1e-5)

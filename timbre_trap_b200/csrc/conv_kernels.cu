@@ -1,0 +1,677 @@
+// Encoder / decoder convolutions of Timbre-Trap (reference: timbre_trap/framework/modules.py:396-777) as bf16
+// implicit GEMMs on the sm_100a tensor cores (tcgen05.mma, fp32 accumulators in TMEM).
+//
+// Activation layout ("C8 planar"):  [B][CG][H][T][8] bf16, CG = ceil(C / 8); the 8 channels of one pixel are 16
+// contiguous bytes and T is the contiguous pixel axis.  A run of 8 consecutive pixels of one channel group is therefore
+// exactly one UMMA core matrix (8 rows x 16 B, SWIZZLE_NONE, K-major), 128 consecutive pixels are the M = 128 rows of
+// one MMA (SBO = 128 B), and a convolution tap is nothing but a different start address into the same shared-memory
+// tile: the im2col matrix is never materialised.  Two core matrices along K (one MMA, K = 16) are either two channel
+// groups of one tap (LBO = plane stride) or, for 8-channel layers, two taps (LBO = their address difference).
+//
+// conv_rows_kernel is the one generic kernel: a CTA owns R "row groups" x 128 pixels; for every row group it issues a
+// list of MMAs (tap table from the host) into its own TMEM columns, then an epilogue (bias, ELU, bf16 pack, coalesced
+// 16 B stores).  Optionally a second GEMM stage (the 1x1 conv of a residual block) runs on the bf16 result of the first,
+// staged through shared memory, with the residual add fused in its epilogue.
+//
+//   layer (modules.py)                       row group      MMAs / group            N
+//   ResidualConv2dBlock :721-777 (fused)     1 output row   9*C/16 (+1 if C = 8)    C     then 1x1: C/16 (1 if C = 8)
+//   EncoderBlock.sconv  :626-629             1 output row   4*Cin/16                Cout
+//   DecoderBlock.tconv  :685-688             2 output rows  2*Cin/16                2*Cout   (polyphase: rows 2q, 2q+1)
+//   Decoder.convin      :533-536             1 output row   latent/16               C0       (weights depend on the row)
+//
+// Weights arrive pre-packed in the B-operand canonical layout [K/8][N][8] bf16 (timbre_trap_b200/framework/packing.py).
+
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/timbre_trap_b200.h"
+#include "tt_common.cuh"
+#include "umma.cuh"
+
+namespace tt {
+
+constexpr int kMaxTaps = 40;
+constexpr int kMaxRows = 16;
+constexpr int kTileT = 128;
+constexpr int kHeaderBytes = 2048;
+
+struct ConvRowsParams {
+    const __nv_bfloat16* x;
+    __nv_bfloat16* y;
+    const __nv_bfloat16* w1;
+    const float* b1;
+    const __nv_bfloat16* w2;
+    const float* b2;
+    int B, CGin, Hin, T, CGout, Hout;
+    int groups;            // row groups in total (Hout, or ceil(Hout/2) for out_mode 1)
+    int R;                 // row groups per CTA (<= kMaxRows)
+    int sh;                // input rows advanced per row group
+    int row_lo;            // input row held by tile row 0 = g0 * sh + row_lo
+    int in_rows;           // tile rows
+    int padT;              // T halo on each side
+    int n_mma1, kg1;       // stage-1 MMAs per group, K groups of 8 in the packed weights
+    int n_mma2, kg2;       // stage 2 (1x1): MMAs per group, K groups in the packed weights
+    int mid_planes;        // channel-group planes of the staged intermediate (1 when C = 8: its pair partner is the next row)
+    int out_mode;          // 0: N channels -> one output row;  1: two output rows of N/2 channels
+    int act;               // ELU on the final output
+    int two_stage;
+    int res_off;           // byte offset of the residual pixel 0 (plane 0) from the group's tile base
+    int w_group_stride;    // bytes between the packed weights of consecutive row groups (0: shared)
+    int b_group_stride;    // floats between the biases of consecutive row groups (0: shared)
+    uint32_t tap_off[kMaxTaps];
+    uint32_t tap_lbo[kMaxTaps];
+};
+
+__device__ __forceinline__ float elu(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+
+__device__ __forceinline__ uint4 pack8(const float* v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
+    __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(v[4], v[5]);
+    __nv_bfloat162 d = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    r.z = *reinterpret_cast<uint32_t*>(&c);
+    r.w = *reinterpret_cast<uint32_t*>(&d);
+    return r;
+}
+
+__device__ __forceinline__ void unpack8(uint4 r, float* v) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 f = __bfloat1622float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+
+template <int N1, int N2>
+__global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ ConvRowsParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int NC = N1 > N2 ? N1 : N2;           // TMEM columns per row group
+    uint64_t* bar1 = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* bar2 = bar1 + kMaxRows;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
+    float* sB1 = reinterpret_cast<float*>(smem + 512);
+    float* sB2 = reinterpret_cast<float*>(smem + 1280);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * kTileT;
+    const int g0 = blockIdx.y * p.R;
+    const int b = blockIdx.z;
+    const int rows = min(p.R, p.groups - g0);
+    const int wrows = p.w_group_stride ? p.R : 1;
+
+    const int TW = kTileT + 2 * p.padT;
+    const uint32_t row_bytes = (uint32_t)TW * 16u;
+    const uint32_t plane_bytes = (uint32_t)p.in_rows * row_bytes;
+    const uint32_t w1_bytes = (uint32_t)p.kg1 * N1 * 16u;
+    const uint32_t w2_bytes = p.two_stage ? (uint32_t)p.kg2 * N2 * 16u : 0u;
+    const uint32_t mid_plane = (uint32_t)(p.R + 1) * 2048u;
+    uint8_t* sW1 = smem + kHeaderBytes;
+    uint8_t* sW2 = sW1 + (size_t)w1_bytes * wrows;
+    uint8_t* sIn = sW2 + w2_bytes;
+    uint8_t* sMid = sIn + (size_t)p.CGin * plane_bytes + 256;
+
+    // ---- setup --------------------------------------------------------------------------------------
+    uint32_t ncols = 32;
+    while (ncols < (uint32_t)(p.R * NC)) ncols <<= 1;
+    if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
+    if (tid == 0) {
+        for (int i = 0; i < kMaxRows; ++i) {
+            umma::mbar_init(&bar1[i], 1);
+            umma::mbar_init(&bar2[i], 1);
+        }
+        umma::mbar_fence_init();
+    }
+    // weights and biases
+    for (int r = 0; r < wrows; ++r) {
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w1) +
+                                                          (size_t)(g0 + r) * p.w_group_stride);
+        if (r < rows)
+            for (int i = tid; i < (int)(w1_bytes / 16); i += 128)
+                reinterpret_cast<uint4*>(sW1 + (size_t)r * w1_bytes)[i] = __ldg(src + i);
+    }
+    if (p.two_stage)
+        for (int i = tid; i < (int)(w2_bytes / 16); i += 128)
+            reinterpret_cast<uint4*>(sW2)[i] = __ldg(reinterpret_cast<const uint4*>(p.w2) + i);
+    if (p.b_group_stride == 0 && tid < N1) sB1[tid] = p.b1[tid];
+    if (N2 > 0 && p.two_stage && tid < N2) sB2[tid] = p.b2[tid];
+
+    // input tile, zero-filled outside the image ('same' padding, transposed-conv borders)
+    {
+        const int h_base = g0 * p.sh + p.row_lo;
+        const int n_rows_all = p.CGin * p.in_rows;
+        for (int rr = warp; rr < n_rows_all; rr += 4) {
+            const int cg = rr / p.in_rows, r = rr - cg * p.in_rows;
+            const int hi = h_base + r;
+            const bool row_ok = hi >= 0 && hi < p.Hin;
+            const uint4* src = reinterpret_cast<const uint4*>(p.x) + (((size_t)b * p.CGin + cg) * p.Hin + (row_ok ? hi : 0)) * p.T;
+            uint4* dst = reinterpret_cast<uint4*>(sIn + (size_t)cg * plane_bytes + (size_t)r * row_bytes);
+            for (int c = lane; c < TW; c += 32) {
+                const int t = t0 - p.padT + c;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (row_ok && t >= 0 && t < p.T) v = __ldg(src + t);
+                dst[c] = v;
+            }
+        }
+        if (tid < 16) reinterpret_cast<uint4*>(sIn + (size_t)p.CGin * plane_bytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
+        if (p.two_stage) {
+            // the spare row after each mid plane is read (times zero weights) when C = 8 pairs a row with its successor
+            const int planes = p.mid_planes;
+            for (int i = tid; i < planes * 128; i += 128)
+                reinterpret_cast<uint4*>(sMid + (size_t)(i / 128) * mid_plane + (size_t)p.R * 2048u)[i % 128] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    // ---- stage 1: all MMAs of all row groups, one commit per group -------------------------------------
+    if (tid == 0) {
+        const uint32_t idesc = umma::make_idesc_bf16(128, N1);
+        const uint32_t in0 = umma::smem_u32(sIn), w0 = umma::smem_u32(sW1);
+        for (int i = 0; i < rows; ++i) {
+            const uint32_t base = in0 + (uint32_t)(i * p.sh) * row_bytes;
+            const uint32_t wb = w0 + (p.w_group_stride ? (uint32_t)i * w1_bytes : 0u);
+            for (int m = 0; m < p.n_mma1; ++m) {
+                const uint64_t da = umma::make_desc(base + p.tap_off[m], p.tap_lbo[m], 128u);
+                const uint64_t db = umma::make_desc(wb + (uint32_t)m * 2u * N1 * 16u, N1 * 16u, 128u);
+                umma::mma_bf16(tmem + (uint32_t)(i * NC), da, db, idesc, m > 0);
+            }
+            umma::commit(&bar1[i]);
+        }
+    }
+
+    const int j = warp * 32 + lane;                 // pixel within the tile = TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const bool t_ok = t0 + j < p.T;
+
+    // ---- epilogue 1 ------------------------------------------------------------------------------------
+    for (int i = 0; i < rows; ++i) {
+        umma::mbar_wait(&bar1[i], 0);
+        umma::fence_after_sync();
+        const float* bias = p.b_group_stride ? p.b1 + (size_t)(g0 + i) * p.b_group_stride : sB1;
+#pragma unroll
+        for (int c0 = 0; c0 < N1; c0 += 16) {
+            float v[16];
+            umma::tmem_ld16(lane_addr + (uint32_t)(i * NC + c0), v);
+            umma::tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) v[k] += bias[c0 + k];
+            if (p.two_stage) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = elu(v[k]);
+                uint8_t* dst = sMid + (size_t)(c0 / 8) * mid_plane + (size_t)i * 2048u + (size_t)j * 16u;
+                *reinterpret_cast<uint4*>(dst) = pack8(v);
+                if (c0 / 8 + 1 < p.mid_planes) *reinterpret_cast<uint4*>(dst + mid_plane) = pack8(v + 8);
+            } else {
+                if (p.act) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = elu(v[k]);
+                }
+                if (t_ok) {
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int c = c0 + 8 * hh;          // first of 8 channels
+                        int ho, cg;
+                        if (p.out_mode == 0) { ho = g0 + i; cg = c >> 3; }
+                        else { ho = 2 * (g0 + i) + (c >= N1 / 2 ? 1 : 0); cg = (c % (N1 / 2)) >> 3; }
+                        if (cg < p.CGout && ho < p.Hout)
+                            reinterpret_cast<uint4*>(p.y)[(((size_t)b * p.CGout + cg) * p.Hout + ho) * p.T + t0 + j] = pack8(v + 8 * hh);
+                    }
+                }
+            }
+        }
+    }
+
+    // ---- stage 2: 1x1 conv on the staged bf16 activations + residual ------------------------------------
+    if constexpr (N2 > 0) {
+        if (p.two_stage) {
+            umma::fence_proxy_async();
+            umma::fence_before_sync();
+            __syncthreads();
+            umma::fence_after_sync();
+            if (tid == 0) {
+                const uint32_t idesc = umma::make_idesc_bf16(128, N2);
+                const uint32_t m0 = umma::smem_u32(sMid), w0 = umma::smem_u32(sW2);
+                const uint32_t lbo = p.mid_planes < 2 ? 2048u : mid_plane;
+                for (int i = 0; i < rows; ++i) {
+                    for (int m = 0; m < p.n_mma2; ++m) {
+                        const uint64_t da = umma::make_desc(m0 + (uint32_t)i * 2048u + (uint32_t)m * 2u * mid_plane, lbo, 128u);
+                        const uint64_t db = umma::make_desc(w0 + (uint32_t)m * 2u * N2 * 16u, N2 * 16u, 128u);
+                        umma::mma_bf16(tmem + (uint32_t)(i * NC), da, db, idesc, m > 0);
+                    }
+                    umma::commit(&bar2[i]);
+                }
+            }
+            for (int i = 0; i < rows; ++i) {
+                umma::mbar_wait(&bar2[i], 0);
+                umma::fence_after_sync();
+                const uint8_t* res = sIn + (size_t)(i * p.sh) * row_bytes + p.res_off + (size_t)j * 16u;
+#pragma unroll
+                for (int c0 = 0; c0 < N2; c0 += 16) {
+                    float v[16];
+                    umma::tmem_ld16(lane_addr + (uint32_t)(i * NC + c0), v);
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int cg = (c0 >> 3) + hh;
+                        if (cg >= p.CGout) continue;
+                        float r[8];
+                        unpack8(*reinterpret_cast<const uint4*>(res + (size_t)cg * plane_bytes), r);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) r[k] += elu(v[8 * hh + k] + sB2[c0 + 8 * hh + k]);
+                        if (t_ok)
+                            reinterpret_cast<uint4*>(p.y)[(((size_t)b * p.CGout + cg) * p.Hout + g0 + i) * p.T + t0 + j] = pack8(r);
+                    }
+                }
+            }
+        }
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+static size_t conv_rows_smem(const ConvRowsParams& p, int n1, int n2) {
+    const size_t TW = kTileT + 2 * p.padT;
+    const size_t plane = (size_t)p.in_rows * TW * 16;
+    size_t s = kHeaderBytes + (size_t)p.kg1 * n1 * 16 * (p.w_group_stride ? p.R : 1);
+    if (p.two_stage) s += (size_t)p.kg2 * n2 * 16;
+    s += (size_t)p.CGin * plane + 256;
+    if (p.two_stage) s += (size_t)p.mid_planes * (p.R + 1) * 2048;
+    return s;
+}
+
+template <int N1, int N2>
+static int launch_conv_rows(const ConvRowsParams& p, cudaStream_t stream) {
+    const size_t smem = conv_rows_smem(p, N1, N2);
+    TT_REQUIRE(smem <= 227 * 1024, "conv tile needs %zu bytes of shared memory", smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+        TT_CUDA_CHECK(cudaFuncSetAttribute(conv_rows_kernel<N1, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    dim3 grid((p.T + kTileT - 1) / kTileT, (p.groups + p.R - 1) / p.R, p.B);
+    conv_rows_kernel<N1, N2><<<grid, 128, smem, stream>>>(p);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
+static int env_int(const char* name, int fallback) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : fallback;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+static void fill_common(ConvRowsParams& p, const void* x, void* y, const void* w1, const float* b1, int B, int CGin, int Hin,
+                        int T, int CGout, int Hout) {
+    memset(&p, 0, sizeof(p));
+    p.x = (const __nv_bfloat16*)x; p.y = (__nv_bfloat16*)y;
+    p.w1 = (const __nv_bfloat16*)w1; p.b1 = b1;
+    p.B = B; p.CGin = CGin; p.Hin = Hin; p.T = T; p.CGout = CGout; p.Hout = Hout;
+}
+
+template <int N2>
+static int dispatch_n1(const ConvRowsParams& p, int n1, cudaStream_t s) {
+    switch (n1) {
+        case 16: return launch_conv_rows<16, N2>(p, s);
+        case 32: return launch_conv_rows<32, N2>(p, s);
+        case 64: return launch_conv_rows<64, N2>(p, s);
+        case 128: return launch_conv_rows<128, N2>(p, s);
+        default: tt_set_error("unsupported GEMM N = %d", n1); return TT_ERR_UNSUPPORTED;
+    }
+}
+
+extern "C" int tt_res_block(const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
+                            int B, int C, int H, int T, int dilation, void* stream) {
+    TT_REQUIRE(x && y && w1 && b1 && w2 && b2, "null argument");
+    TT_REQUIRE(C == 8 || C == 16 || C == 32, "res block: padded channel count must be 8, 16 or 32 (got %d)", C);
+    TT_REQUIRE(dilation >= 1 && dilation <= 4, "dilation must be in [1,4]");
+    if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
+    ConvRowsParams p;
+    const int d = dilation, CG = C / 8;
+    fill_common(p, x, y, w1, b1, B, CG, H, T, CG, H);
+    p.w2 = (const __nv_bfloat16*)w2; p.b2 = b2;
+    p.groups = H;
+    p.R = std::min(env_int("TT_RES_ROWS", C == 8 ? 16 : (C == 16 ? 8 : 4)), kMaxRows);
+    p.sh = 1; p.row_lo = -d; p.in_rows = p.R + 2 * d; p.padT = d;
+    p.out_mode = 0; p.act = 1; p.two_stage = 1;
+    const uint32_t TW = kTileT + 2 * d, row_bytes = TW * 16, plane = (uint32_t)p.in_rows * row_bytes;
+    auto tap_addr = [&](int tap) { return (uint32_t)(((tap / 3) * d) * TW + (tap % 3) * d) * 16u; };
+    p.res_off = (int)tap_addr(4);
+    int m = 0;
+    if (CG == 1) {
+        // K order: tap-major, 8 channels per tap; an MMA pairs two consecutive taps, the 10th K group has zero weights
+        for (int t = 0; t < 10; t += 2) {
+            p.tap_off[m] = tap_addr(t);
+            p.tap_lbo[m] = t + 1 < 9 ? tap_addr(t + 1) - tap_addr(t) : 16u;
+            ++m;
+        }
+        p.kg1 = 10;
+        p.kg2 = 2; p.n_mma2 = 1; p.mid_planes = 1;
+    } else {
+        for (int t = 0; t < 9; ++t)
+            for (int q = 0; q < CG / 2; ++q) {
+                p.tap_off[m] = tap_addr(t) + (uint32_t)(2 * q) * plane;
+                p.tap_lbo[m] = plane;
+                ++m;
+            }
+        p.kg1 = 9 * CG;
+        p.kg2 = CG; p.n_mma2 = CG / 2; p.mid_planes = CG;
+    }
+    p.n_mma1 = m;
+    cudaStream_t s = (cudaStream_t)stream;
+    return C == 32 ? launch_conv_rows<32, 32>(p, s) : launch_conv_rows<16, 16>(p, s);
+}
+
+// EncoderBlock.sconv (+ELU): Conv2d(Cin, Cout, (4,1), stride (2,1)).  K order (kh, channel group).
+extern "C" int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int T,
+                            void* stream) {
+    TT_REQUIRE(x && y && w && bias, "null argument");
+    TT_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin >= 8 && Cin <= 64, "conv_down: padded channels must be multiples of 8");
+    if (B <= 0 || T <= 0) return TT_OK;
+    const int Hout = (Hin - 4) / 2 + 1;
+    TT_REQUIRE(Hout >= 1, "conv_down: input too short");
+    ConvRowsParams p;
+    const int CG = Cin / 8;
+    fill_common(p, x, y, w, bias, B, CG, Hin, T, Cout / 8, Hout);
+    p.groups = Hout;
+    p.R = std::min(env_int("TT_DOWN_ROWS", Cin >= 32 ? 4 : 8), kMaxRows);
+    p.sh = 2; p.row_lo = 0; p.in_rows = (p.R - 1) * 2 + 4; p.padT = 0;
+    p.out_mode = 0; p.act = 1;
+    const uint32_t row_bytes = kTileT * 16, plane = (uint32_t)p.in_rows * row_bytes;
+    int m = 0;
+    if (CG == 1) {
+        for (int kh = 0; kh < 4; kh += 2) { p.tap_off[m] = kh * row_bytes; p.tap_lbo[m] = row_bytes; ++m; }
+    } else {
+        for (int kh = 0; kh < 4; ++kh)
+            for (int q = 0; q < CG / 2; ++q) { p.tap_off[m] = kh * row_bytes + 2 * q * plane; p.tap_lbo[m] = plane; ++m; }
+    }
+    p.n_mma1 = m; p.kg1 = 4 * CG;
+    const int n1 = std::max(16, Cout);
+    return dispatch_n1<0>(p, n1, (cudaStream_t)stream);
+}
+
+// DecoderBlock.tconv (+ELU): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding (op,0)), polyphase:
+//   out[2q + r] = bias + W[.,.,r+2] x[q-1] + W[.,.,r] x[q];  K order (a' in {row q-1, row q}, channel group), N = (r, co).
+extern "C" int tt_conv_up(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin,
+                          int out_pad, int T, void* stream) {
+    TT_REQUIRE(x && y && w && bias, "null argument");
+    TT_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin >= 8 && Cin <= 64, "conv_up: padded channels must be multiples of 8");
+    if (B <= 0 || T <= 0 || Hin <= 0) return TT_OK;
+    const int Hout = 2 * Hin + 2 + out_pad;
+    ConvRowsParams p;
+    const int CG = Cin / 8;
+    fill_common(p, x, y, w, bias, B, CG, Hin, T, Cout / 8, Hout);
+    p.groups = (Hout + 1) / 2;
+    p.R = std::min(env_int("TT_UP_ROWS", Cin >= 64 ? 4 : 8), kMaxRows);
+    p.sh = 1; p.row_lo = -1; p.in_rows = p.R + 1; p.padT = 0;
+    p.out_mode = 1; p.act = 1;
+    const uint32_t row_bytes = kTileT * 16, plane = (uint32_t)p.in_rows * row_bytes;
+    int m = 0;
+    if (CG == 1) {
+        p.tap_off[m] = 0; p.tap_lbo[m] = row_bytes; ++m;
+    } else {
+        for (int a = 0; a < 2; ++a)
+            for (int q = 0; q < CG / 2; ++q) { p.tap_off[m] = a * row_bytes + 2 * q * plane; p.tap_lbo[m] = plane; ++m; }
+    }
+    p.n_mma1 = m; p.kg1 = 2 * CG;
+    const int n1 = std::max(16, 2 * Cout);
+    return dispatch_n1<0>(p, n1, (cudaStream_t)stream);
+}
+
+// Decoder.convin (+ELU): ConvTranspose2d(latent+1, C0, (H0,1)) on a height-1 input = one GEMM per output row h with
+// its own weight slice W[:, :, h]; the indicator channel (modules.py:139-142) is folded into a per-row bias table.
+//   lat (B, Clat/8, 1, T, 8) -> y (B, C0/8, H0, T, 8);  w packed [H0][Clat/8][C0][8];  bias [H0][C0]
+extern "C" int tt_deconv_in(const void* lat, void* y, const void* w, const float* bias, int B, int Clat, int C0, int H0, int T,
+                            void* stream) {
+    TT_REQUIRE(lat && y && w && bias, "null argument");
+    TT_REQUIRE(Clat % 16 == 0 && Clat <= 256 && (C0 == 16 || C0 == 32 || C0 == 64 || C0 == 128), "deconv_in: unsupported sizes");
+    if (B <= 0 || T <= 0) return TT_OK;
+    ConvRowsParams p;
+    const int CG = Clat / 8;
+    fill_common(p, lat, y, w, bias, B, CG, 1, T, C0 / 8, H0);
+    p.groups = H0;
+    p.R = std::min(env_int("TT_DECIN_ROWS", 4), kMaxRows);
+    p.sh = 0; p.row_lo = 0; p.in_rows = 1; p.padT = 0;
+    p.out_mode = 0; p.act = 1;
+    const uint32_t plane = kTileT * 16;
+    int m = 0;
+    for (int q = 0; q < CG / 2; ++q) { p.tap_off[m] = 2 * q * plane; p.tap_lbo[m] = plane; ++m; }
+    p.n_mma1 = m; p.kg1 = CG;
+    p.w_group_stride = CG * C0 * 16;
+    p.b_group_stride = C0;
+    return dispatch_n1<0>(p, C0, (cudaStream_t)stream);
+}
+
+// =========================================================================================================
+// Encoder.convlat (modules.py:446,478): Conv2d(C4, latent, (H4,1)) over the full height -> one GEMM over T with
+// K = H4 * C4 streamed through a two-stage shared-memory ring (A = input row kh, B = weight slice kh).
+//   x (B, C4/8, H4, T, 8) -> lat (B, NL/8, 1, T, 8);  w packed [H4 * C4/8][NL][8];  no activation
+// =========================================================================================================
+namespace tt {
+
+template <int NL>
+__global__ void __launch_bounds__(128) conv_lat_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ lat,
+                                                       const __nv_bfloat16* __restrict__ w, const float* __restrict__ bias,
+                                                       int CG, int H, int T) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bar_free = reinterpret_cast<uint64_t*>(smem);          // [2] stage consumed by the tensor core
+    uint64_t* bar_done = bar_free + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 64);
+    float* sBias = reinterpret_cast<float*>(smem + 128);
+    const uint32_t a_bytes = (uint32_t)CG * kTileT * 16u, b_bytes = (uint32_t)CG * NL * 16u;
+    uint8_t* stage0 = smem + 1024;
+    const uint32_t stage_bytes = a_bytes + b_bytes;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * kTileT, b = blockIdx.y;
+    constexpr uint32_t ncols = NL < 32 ? 32 : NL;
+    if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
+    if (tid == 0) {
+        umma::mbar_init(&bar_free[0], 1);
+        umma::mbar_init(&bar_free[1], 1);
+        umma::mbar_init(bar_done, 1);
+        umma::mbar_fence_init();
+    }
+    for (int i = tid; i < NL; i += 128) sBias[i] = bias[i];
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t idesc = umma::make_idesc_bf16(128, NL);
+
+    for (int kh = 0; kh < H; ++kh) {
+        const int s = kh & 1;
+        uint8_t* sA = stage0 + (size_t)s * stage_bytes;
+        uint8_t* sB = sA + a_bytes;
+        if (kh >= 2) {
+            umma::mbar_wait(&bar_free[s], (uint32_t)(((kh >> 1) - 1) & 1));
+            umma::fence_after_sync();
+        }
+        for (int i = tid; i < CG * kTileT; i += 128) {
+            const int cg = i / kTileT, c = i - cg * kTileT;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (t0 + c < T) v = __ldg(reinterpret_cast<const uint4*>(x) + (((size_t)b * CG + cg) * H + kh) * T + t0 + c);
+            reinterpret_cast<uint4*>(sA)[i] = v;
+        }
+        const uint4* wsrc = reinterpret_cast<const uint4*>(w) + (size_t)kh * CG * NL;
+        for (int i = tid; i < CG * NL; i += 128) reinterpret_cast<uint4*>(sB)[i] = __ldg(wsrc + i);
+        umma::fence_proxy_async();
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+        if (tid == 0) {
+            const uint32_t a0 = umma::smem_u32(sA), b0 = umma::smem_u32(sB);
+            for (int m = 0; m < CG / 2; ++m) {
+                const uint64_t da = umma::make_desc(a0 + (uint32_t)m * 2u * kTileT * 16u, kTileT * 16u, 128u);
+                const uint64_t db = umma::make_desc(b0 + (uint32_t)m * 2u * NL * 16u, NL * 16u, 128u);
+                umma::mma_bf16(tmem, da, db, idesc, kh > 0 || m > 0);
+            }
+            umma::commit(&bar_free[s]);
+            if (kh == H - 1) umma::commit(bar_done);
+        }
+    }
+    umma::mbar_wait(bar_done, 0);
+    umma::fence_after_sync();
+    const int j = warp * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int c0 = 0; c0 < NL; c0 += 16) {
+        float v[16];
+        umma::tmem_ld16(lane_addr + (uint32_t)c0, v);
+        umma::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] += sBias[c0 + k];
+        if (t0 + j < T) {
+            reinterpret_cast<uint4*>(lat)[((size_t)b * (NL / 8) + (c0 >> 3)) * T + t0 + j] = pack8(v);
+            reinterpret_cast<uint4*>(lat)[((size_t)b * (NL / 8) + (c0 >> 3) + 1) * T + t0 + j] = pack8(v + 8);
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+// =========================================================================================================
+// Encoder.convin (modules.py:430-433): Conv2d(2, C0, 3, 'same') + ELU, reading the CQT's fp32 interleaved
+// (B, F, T, 2) buffer directly and writing C8 planar bf16.  K = 18: CUDA cores, one thread per pixel.
+// Decoder.convout (modules.py:543): Conv2d(C, 2, 3, 'same'), C8 planar bf16 -> fp32 interleaved (B, F, T, 2),
+// optionally scaled by a per-frame window and accumulated (chunk cross-fade of modules.py:259-263).
+// =========================================================================================================
+__global__ void __launch_bounds__(256) conv_in_kernel(const float2* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                      const float* __restrict__ w /* [C0][2][3][3] */,
+                                                      const float* __restrict__ bias, int C0, int H, int T) {
+    __shared__ float sw[8 * 18 + 8];
+    for (int i = threadIdx.x; i < 8 * 18 + 8; i += 256) {
+        float v = 0.f;
+        if (i < 8 * 18) { if (i < C0 * 18) v = w[i]; }
+        else if (i - 8 * 18 < C0) v = bias[i - 8 * 18];
+        sw[i] = v;
+    }
+    __syncthreads();
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int h = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    float acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = sw[8 * 18 + c];
+    const float2* xb = x + (size_t)b * H * T;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int hh = h + ky - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int tt_ = t + kx - 1;
+            if (tt_ < 0 || tt_ >= T) continue;
+            const float2 v = __ldg(xb + (size_t)hh * T + tt_);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                acc[c] = fmaf(sw[c * 18 + ky * 3 + kx], v.x, acc[c]);
+                acc[c] = fmaf(sw[c * 18 + 9 + ky * 3 + kx], v.y, acc[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[c] = c < C0 ? elu(acc[c]) : 0.f;
+    reinterpret_cast<uint4*>(y)[((size_t)b * H + h) * T + t] = pack8(acc);
+}
+
+__global__ void __launch_bounds__(256) conv_out_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ y,
+                                                       const float* __restrict__ w /* [2][C][3][3] */,
+                                                       const float* __restrict__ bias, int C, int H, int T) {
+    __shared__ float sw[2 * 8 * 9 + 2];
+    for (int i = threadIdx.x; i < 2 * 8 * 9 + 2; i += 256) {
+        float v = 0.f;
+        if (i < 144) {
+            const int o = i / 72, c = (i % 72) / 9, k = i % 9;
+            if (c < C) v = w[(o * C + c) * 9 + k];
+        } else v = bias[i - 144];
+        sw[i] = v;
+    }
+    __syncthreads();
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int h = blockIdx.y, b = blockIdx.z;
+    if (t >= T) return;
+    float a0 = sw[144], a1 = sw[145];
+    const uint4* xb = reinterpret_cast<const uint4*>(x) + (size_t)b * H * T;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int hh = h + ky - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            const int tt_ = t + kx - 1;
+            if (tt_ < 0 || tt_ >= T) continue;
+            float v[8];
+            unpack8(__ldg(xb + (size_t)hh * T + tt_), v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                a0 = fmaf(sw[c * 9 + ky * 3 + kx], v[c], a0);
+                a1 = fmaf(sw[72 + c * 9 + ky * 3 + kx], v[c], a1);
+            }
+        }
+    }
+    y[((size_t)b * H + h) * T + t] = make_float2(a0, a1);
+}
+
+}  // namespace tt
+
+extern "C" int tt_conv_lat(const void* x, void* lat, const void* w, const float* bias, int B, int C4, int H4, int NL, int T,
+                           void* stream) {
+    TT_REQUIRE(x && lat && w && bias, "null argument");
+    TT_REQUIRE(C4 % 16 == 0 && C4 <= 128, "conv_lat: input channels must be a multiple of 16 (<= 128), got %d", C4);
+    if (B <= 0 || T <= 0) return TT_OK;
+    const int CG = C4 / 8;
+    dim3 grid((T + kTileT - 1) / kTileT, B);
+    const size_t smem = 1024 + 2 * ((size_t)CG * kTileT * 16 + (size_t)CG * NL * 16);
+    cudaStream_t s = (cudaStream_t)stream;
+#define TT_LAT_CASE(N)                                                                                               \
+    case N:                                                                                                          \
+        TT_CUDA_CHECK(cudaFuncSetAttribute(conv_lat_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        conv_lat_kernel<N><<<grid, 128, smem, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)lat, (const __nv_bfloat16*)w, bias, CG, H4, T); \
+        break;
+    switch (NL) {
+        TT_LAT_CASE(16) TT_LAT_CASE(32) TT_LAT_CASE(64) TT_LAT_CASE(128) TT_LAT_CASE(256)
+        default: tt_set_error("conv_lat: padded latent size must be 16, 32, 64, 128 or 256 (got %d)", NL); return TT_ERR_UNSUPPORTED;
+    }
+#undef TT_LAT_CASE
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
+extern "C" int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, int B, int C0, int H, int T, void* stream) {
+    TT_REQUIRE(coeffs && y && w && bias, "null argument");
+    TT_REQUIRE(C0 >= 1 && C0 <= 8, "conv_in: at most 8 output channels");
+    if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
+    dim3 grid((T + 255) / 256, H, B);
+    conv_in_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
+extern "C" int tt_conv_out(const void* x, float* coeffs, const float* w, const float* bias, int B, int C, int H, int T, void* stream) {
+    TT_REQUIRE(x && coeffs && w && bias, "null argument");
+    TT_REQUIRE(C >= 1 && C <= 8, "conv_out: at most 8 input channels");
+    if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
+    dim3 grid((T + 255) / 256, H, B);
+    conv_out_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}

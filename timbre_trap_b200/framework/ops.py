@@ -1,0 +1,90 @@
+"""
+Thin torch-tensor wrappers over the conv entry points of the C ABI (include/timbre_trap_b200.h).
+Tensors are C8 planar bf16 (B, CG, H, T, 8) unless noted; weights are already packed (packing.py).
+PyTorch is used for allocation and stream ownership only.
+"""
+
+import ctypes
+
+import torch
+
+from .. import _lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _s(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _check_c8(x, name='x'):
+    _lib.require_cuda(x, name)
+    if x.dtype != torch.bfloat16 or x.dim() != 5 or x.size(-1) != 8 or not x.is_contiguous():
+        raise ValueError(f'{name} must be a contiguous C8 planar bf16 tensor (B, CG, H, T, 8), got {tuple(x.shape)} {x.dtype}')
+
+
+def res_block(x, w1, b1, w2, b2, dilation, out=None):
+    _check_c8(x)
+    B, CG, H, T, _ = x.shape
+    y = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_res_block(_p(x), _p(y), _p(w1), _p(b1), _p(w2), _p(b2), B, CG * 8, H, T, dilation, _s(x)))
+    return y
+
+
+def conv_down(x, w, b, cout_pad):
+    _check_c8(x)
+    B, CG, H, T, _ = x.shape
+    y = torch.empty((B, cout_pad // 8, (H - 4) // 2 + 1, T, 8), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_conv_down(_p(x), _p(y), _p(w), _p(b), B, CG * 8, cout_pad, H, T, _s(x)))
+    return y
+
+
+def conv_up(x, w, b, cout_pad, out_pad):
+    _check_c8(x)
+    B, CG, H, T, _ = x.shape
+    y = torch.empty((B, cout_pad // 8, 2 * H + 2 + out_pad, T, 8), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_conv_up(_p(x), _p(y), _p(w), _p(b), B, CG * 8, cout_pad, H, out_pad, T, _s(x)))
+    return y
+
+
+def conv_lat(x, w, b, latent_pad):
+    _check_c8(x)
+    B, CG, H, T, _ = x.shape
+    y = torch.empty((B, latent_pad // 8, 1, T, 8), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_conv_lat(_p(x), _p(y), _p(w), _p(b), B, CG * 8, H, latent_pad, T, _s(x)))
+    return y
+
+
+def deconv_in(lat, w, bias_table, c0_pad, h0):
+    _check_c8(lat, 'latents')
+    B, CG, _, T, _ = lat.shape
+    y = torch.empty((B, c0_pad // 8, h0, T, 8), dtype=torch.bfloat16, device=lat.device)
+    with torch.cuda.device(lat.device):
+        _lib.check(_lib.lib().tt_deconv_in(_p(lat), _p(y), _p(w), _p(bias_table), B, CG * 8, c0_pad, h0, T, _s(lat)))
+    return y
+
+
+def conv_in(coeffs_bft2, w, b, c0):
+    """coeffs (B, F, T, 2) fp32 interleaved -> C8 planar (B, 1, F, T, 8)."""
+    _lib.require_cuda(coeffs_bft2, 'coefficients')
+    B, F, T, _ = coeffs_bft2.shape
+    y = torch.empty((B, 1, F, T, 8), dtype=torch.bfloat16, device=coeffs_bft2.device)
+    with torch.cuda.device(y.device):
+        _lib.check(_lib.lib().tt_conv_in(_p(coeffs_bft2), _p(y), _p(w), _p(b), B, c0, F, T, _s(y)))
+    return y
+
+
+def conv_out(x, w, b, c):
+    """C8 planar (B, 1, F, T, 8) -> coeffs (B, F, T, 2) fp32 interleaved."""
+    _check_c8(x)
+    B, _, F, T, _ = x.shape
+    y = torch.empty((B, F, T, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_conv_out(_p(x), _p(y), _p(w), _p(b), B, c, F, T, _s(x)))
+    return y

@@ -1,0 +1,132 @@
+"""
+Weight packing for the tensor-core conv kernels (csrc/conv_kernels.cu).
+
+Every GEMM-shaped layer consumes its weights as the tcgen05 B operand in the SWIZZLE_NONE K-major
+canonical layout:  packed[k // 8][n][k % 8]  (bf16), i.e. for each group of 8 consecutive K indices
+a contiguous (N x 8) slab.  The K order of each layer matches the order in which the kernel's tap
+table walks the shared-memory input tile; channel counts are zero-padded to multiples of 8 (K) and
+to at least 16 (N).  Shapes on the left are the reference's state_dict shapes.
+
+The C8 planar activation layout is (B, ceil(C/8), H, T, 8) bf16.
+"""
+
+import torch
+
+__all__ = ['pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
+           'pad_vec']
+
+
+def pad8(c):
+    return (c + 7) // 8 * 8
+
+
+def to_c8(x):
+    """(B, C, H, T) -> (B, ceil(C/8), H, T, 8) bf16, zero-padded channels (test/plumbing helper)."""
+    B, C, H, T = x.shape
+    Cp = pad8(C)
+    if Cp != C:
+        x = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, Cp - C))
+    return x.reshape(B, Cp // 8, 8, H, T).permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
+
+
+def from_c8(y, C):
+    """(B, CG, H, T, 8) -> (B, C, H, T) fp32."""
+    B, CG, H, T, _ = y.shape
+    return y.permute(0, 1, 4, 2, 3).reshape(B, CG * 8, H, T)[:, :C].float()
+
+
+def pad_vec(b, n):
+    out = torch.zeros(n, dtype=torch.float32, device=b.device)
+    out[:b.numel()] = b.detach().float()
+    return out
+
+
+def _to_b_operand(w_nk):
+    """(N, K) fp32 with K % 8 == 0 -> packed (K/8, N, 8) bf16."""
+    N, K = w_nk.shape
+    return w_nk.reshape(N, K // 8, 8).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+
+
+def pack_res3x3(w):
+    """conv1.0.weight (C, C, 3, 3) -> K order (tap = ky*3+kx, ci); C = 8 gets a 10th all-zero K group (MMA K = 16)."""
+    Co, Ci = w.shape[:2]
+    Cp = pad8(Ci)
+    N = max(16, pad8(Co))
+    k = torch.zeros((N, 9, Cp), dtype=torch.float32, device=w.device)
+    k[:Co, :, :Ci] = w.detach().float().permute(0, 2, 3, 1).reshape(Co, 9, Ci)
+    k = k.reshape(N, 9 * Cp)
+    if Cp == 8:
+        k = torch.nn.functional.pad(k, (0, 8))
+    return _to_b_operand(k)
+
+
+def pack_res1x1(w):
+    """conv2.0.weight (C, C, 1, 1) -> K = ci, padded to at least 16."""
+    Co, Ci = w.shape[:2]
+    K = max(16, pad8(Ci))
+    N = max(16, pad8(Co))
+    k = torch.zeros((N, K), dtype=torch.float32, device=w.device)
+    k[:Co, :Ci] = w.detach().float().reshape(Co, Ci)
+    return _to_b_operand(k)
+
+
+def pack_down(w):
+    """sconv.0.weight (Cout, Cin, 4, 1) -> K order (kh, ci)."""
+    Co, Ci = w.shape[:2]
+    Cp = pad8(Ci)
+    N = max(16, pad8(Co))
+    k = torch.zeros((N, 4, Cp), dtype=torch.float32, device=w.device)
+    k[:Co, :, :Ci] = w.detach().float()[..., 0].permute(0, 2, 1)
+    return _to_b_operand(k.reshape(N, 4 * Cp))
+
+
+def pack_up(w):
+    """
+    tconv.0.weight (Cin, Cout, 4, 1) -> polyphase GEMM: N = (r, co) with r the output-row parity, K = (a, ci) with
+    a = 0 the input row q-1 (kernel tap r+2) and a = 1 the input row q (kernel tap r).
+    """
+    Ci, Co = w.shape[:2]
+    Cip, Cop = pad8(Ci), pad8(Co)
+    N = max(16, 2 * Cop)
+    k = torch.zeros((N, 2, Cip), dtype=torch.float32, device=w.device)
+    wf = w.detach().float()[..., 0]                      # (Ci, Co, 4)
+    for r in range(2):
+        k[r * Cop: r * Cop + Co, 0, :Ci] = wf[:, :, r + 2].t()
+        k[r * Cop: r * Cop + Co, 1, :Ci] = wf[:, :, r].t()
+    return _to_b_operand(k.reshape(N, 2 * Cip))
+
+
+def pack_up_bias(b, Co):
+    Cop = pad8(Co)
+    out = torch.zeros(max(16, 2 * Cop), dtype=torch.float32, device=b.device)
+    out[:Co] = b.detach().float()
+    out[Cop:Cop + Co] = b.detach().float()
+    return out
+
+
+def pack_lat(w, latent_pad):
+    """convlat.weight (D, C4, H4, 1) -> K order (kh, ci), N = D padded to latent_pad."""
+    D, C4, H4 = w.shape[:3]
+    Cp = pad8(C4)
+    k = torch.zeros((latent_pad, H4, Cp), dtype=torch.float32, device=w.device)
+    k[:D, :, :C4] = w.detach().float()[..., 0].permute(0, 2, 1)
+    return _to_b_operand(k.reshape(latent_pad, H4 * Cp))
+
+
+def pack_deconv_in(w, b, latent_pad):
+    """
+    decoder.convin.0.weight (D+1, C0, H0, 1), bias (C0) -> per output row h a (C0 x D) B operand, packed
+    (H0, latent_pad/8, C0, 8); plus the two per-row bias tables (H0, C0): index 0 = transcribe (indicator 0),
+    1 = reconstruct (indicator 1: the last input channel's weights are added to the bias).
+    """
+    D1, C0, H0 = w.shape[:3]
+    D = D1 - 1
+    N = max(16, pad8(C0))
+    wf = w.detach().float()[..., 0]                      # (D+1, C0, H0)
+    k = torch.zeros((H0, N, latent_pad), dtype=torch.float32, device=w.device)
+    k[:, :C0, :D] = wf[:D].permute(2, 1, 0)
+    packed = k.reshape(H0, N, latent_pad // 8, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16)
+    bias = torch.zeros((2, H0, N), dtype=torch.float32, device=w.device)
+    bias[0, :, :C0] = b.detach().float()[None, :]
+    bias[1, :, :C0] = b.detach().float()[None, :] + wf[D].t()
+    return packed, bias
