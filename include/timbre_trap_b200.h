@@ -89,6 +89,17 @@ int tt_to_decibels(const float* magnitude, int batch, int64_t per_item, int resc
                    float* item_max, void* stream);
 
 /*
+ * Hann cross-fade of 50 %-overlapped chunk outputs + trim (TimbreTrap.chunked_inference, modules.py:237-267).
+ *   chunks      (batch * n_chunks, F, M, 2) fp32 - chunk i of item b at index b * n_chunks + i
+ *   window      (M) fp32 device (torch.signal.windows.hann, modules.py:239)
+ *   coeffs_out  (batch, F, (n_chunks-1) * M/2, 2) or NULL
+ *   act_out     (batch, F, (n_chunks-1) * M/2)    or NULL: tanh(|.|) of the cross-faded coefficients
+ *               (TimbreTrap.to_activations, modules.py:271-289, fused for transcribe())
+ */
+int tt_chunk_crossfade(const float* chunks, const float* window, int batch, int n_chunks, int n_bins, int frames_per_chunk,
+                       float* coeffs_out, float* act_out, void* stream);
+
+/*
  * ---- conv autoencoder (modules.py:396-777), bf16 tensor-core implicit GEMMs --------------------------------
  * Activations: "C8 planar" bf16  [B][ceil(C/8)][H][T][8]  (channel counts below are the PADDED counts, multiples of 8).
  * Weights: pre-packed bf16 in the tcgen05 B-operand layout [K/8][N][8]; K order and zero padding are documented at

@@ -161,10 +161,11 @@ __global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ 
         }
         if (tid < 16) reinterpret_cast<uint4*>(sIn + (size_t)p.CGin * plane_bytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
         if (p.two_stage) {
-            // the spare row after each mid plane is read (times zero weights) when C = 8 pairs a row with its successor
+            // when C = 8 an MMA pairs mid row i with row i + 1 (times zero weights): the row after the last one this
+            // CTA produces must hold finite values, not stale shared memory
             const int planes = p.mid_planes;
             for (int i = tid; i < planes * 128; i += 128)
-                reinterpret_cast<uint4*>(sMid + (size_t)(i / 128) * mid_plane + (size_t)p.R * 2048u)[i % 128] = make_uint4(0u, 0u, 0u, 0u);
+                reinterpret_cast<uint4*>(sMid + (size_t)(i / 128) * mid_plane + (size_t)rows * 2048u)[i % 128] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
     umma::fence_proxy_async();

@@ -537,6 +537,34 @@ __global__ void decibels_kernel(const float* __restrict__ x, long long per_item,
     }
 }
 
+
+// Cross-fade of 50 %-overlapped chunk outputs (TimbreTrap.chunked_inference, modules.py:259-267), as a gather: output
+// frame t (after the M/2 trim) receives chunk i1 = (t + M/2) / (M/2) at position p1 = (t + M/2) mod (M/2) and chunk
+// i1 - 1 at position p1 + M/2, each scaled by the window.  Products are rounded separately and added in chunk order,
+// like the reference's `coefficients[...] += window * output_chunk`.
+__global__ void crossfade_kernel(const float2* __restrict__ chunks, const float* __restrict__ window, int n_chunks, int F,
+                                 int M, float2* __restrict__ coeffs_out, float* __restrict__ act_out) {
+    const int half = M / 2;
+    const long long n_out = (long long)(n_chunks - 1) * half;
+    const int b = blockIdx.z, f = blockIdx.y;
+    const float2* base = chunks + ((size_t)b * n_chunks * F + f) * M;       // chunk i of item b: + i * F * M
+    const size_t chunk_stride = (size_t)F * M;
+    const size_t out_row = ((size_t)b * F + f) * n_out;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_out; t += (long long)gridDim.x * blockDim.x) {
+        const long long tf = t + half;
+        const int i1 = (int)(tf / half);
+        const int p1 = (int)(tf - (long long)i1 * half);
+        const float2 c0 = ld_stream(base + (size_t)(i1 - 1) * chunk_stride + p1 + half);
+        const float2 c1 = ld_stream(base + (size_t)i1 * chunk_stride + p1);
+        const float w0 = window[p1 + half], w1 = window[p1];
+        float2 r;
+        r.x = __fadd_rn(__fmul_rn(w0, c0.x), __fmul_rn(w1, c1.x));
+        r.y = __fadd_rn(__fmul_rn(w0, c0.y), __fmul_rn(w1, c1.y));
+        if (coeffs_out) coeffs_out[out_row + t] = r;
+        if (act_out) act_out[out_row + t] = tanhf(sqrtf(r.x * r.x + r.y * r.y));
+    }
+}
+
 }  // namespace tt
 
 // =============================================================================================
@@ -795,6 +823,19 @@ extern "C" int tt_to_decibels(const float* magnitude, int batch, int64_t per_ite
     dim3 grid(gx, batch);
     item_max_kernel<<<grid, 256, 0, stream>>>(magnitude, per_item, (unsigned int*)item_max);
     decibels_kernel<<<grid, 256, 0, stream>>>(magnitude, per_item, rescale, out, item_max);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
+extern "C" int tt_chunk_crossfade(const float* chunks, const float* window, int batch, int n_chunks, int n_bins, int frames_per_chunk,
+                                  float* coeffs_out, float* act_out, void* stream_) {
+    TT_REQUIRE(chunks && window && (coeffs_out || act_out), "null argument");
+    TT_REQUIRE(n_chunks >= 2 && frames_per_chunk % 2 == 0, "need at least two chunks and an even chunk length");
+    if (batch <= 0 || n_bins <= 0) return TT_OK;
+    const long long n_out = (long long)(n_chunks - 1) * (frames_per_chunk / 2);
+    dim3 grid((unsigned)std::min<long long>((n_out + 255) / 256, 64), n_bins, batch);
+    crossfade_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const float2*)chunks, window, n_chunks, n_bins, frames_per_chunk,
+                                                              (float2*)coeffs_out, act_out);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }

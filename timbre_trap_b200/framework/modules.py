@@ -1,0 +1,411 @@
+"""
+Drop-in for the autoencoder of `timbre_trap.framework.modules` (reference:
+timbre_trap/framework/modules.py:23-777): `TimbreTrap`, `Encoder`, `Decoder`, `EncoderBlock`,
+`DecoderBlock`, `ResidualConv2dBlock` with the reference's constructor signatures, attribute
+names and state_dict keys - so reference checkpoints load unchanged - but every
+convolution runs in the sm_100a kernels of csrc/conv_kernels.cu (bf16 operands, fp32 accumulate).
+
+The torch.nn.Conv2d / ConvTranspose2d objects inside the blocks are PARAMETER HOLDERS only (same
+names, shapes and default initialisation as the reference); their forward is never called.
+Activations between layers live in the C8 planar bf16 layout (B, ceil(C/8), H, T, 8).
+"""
+
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+from . import ops
+from . import packing as P
+from .cqt import CQT
+
+__all__ = ['TimbreTrap', 'Encoder', 'Decoder', 'EncoderBlock', 'DecoderBlock', 'ResidualConv2dBlock']
+
+
+class _PackedCache:
+    """Packed (kernel-layout) copies of a module's parameters, rebuilt when a parameter is modified or moved."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, params, build):
+        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        if key != self._key:
+            with torch.no_grad():
+                self._val = build()
+            self._key = key
+        return self._val
+
+
+def _n16(c):
+    return max(16, P.pad8(c))
+
+
+class ResidualConv2dBlock(nn.Module):
+    """modules.py:721-777: y = x + ELU(conv1x1(ELU(conv3x3_dilated(x)))), one fused kernel."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, dilation=1):
+        super().__init__()
+        if in_channels != out_channels or kernel_size != 3:
+            raise ValueError('timbre_trap_b200 implements the residual block as the reference uses it: C -> C, 3x3')
+        self.conv1 = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, padding='same', dilation=dilation),
+                                   nn.ELU(inplace=True))
+        self.conv2 = nn.Sequential(nn.Conv2d(out_channels, out_channels, kernel_size=1), nn.ELU(inplace=True))
+        self.dilation = dilation
+        self.channels = in_channels
+        self._cache = _PackedCache()
+
+    def _packed(self):
+        c1, c2 = self.conv1[0], self.conv2[0]
+        n = _n16(self.channels)
+        return self._cache.get((c1.weight, c1.bias, c2.weight, c2.bias),
+                               lambda: (P.pack_res3x3(c1.weight), P.pad_vec(c1.bias, n), P.pack_res1x1(c2.weight), P.pad_vec(c2.bias, n)))
+
+    def forward_c8(self, x, out=None):
+        w1, b1, w2, b2 = self._packed()
+        return ops.res_block(x, w1, b1, w2, b2, self.dilation, out=out)
+
+    def forward(self, x):
+        """(B, C, H, W) -> (B, C, H, W) fp32 (API parity; the fast paths stay in C8 planar)."""
+        return P.from_c8(self.forward_c8(P.to_c8(x)), self.channels)
+
+
+class EncoderBlock(nn.Module):
+    """modules.py:597-655: residual blocks with dilation 1, 2, 3, then a (4,1)/(2,1) strided conv + ELU."""
+
+    def __init__(self, in_channels, out_channels, stride=2):
+        super().__init__()
+        if stride != 2:
+            raise ValueError('stride 2 only (the reference never uses another value)')
+        self.block1 = ResidualConv2dBlock(in_channels, in_channels, kernel_size=3, dilation=1)
+        self.block2 = ResidualConv2dBlock(in_channels, in_channels, kernel_size=3, dilation=2)
+        self.block3 = ResidualConv2dBlock(in_channels, in_channels, kernel_size=3, dilation=3)
+        self.hop = stride
+        self.win = 2 * stride
+        self.sconv = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size=(self.win, 1), stride=(self.hop, 1)),
+                                   nn.ELU(inplace=True))
+        self.out_channels = out_channels
+        self._cache = _PackedCache()
+
+    def forward_c8(self, x):
+        a = self.block1.forward_c8(x)
+        b = self.block2.forward_c8(a)
+        a = self.block3.forward_c8(b, out=a)
+        c = self.sconv[0]
+        w, bias = self._cache.get((c.weight, c.bias), lambda: (P.pack_down(c.weight), P.pad_vec(c.bias, _n16(self.out_channels))))
+        return ops.conv_down(a, w, bias, P.pad8(self.out_channels))
+
+    def forward(self, x):
+        return P.from_c8(self.forward_c8(P.to_c8(x)), self.out_channels)
+
+
+class DecoderBlock(nn.Module):
+    """modules.py:658-718: (4,1)/(2,1) transposed conv (+output_padding) + ELU, then dilations 1, 2, 3."""
+
+    def __init__(self, in_channels, out_channels, stride=2, padding=0):
+        super().__init__()
+        if stride != 2:
+            raise ValueError('stride 2 only (the reference never uses another value)')
+        self.hop = stride
+        self.win = 2 * stride
+        self.tconv = nn.Sequential(nn.ConvTranspose2d(in_channels, out_channels, kernel_size=(self.win, 1), stride=(self.hop, 1),
+                                                      output_padding=(padding, 0)),
+                                   nn.ELU(inplace=True))
+        self.block1 = ResidualConv2dBlock(out_channels, out_channels, kernel_size=3, dilation=1)
+        self.block2 = ResidualConv2dBlock(out_channels, out_channels, kernel_size=3, dilation=2)
+        self.block3 = ResidualConv2dBlock(out_channels, out_channels, kernel_size=3, dilation=3)
+        self.out_channels = out_channels
+        self.out_pad = padding
+        self._cache = _PackedCache()
+
+    def forward_c8(self, x):
+        c = self.tconv[0]
+        w, bias = self._cache.get((c.weight, c.bias), lambda: (P.pack_up(c.weight), P.pack_up_bias(c.bias, self.out_channels)))
+        a = ops.conv_up(x, w, bias, P.pad8(self.out_channels), self.out_pad)
+        b = self.block1.forward_c8(a)
+        a = self.block2.forward_c8(b, out=a)
+        return self.block3.forward_c8(a, out=b)
+
+    def forward(self, x):
+        return P.from_c8(self.forward_c8(P.to_c8(x)), self.out_channels)
+
+
+def _channels(model_complexity):
+    return tuple(round(c * 2 ** (model_complexity - 1)) for c in (2, 4, 8, 16, 32))
+
+
+class Encoder(nn.Module):
+    """modules.py:396-483."""
+
+    def __init__(self, feature_size, latent_size=None, model_complexity=1):
+        super().__init__()
+        channels = _channels(model_complexity)
+        if latent_size is None:
+            latent_size = 32 * 2 ** (model_complexity - 1)
+        if channels[0] > 8 or channels[4] % 16:
+            raise ValueError('timbre_trap_b200 supports model_complexity 1..3 channel plans (first stage <= 8 channels)')
+        self.convin = nn.Sequential(nn.Conv2d(2, channels[0], kernel_size=3, padding='same'), nn.ELU(inplace=True))
+        self.block1 = EncoderBlock(channels[0], channels[1], stride=2)
+        self.block2 = EncoderBlock(channels[1], channels[2], stride=2)
+        self.block3 = EncoderBlock(channels[2], channels[3], stride=2)
+        self.block4 = EncoderBlock(channels[3], channels[4], stride=2)
+        embedding_size = feature_size
+        for _ in range(4):
+            embedding_size = embedding_size // 2 - 1
+        self.convlat = nn.Conv2d(channels[4], latent_size, kernel_size=(embedding_size, 1))
+        self.channels = channels
+        self.latent_size = latent_size
+        self.latent_pad = (latent_size + 15) // 16 * 16
+        self._cache = _PackedCache()
+
+    def _packed(self):
+        ci, cl = self.convin[0], self.convlat
+        return self._cache.get((ci.weight, ci.bias, cl.weight, cl.bias),
+                               lambda: (ci.weight.detach().float().contiguous(), ci.bias.detach().float().contiguous(),
+                                        P.pack_lat(cl.weight, self.latent_pad), P.pad_vec(cl.bias, self.latent_pad)))
+
+    def forward_c8(self, coeffs_bft2):
+        """coeffs (B, F, T, 2) fp32 interleaved -> (latents C8 (B, Dp/8, 1, T, 8), [5 embeddings C8])."""
+        w_in, b_in, w_lat, b_lat = self._packed()
+        emb = [ops.conv_in(coeffs_bft2, w_in, b_in, self.channels[0])]
+        for blk in (self.block1, self.block2, self.block3, self.block4):
+            emb.append(blk.forward_c8(emb[-1]))
+        return ops.conv_lat(emb[-1], w_lat, b_lat, self.latent_pad), emb
+
+    def forward(self, coefficients):
+        """Encoder.forward (modules.py:448-483): (B, 2, F, T) -> (latents (B, D, T), embeddings, {})."""
+        _lib.require_cuda(coefficients, 'coefficients')
+        with torch.no_grad():
+            lat, emb = self.forward_c8(_interleave(coefficients))
+            latents = P.from_c8(lat, self.latent_size).squeeze(-2)
+            embeddings = [P.from_c8(e, c) for e, c in zip(emb, self.channels)]
+        return latents, embeddings, dict()
+
+
+class Decoder(nn.Module):
+    """modules.py:486-594."""
+
+    def __init__(self, feature_size, latent_size=None, model_complexity=1):
+        super().__init__()
+        channels = _channels(model_complexity)[::-1]
+        if latent_size is None:
+            latent_size = 32 * 2 ** (model_complexity - 1)
+        padding = []
+        embedding_size = feature_size
+        for _ in range(4):
+            padding.append(embedding_size % 2)
+            embedding_size = embedding_size // 2 - 1
+        padding.reverse()
+        self.convin = nn.Sequential(nn.ConvTranspose2d(latent_size + 1, channels[0], kernel_size=(embedding_size, 1)), nn.ELU(inplace=True))
+        self.block1 = DecoderBlock(channels[0], channels[1], stride=2, padding=padding[0])
+        self.block2 = DecoderBlock(channels[1], channels[2], stride=2, padding=padding[1])
+        self.block3 = DecoderBlock(channels[2], channels[3], stride=2, padding=padding[2])
+        self.block4 = DecoderBlock(channels[3], channels[4], stride=2, padding=padding[3])
+        self.convout = nn.Conv2d(channels[4], 2, kernel_size=3, padding='same')
+        self.channels = channels
+        self.latent_size = latent_size
+        self.latent_pad = (latent_size + 15) // 16 * 16
+        self.embedding_size = embedding_size
+        self._cache = _PackedCache()
+
+    def _packed(self):
+        ci, co = self.convin[0], self.convout
+        def build():
+            w, tables = P.pack_deconv_in(ci.weight, ci.bias, self.latent_pad)
+            return w, tables, co.weight.detach().float().contiguous(), co.bias.detach().float().contiguous()
+        return self._cache.get((ci.weight, ci.bias, co.weight, co.bias), build)
+
+    def forward_c8(self, lat_c8, reconstruct, skips=None):
+        """latents C8 (B, Dp/8, 1, T, 8) (without the indicator channel) -> coefficients (B, F, T, 2) fp32 interleaved."""
+        w_in, tables, w_out, b_out = self._packed()
+        x = ops.deconv_in(lat_c8, w_in, tables[1 if reconstruct else 0], P.pad8(self.channels[0]), self.embedding_size)
+        blocks = (self.block1, self.block2, self.block3, self.block4)
+        for i, blk in enumerate(blocks):
+            if skips is not None:
+                x = x + skips[-1 - i]
+            x = blk.forward_c8(x)
+        if skips is not None:
+            x = x + skips[0]
+        return ops.conv_out(x, w_out, b_out, self.channels[4])
+
+    def forward(self, latents, encoder_embeddings=None):
+        """Decoder.forward (modules.py:545-594): latents (B, D+1, T) WITH the indicator channel -> (B, 2, F, T)."""
+        _lib.require_cuda(latents, 'latents')
+        with torch.no_grad():
+            flag = latents[:, -1]
+            is_one, is_zero = bool((flag == 1).all()), bool((flag == 0).all())
+            if not (is_one or is_zero):
+                raise ValueError('the indicator channel must be all ones (reconstruct) or all zeros (transcribe), as '
+                                 'TimbreTrap.decode builds it (modules.py:139-142)')
+            lat = _latents_to_c8(latents[:, :-1], self.latent_pad)
+            skips = None if encoder_embeddings is None else [P.to_c8(e) for e in encoder_embeddings]
+            return self.forward_c8(lat, is_one, skips).permute(0, 3, 1, 2)
+
+
+def _interleave(coefficients):
+    """(B, 2, F, T) real (any strides) -> contiguous (B, F, T, 2) fp32 (free for the CQT's own output)."""
+    c = coefficients.detach().permute(0, 2, 3, 1)
+    if c.dtype != torch.float32:
+        c = c.float()
+    return c if c.is_contiguous() else c.contiguous()
+
+
+def _latents_to_c8(latents, latent_pad):
+    """(B, D, T) -> C8 planar (B, Dp/8, 1, T, 8) bf16."""
+    B, D, T = latents.shape
+    x = latents.detach().float()
+    if D != latent_pad:
+        x = torch.nn.functional.pad(x, (0, 0, 0, latent_pad - D))
+    return x.reshape(B, latent_pad // 8, 8, 1, T).permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
+
+
+class TimbreTrap(nn.Module):
+    """modules.py:23-393.  Same public surface; `sliCQ` is the CQT module (every reference script uses that name)."""
+
+    # chunks per kernel batch of the chunked paths (bounds activation memory: ~2.3 GB per live tensor at 256 chunks)
+    MAX_CHUNKS_PER_BATCH = 256
+
+    def __init__(self, sample_rate, n_octaves, bins_per_octave, secs_per_block=3, latent_size=None, model_complexity=1,
+                 skip_connections=False):
+        nn.Module.__init__(self)
+        self.sliCQ = CQT(n_octaves=n_octaves, bins_per_octave=bins_per_octave, sample_rate=sample_rate, secs_per_block=secs_per_block)
+        self.encoder = Encoder(feature_size=self.sliCQ.n_bins, latent_size=latent_size, model_complexity=model_complexity)
+        self.decoder = Decoder(feature_size=self.sliCQ.n_bins, latent_size=latent_size, model_complexity=model_complexity)
+        self.skip_weights = torch.nn.Parameter(torch.ones(5)) if skip_connections else None
+        self._windows = {}
+
+    # ---- C8 fast paths -----------------------------------------------------------------------------
+    def _skips_c8(self, emb):
+        if self.skip_weights is None:
+            return None
+        return [(self.skip_weights[i].to(torch.bfloat16) * e) for i, e in enumerate(emb)]
+
+    def _codes(self, audio):
+        """audio (B, 1, n*L) -> (latents C8, skips C8 or None)."""
+        lat, emb = self.encoder.forward_c8(self.sliCQ.encode_interleaved(audio))
+        return lat, self._skips_c8(emb)
+
+    # ---- reference API -------------------------------------------------------------------------------
+    def encode(self, audio):
+        """modules.py:67-93."""
+        coefficients = self.sliCQ(audio)
+        return self.encoder(coefficients)
+
+    def apply_skip_connections(self, embeddings):
+        """modules.py:95-117."""
+        if self.skip_weights is not None:
+            return [self.skip_weights[i] * e for i, e in enumerate(embeddings)]
+        return None
+
+    def decode(self, latents, embeddings=None, transcribe=False):
+        """modules.py:119-147: latents (B, D, T) -> logits (B, 2, F, T)."""
+        _lib.require_cuda(latents, 'latents')
+        with torch.no_grad():
+            lat = _latents_to_c8(latents, self.decoder.latent_pad)
+            skips = None if embeddings is None else [P.to_c8(e) for e in embeddings]
+            return self.decoder.forward_c8(lat, not transcribe, skips).permute(0, 3, 1, 2)
+
+    def _inference(self, audio, transcribe=False):
+        """modules.py:149-177."""
+        with torch.no_grad():
+            lat, skips = self._codes(audio)
+            return self.decoder.forward_c8(lat, not transcribe, skips).permute(0, 3, 1, 2)
+
+    def inference(self, audio, transcribe=False):
+        """modules.py:179-202."""
+        return self._inference(self.sliCQ.pad_to_block_length(audio), transcribe)
+
+    def _window(self, device):
+        key = (device.type, device.index)
+        if key not in self._windows:
+            self._windows[key] = torch.signal.windows.hann(self.sliCQ.max_window_length, device=device)
+        return self._windows[key]
+
+    def _chunks(self, audio):
+        """Pad and slice audio into 50 %-overlapped blocks (modules.py:226-234, 247-253): (B*n_chunks, 1, L), n_chunks."""
+        audio = self.sliCQ.pad_to_block_length(audio)
+        L = self.sliCQ.block_length
+        hop = L // 2
+        audio = torch.nn.functional.pad(audio, [hop] * 2)
+        n_chunks = (audio.size(-1) - hop) // hop
+        chunks = audio.unfold(-1, L, hop)[:, :, :n_chunks]                 # (B, 1, n_chunks, L) view
+        return chunks.reshape(audio.size(0) * n_chunks, 1, L), n_chunks
+
+    def _chunked(self, audio, want_transcription, want_reconstruction, activations=True):
+        """
+        Batched form of chunked_inference (modules.py:204-269) for one or both switch settings with a shared
+        encoder pass.  Returns (transcription, reconstruction) coefficient tensors (B, F, T, 2) interleaved - or the
+        activations (B, F, T) for the transcription when `activations` - None where not requested.
+        """
+        _lib.require_cuda(audio, 'audio')
+        with torch.no_grad():
+            B, F, M = audio.size(0), self.sliCQ.n_bins, self.sliCQ.max_window_length
+            chunks, n_chunks = self._chunks(audio.detach().float())
+            n_out = (n_chunks - 1) * (M // 2)
+            window = self._window(audio.device)
+            outs = []
+            for want, reconstruct in ((want_transcription, False), (want_reconstruction, True)):
+                outs.append(torch.empty((B * n_chunks, F, M, 2), dtype=torch.float32, device=audio.device) if want else None)
+            step = self.MAX_CHUNKS_PER_BATCH
+            for c0 in range(0, B * n_chunks, step):
+                lat, skips = self._codes(chunks[c0:c0 + step])
+                for out, reconstruct in zip(outs, (False, True)):
+                    if out is not None:
+                        out[c0:c0 + step] = self.decoder.forward_c8(lat, reconstruct, skips)
+            results = []
+            for out, as_act in zip(outs, (activations, False)):
+                if out is None:
+                    results.append(None)
+                    continue
+                if as_act:
+                    res = torch.empty((B, F, n_out), dtype=torch.float32, device=audio.device)
+                    args = (None, ctypes.c_void_p(res.data_ptr()))
+                else:
+                    res = torch.empty((B, F, n_out, 2), dtype=torch.float32, device=audio.device)
+                    args = (ctypes.c_void_p(res.data_ptr()), None)
+                with torch.cuda.device(audio.device):
+                    _lib.check(_lib.lib().tt_chunk_crossfade(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(window.data_ptr()),
+                                                             B, n_chunks, F, M, args[0], args[1],
+                                                             ctypes.c_void_p(torch.cuda.current_stream(audio.device).cuda_stream)))
+                results.append(res)
+            return results
+
+    def chunked_inference(self, audio, transcribe=False):
+        """modules.py:204-269: (B, 1, N) -> (B, 2, F, T) cross-faded coefficients."""
+        trn, rec = self._chunked(audio, transcribe, not transcribe, activations=False)
+        return (trn if transcribe else rec).permute(0, 3, 1, 2)
+
+    def to_activations(self, coefficients):
+        """modules.py:271-289."""
+        return CQT._magnitude(coefficients, True)
+
+    def transcribe(self, audio):
+        """modules.py:292-313: (B, 1, N) -> activations (B, F, T) in [0, 1)."""
+        return self._chunked(audio, True, False)[0]
+
+    def reconstruct(self, audio_in):
+        """modules.py:315-336: (B, 1, N) -> audio (B, 1, N') in [-1, 1]."""
+        return self.sliCQ.decode(self._chunked(audio_in, False, True)[1].permute(0, 3, 1, 2))
+
+    def transcribe_and_reconstruct(self, audio):
+        """Both outputs of transcribe() and reconstruct() from ONE encoder pass (not in the reference, which runs two)."""
+        act, rec = self._chunked(audio, True, True)
+        return act, self.sliCQ.decode(rec.permute(0, 3, 1, 2))
+
+    def forward(self, audio, consistency=False):
+        """modules.py:338-393 (inference semantics; the training step with gradients is framework.train_step)."""
+        with torch.no_grad():
+            lat, skips = self._codes(audio)
+            reconstruction = self.decoder.forward_c8(lat, True, skips)
+            transcription = self.decoder.forward_c8(lat, False, skips)
+            transcription_rec = transcription_scr = None
+            if consistency:
+                lat_t, emb_t = self.encoder.forward_c8(transcription)
+                skips_t = self._skips_c8(emb_t)
+                transcription_rec = self.decoder.forward_c8(lat_t, True, skips_t).permute(0, 3, 1, 2)
+                transcription_scr = self.decoder.forward_c8(lat_t, False, skips_t).permute(0, 3, 1, 2)
+            latents = P.from_c8(lat, self.encoder.latent_size).squeeze(-2)
+        return (reconstruction.permute(0, 3, 1, 2), latents, transcription.permute(0, 3, 1, 2), transcription_rec,
+                transcription_scr, dict())
