@@ -34,6 +34,8 @@ typedef struct tt_cqt_plan tt_cqt_plan;
 /* library / error plumbing */
 const char* tt_last_error(void);
 int tt_version(void);
+/* number of kernels this library has launched since load (or since the last call with reset != 0) */
+long long tt_launch_count(int reset);
 
 /*
  * Replaces cqt_pytorch.CQT.__init__ as called from cqtwrapper.py:31-35 (the window / index /

@@ -21,6 +21,7 @@ c_void_p, c_int, c_int64, c_float_p, c_int32_p = (ctypes.c_void_p, ctypes.c_int,
 SIGNATURES = {
     'tt_last_error': (ctypes.c_char_p, []),
     'tt_version': (c_int, []),
+    'tt_launch_count': (ctypes.c_longlong, [c_int]),
     'tt_cqt_plan_create': (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int32_p, c_int32_p, c_int32_p,
                                    c_int32_p, c_float_p, c_float_p, c_int, c_int]),
     'tt_cqt_plan_destroy': (c_int, [c_void_p]),

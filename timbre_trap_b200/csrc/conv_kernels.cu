@@ -89,8 +89,10 @@ __device__ __forceinline__ void unpack8(uint4 r, float* v) {
     }
 }
 
+constexpr int kConvThreads = 512;   // 16 warps: warp w owns TMEM lane quadrant w % 4 and row groups (w / 4) mod 4
+
 template <int N1, int N2>
-__global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ ConvRowsParams p) {
+__global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_constant__ ConvRowsParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int NC = N1 > N2 ? N1 : N2;           // TMEM columns per row group
     uint64_t* bar1 = reinterpret_cast<uint64_t*>(smem);
@@ -99,7 +101,9 @@ __global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ 
     float* sB1 = reinterpret_cast<float*>(smem + 512);
     float* sB2 = reinterpret_cast<float*>(smem + 1280);
 
+    constexpr int NT = kConvThreads, NW = NT / 32, NWG = NW / 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, wg = warp >> 2;
     const int t0 = blockIdx.x * kTileT;
     const int g0 = blockIdx.y * p.R;
     const int b = blockIdx.z;
@@ -133,12 +137,12 @@ __global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ 
         const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.w1) +
                                                           (size_t)(g0 + r) * p.w_group_stride);
         if (r < rows)
-            for (int i = tid; i < (int)(w1_bytes / 16); i += 128)
-                reinterpret_cast<uint4*>(sW1 + (size_t)r * w1_bytes)[i] = __ldg(src + i);
+            for (int i = tid; i < (int)(w1_bytes / 16); i += NT)
+                umma::cp_async16(reinterpret_cast<uint4*>(sW1 + (size_t)r * w1_bytes) + i, src + i, 16u);
     }
     if (p.two_stage)
-        for (int i = tid; i < (int)(w2_bytes / 16); i += 128)
-            reinterpret_cast<uint4*>(sW2)[i] = __ldg(reinterpret_cast<const uint4*>(p.w2) + i);
+        for (int i = tid; i < (int)(w2_bytes / 16); i += NT)
+            umma::cp_async16(reinterpret_cast<uint4*>(sW2) + i, reinterpret_cast<const uint4*>(p.w2) + i, 16u);
     if (p.b_group_stride == 0 && tid < N1) sB1[tid] = p.b1[tid];
     if (N2 > 0 && p.two_stage && tid < N2) sB2[tid] = p.b2[tid];
 
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ 
     {
         const int h_base = g0 * p.sh + p.row_lo;
         const int n_rows_all = p.CGin * p.in_rows;
-        for (int rr = warp; rr < n_rows_all; rr += 4) {
+        for (int rr = warp; rr < n_rows_all; rr += NW) {
             const int cg = rr / p.in_rows, r = rr - cg * p.in_rows;
             const int hi = h_base + r;
             const bool row_ok = hi >= 0 && hi < p.Hin;
@@ -154,9 +158,8 @@ __global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ 
             uint4* dst = reinterpret_cast<uint4*>(sIn + (size_t)cg * plane_bytes + (size_t)r * row_bytes);
             for (int c = lane; c < TW; c += 32) {
                 const int t = t0 - p.padT + c;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (row_ok && t >= 0 && t < p.T) v = __ldg(src + t);
-                dst[c] = v;
+                const bool ok = row_ok && t >= 0 && t < p.T;
+                umma::cp_async16(dst + c, ok ? src + t : reinterpret_cast<const uint4*>(p.x), ok ? 16u : 0u);
             }
         }
         if (tid < 16) reinterpret_cast<uint4*>(sIn + (size_t)p.CGin * plane_bytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
@@ -164,10 +167,11 @@ __global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ 
             // when C = 8 an MMA pairs mid row i with row i + 1 (times zero weights): the row after the last one this
             // CTA produces must hold finite values, not stale shared memory
             const int planes = p.mid_planes;
-            for (int i = tid; i < planes * 128; i += 128)
+            for (int i = tid; i < planes * 128; i += NT)
                 reinterpret_cast<uint4*>(sMid + (size_t)(i / 128) * mid_plane + (size_t)rows * 2048u)[i % 128] = make_uint4(0u, 0u, 0u, 0u);
         }
     }
+    umma::cp_async_wait_all();
     umma::fence_proxy_async();
     umma::fence_before_sync();
     __syncthreads();
@@ -190,12 +194,12 @@ __global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ 
         }
     }
 
-    const int j = warp * 32 + lane;                 // pixel within the tile = TMEM lane
-    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    const int j = quad * 32 + lane;                 // pixel within the tile = TMEM lane
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const bool t_ok = t0 + j < p.T;
 
     // ---- epilogue 1 ------------------------------------------------------------------------------------
-    for (int i = 0; i < rows; ++i) {
+    for (int i = wg; i < rows; i += NWG) {
         umma::mbar_wait(&bar1[i], 0);
         umma::fence_after_sync();
         const float* bias = p.b_group_stride ? p.b1 + (size_t)(g0 + i) * p.b_group_stride : sB1;
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(128) conv_rows_kernel(const __grid_constant__ 
                     umma::commit(&bar2[i]);
                 }
             }
-            for (int i = 0; i < rows; ++i) {
+            for (int i = wg; i < rows; i += NWG) {
                 umma::mbar_wait(&bar2[i], 0);
                 umma::fence_after_sync();
                 const uint8_t* res = sIn + (size_t)(i * p.sh) * row_bytes + p.res_off + (size_t)j * 16u;
@@ -305,7 +309,8 @@ static int launch_conv_rows(const ConvRowsParams& p, cudaStream_t stream) {
         configured = smem;
     }
     dim3 grid((p.T + kTileT - 1) / kTileT, (p.groups + p.R - 1) / p.R, p.B);
-    conv_rows_kernel<N1, N2><<<grid, 128, smem, stream>>>(p);
+    conv_rows_kernel<N1, N2><<<grid, kConvThreads, smem, stream>>>(p);
+    tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }
@@ -653,6 +658,7 @@ extern "C" int tt_conv_lat(const void* x, void* lat, const void* w, const float*
         default: tt_set_error("conv_lat: padded latent size must be 16, 32, 64, 128 or 256 (got %d)", NL); return TT_ERR_UNSUPPORTED;
     }
 #undef TT_LAT_CASE
+    tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }
@@ -663,6 +669,7 @@ extern "C" int tt_conv_in(const float* coeffs, void* y, const float* w, const fl
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
     dim3 grid((T + 255) / 256, H, B);
     conv_in_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T);
+    tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }
@@ -673,6 +680,7 @@ extern "C" int tt_conv_out(const void* x, float* coeffs, const float* w, const f
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
     dim3 grid((T + 255) / 256, H, B);
     conv_out_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T);
+    tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }

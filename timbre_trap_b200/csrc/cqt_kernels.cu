@@ -49,6 +49,13 @@ void tt_set_error(const char* fmt, ...) {
 extern "C" const char* tt_last_error(void) { return g_err; }
 extern "C" int tt_version(void) { return 1; }
 
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+void tt_count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long tt_launch_count(int reset) {
+    return reset ? g_launches.exchange(0, std::memory_order_relaxed) : g_launches.load(std::memory_order_relaxed);
+}
+
 namespace tt {
 
 constexpr int kColsPerCta = 14;   // A1 / S3: real columns per CTA (even: two per complex transform)
@@ -755,6 +762,7 @@ extern "C" int tt_cqt_forward(tt_cqt_plan* p, const float* audio, int batch, int
                                                                                      n_blocks, (int)b0, p->spec_m,
                                                                                      p->d_tw_m_fwd);
         }
+        tt_count_launches(3);
     }
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
@@ -766,6 +774,7 @@ extern "C" int tt_scale_by_peak(float* audio, int64_t n, const float* peak, void
     cudaStream_t stream = (cudaStream_t)stream_;
     const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 8);
     scale_by_peak_kernel<<<grid, 256, 0, stream>>>(audio, n, peak);
+    tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }
@@ -798,6 +807,7 @@ extern "C" int tt_cqt_inverse(tt_cqt_plan* p, const float* coeffs, int batch, in
         dim3 g3((p->N2 + kColsPerCta - 1) / kColsPerCta, nb);
         cols_inv_kernel<<<g3, kFftThreads, cols_smem(p), stream>>>(p->d_T, audio + (size_t)b0 * p->L, p->spec_n1, p->N2,
                                                                     p->K1, p->L, p->d_tw_n1, (unsigned int*)peak);
+        tt_count_launches(3);
     }
     TT_CUDA_CHECK(cudaGetLastError());
     if (normalise) return tt_scale_by_peak(audio, total * p->L, peak, stream_);
@@ -809,6 +819,7 @@ extern "C" int tt_magnitude(const float* coeffs, int64_t n, int apply_tanh, floa
     if (n <= 0) return TT_OK;
     const int grid = (int)std::min<long long>((n + 255) / 256, 148 * 16);
     magnitude_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const float2*)coeffs, n, apply_tanh, out);
+    tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }
@@ -823,6 +834,7 @@ extern "C" int tt_to_decibels(const float* magnitude, int batch, int64_t per_ite
     dim3 grid(gx, batch);
     item_max_kernel<<<grid, 256, 0, stream>>>(magnitude, per_item, (unsigned int*)item_max);
     decibels_kernel<<<grid, 256, 0, stream>>>(magnitude, per_item, rescale, out, item_max);
+    tt_count_launches(2);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }
@@ -836,6 +848,7 @@ extern "C" int tt_chunk_crossfade(const float* chunks, const float* window, int 
     dim3 grid((unsigned)std::min<long long>((n_out + 255) / 256, 64), n_bins, batch);
     crossfade_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>((const float2*)chunks, window, n_chunks, n_bins, frames_per_chunk,
                                                               (float2*)coeffs_out, act_out);
+    tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }

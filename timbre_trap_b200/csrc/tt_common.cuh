@@ -12,6 +12,7 @@
 #define TT_ERR_ALLOC 4
 
 void tt_set_error(const char* fmt, ...);
+void tt_count_launches(int n);   // bookkeeping for tt_launch_count()
 
 #define TT_CUDA_CHECK(expr)                                                                  \
     do {                                                                                     \

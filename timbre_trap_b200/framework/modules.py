@@ -385,14 +385,29 @@ class TimbreTrap(nn.Module):
         """modules.py:292-313: (B, 1, N) -> activations (B, F, T) in [0, 1)."""
         return self._chunked(audio, True, False)[0]
 
-    def reconstruct(self, audio_in):
-        """modules.py:315-336: (B, 1, N) -> audio (B, 1, N') in [-1, 1]."""
-        return self.sliCQ.decode(self._chunked(audio_in, False, True)[1].permute(0, 3, 1, 2))
+    def _decode_shared_peak(self, coefficients, group):
+        """
+        CQT.decode with the reference's GLOBAL infinity-norm normalise (cqtwrapper.py:209-211) when the batch is sharded
+        over the ranks of `group`: one scalar MAX all-reduce of the per-rank peaks, then a local scale.
+        """
+        if group is None:
+            return self.sliCQ.decode(coefficients)
+        import torch.distributed as dist
+        audio, peak = self.sliCQ.decode_raw(coefficients, normalise=False)
+        dist.all_reduce(peak, op=dist.ReduceOp.MAX, group=group)
+        with torch.cuda.device(audio.device):
+            _lib.check(_lib.lib().tt_scale_by_peak(ctypes.c_void_p(audio.data_ptr()), audio.numel(), ctypes.c_void_p(peak.data_ptr()),
+                                                   ctypes.c_void_p(torch.cuda.current_stream(audio.device).cuda_stream)))
+        return audio
 
-    def transcribe_and_reconstruct(self, audio):
+    def reconstruct(self, audio_in, group=None):
+        """modules.py:315-336: (B, 1, N) -> audio (B, 1, N') in [-1, 1].  `group`: see _decode_shared_peak."""
+        return self._decode_shared_peak(self._chunked(audio_in, False, True)[1].permute(0, 3, 1, 2), group)
+
+    def transcribe_and_reconstruct(self, audio, group=None):
         """Both outputs of transcribe() and reconstruct() from ONE encoder pass (not in the reference, which runs two)."""
         act, rec = self._chunked(audio, True, True)
-        return act, self.sliCQ.decode(rec.permute(0, 3, 1, 2))
+        return act, self._decode_shared_peak(rec.permute(0, 3, 1, 2), group)
 
     def forward(self, audio, consistency=False):
         """modules.py:338-393 (inference semantics; the training step with gradients is framework.train_step)."""
