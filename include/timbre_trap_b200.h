@@ -111,6 +111,10 @@ int tt_chunk_crossfade(const float* chunks, const float* window, int batch, int 
 /* ResidualConv2dBlock.forward (modules.py:743-777), fused: y = x + ELU(W2 * ELU(W1 (*)_dilation x + b1) + b2) */
 int tt_res_block(const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
                  int B, int C, int H, int T, int dilation, void* stream);
+/* The same block as a warp-specialised, row-pipelined kernel (TMA row ring -> tcgen05 -> TMEM -> epilogue warps);
+ * weights from packing.pack_res_strip (biases folded in as a K group); c_real = un-padded channel count. */
+int tt_res_block_strip(const void* x, void* y, const void* w1, const void* w2, int B, int C, int c_real, int H, int T,
+                       int dilation, void* stream);
 /* EncoderBlock.sconv + ELU (modules.py:626-629): Conv2d(Cin, Cout, (4,1), stride (2,1)); Hout = (Hin-4)/2 + 1 */
 int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int T, void* stream);
 /* DecoderBlock.tconv + ELU (modules.py:685-688): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding); Hout = 2 Hin + 2 + out_pad */

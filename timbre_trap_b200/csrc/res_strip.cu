@@ -1,0 +1,422 @@
+// Fused ResidualConv2dBlock (reference: timbre_trap/framework/modules.py:721-777) as a warp-specialised, row-pipelined
+// tcgen05 kernel:   y = x + ELU(W2 * ELU(W1 (*)_d x + b1) + b2)      (3x3 dilated 'same' conv, 1x1 conv, residual)
+//
+// One CTA owns a strip: 128 consecutive frames (T) x a run of rows (H) of one item, and walks down the rows:
+//
+//   warp 16 (producer)  one TMA box per input row (all channel groups, 128 + 2d frames, zero-filled outside the image)
+//                       into a 16-slot shared-memory ring; every input row is fetched once per strip (no row halo re-reads)
+//   warp 17 (MMA)       for row h: the 3x3 taps are start-address offsets into the ring slots of rows h-d, h, h+d
+//                       (implicit GEMM, M = 128 frames, N = C, K = 9 C) -> TMEM accumulator acc1[h % 4];
+//                       two rows later the 1x1 conv of row h-2 from the bf16 intermediate in shared memory -> acc2[(h-2) % 4].
+//                       The biases ride along as one extra K group against a constant "ones" operand (bias split into
+//                       bf16 hi + lo, so it is fp32-accurate), which removes the bias adds from the epilogues.
+//   warps 0-15          four epilogue groups (row h -> group h % 4; warp quadrant = TMEM lane quadrant):
+//                       acc1 -> ELU -> bf16 -> shared memory (A operand of the 1x1 conv);  acc2 -> ELU -> + x (from the
+//                       ring slot of row h) -> bf16 -> coalesced 16 B stores.
+//
+// All hand-offs are mbarriers (ring_full / ring_free / acc1_full / acc1_free / mid_full / acc2_full); nothing in the row
+// loop is a CTA-wide barrier.  HBM traffic is the algorithmic minimum (x read once, y written once) plus the 2d halo
+// frames per row; the epilogues (one exp per conv output) are the co-limiter - see DESIGN.md.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/timbre_trap_b200.h"
+#include "tt_common.cuh"
+#include "umma.cuh"
+
+namespace tt {
+
+constexpr int kRing = 16;          // input-row ring slots
+constexpr int kAcc = 4;            // accumulator / intermediate slots = epilogue groups
+constexpr int kLag = 2;            // rows between issuing the 3x3 MMAs of row h and the 1x1 MMAs of row h - kLag
+constexpr int kEpiWarps = 16;
+constexpr int kStripThreads = (kEpiWarps + 2) * 32;
+constexpr int kStripTileT = 128;
+
+struct ResStripParams {
+    __nv_bfloat16* y;
+    const __nv_bfloat16* w1;   // packed, see packing.pack_res_strip
+    const __nv_bfloat16* w2;
+    int B, H, T;
+    int d;                     // dilation
+    int rows_per_strip;
+};
+
+// ---- extra PTX: TMA tile load, mbarrier arrive variants ---------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(umma::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(umma::smem_u32(smem_dst)), "l"(map), "r"(umma::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+__device__ __forceinline__ float elu_f(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+template <int NV>
+__device__ __forceinline__ void tmem_load(uint32_t taddr, float (&v)[NV]) {
+    uint32_t r[NV];
+    if constexpr (NV == 4) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+    } else if constexpr (NV == 8) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    } else {
+        static_assert(NV == 16, "tmem_load: 4, 8 or 16 columns");
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory plan (bytes)
+template <int CG>
+struct StripSmem {
+    static constexpr int N = CG >= 4 ? 8 * CG : 16;                  // MMA N (padded)
+    static constexpr int KG1 = CG == 1 ? 12 : 9 * CG + 2;            // K groups of W1 incl. the bias / padding groups
+    static constexpr int KG2 = CG == 1 ? 2 : CG + 2;
+    static constexpr int kBars = 0;                                  // 64 mbarriers
+    static constexpr int kTmemSlot = 512;
+    static constexpr int kW1 = 1024;
+    static constexpr int kW2 = kW1 + KG1 * N * 16;
+    static constexpr int kMid = (kW2 + KG2 * N * 16 + 127) / 128 * 128;
+    static constexpr int kMidSlot = CG * 2048;
+    static constexpr int kRingBase = kMid + kAcc * kMidSlot;
+    __host__ __device__ static constexpr int slot_bytes(int d) { return (CG * (kStripTileT + 2 * d) * 16 + 127) / 128 * 128; }
+    __host__ __device__ static constexpr int ones_off(int d) { return kRingBase + kRing * slot_bytes(d); }
+    __host__ __device__ static constexpr int total(int d) { return ones_off(d) + 4096; }
+};
+
+template <int CG, int NREAL>
+__global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResStripParams p) {
+    using S = StripSmem<CG>;
+    constexpr int N = S::N;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
+    uint64_t* ring_full = bars;                 // [kRing]  TMA landed
+    uint64_t* ring_free = bars + kRing;         // [kRing]  1 commit (last 3x3 user) + 128 residual readers
+    uint64_t* acc1_full = bars + 2 * kRing;     // [kAcc]
+    uint64_t* acc1_free = acc1_full + kAcc;     // [kAcc]   128 arrivals
+    uint64_t* mid_full = acc1_free + kAcc;      // [kAcc]   128 arrivals
+    uint64_t* acc2_full = mid_full + kAcc;      // [kAcc]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = p.d;
+    const int TW = kStripTileT + 2 * d;
+    const int slot_bytes = S::slot_bytes(d);
+    uint8_t* sW1 = smem + S::kW1;
+    uint8_t* sW2 = smem + S::kW2;
+    uint8_t* sMid = smem + S::kMid;
+    uint8_t* sRing = smem + S::kRingBase;
+    uint8_t* sOnes = smem + S::ones_off(d);
+
+    const int t0 = blockIdx.x * kStripTileT;
+    const int h_start = blockIdx.y * p.rows_per_strip;
+    const int h_end = min(p.H, h_start + p.rows_per_strip);
+    const int b = blockIdx.z;
+    const int first_row = h_start - d;                       // ring index 0
+    constexpr uint32_t ncols = 2 * kAcc * N < 32 ? 32 : 2 * kAcc * N;
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------
+    if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
+    if (tid == 32) {
+        for (int i = 0; i < kRing; ++i) {
+            umma::mbar_init(&ring_full[i], 1);
+            umma::mbar_init(&ring_free[i], 129);
+        }
+        for (int i = 0; i < kAcc; ++i) {
+            umma::mbar_init(&acc1_full[i], 1);
+            umma::mbar_init(&acc1_free[i], 128);
+            umma::mbar_init(&mid_full[i], 128);
+            umma::mbar_init(&acc2_full[i], 1);
+        }
+        umma::mbar_fence_init();
+    }
+    for (int i = tid; i < S::KG1 * N; i += kStripThreads) reinterpret_cast<uint4*>(sW1)[i] = __ldg(reinterpret_cast<const uint4*>(p.w1) + i);
+    for (int i = tid; i < S::KG2 * N; i += kStripThreads) reinterpret_cast<uint4*>(sW2)[i] = __ldg(reinterpret_cast<const uint4*>(p.w2) + i);
+    // "ones" operand: plane 0 rows = (1, 1, 0, ..., 0), plane 1 = zeros
+    for (int i = tid; i < 256; i += kStripThreads)
+        reinterpret_cast<uint4*>(sOnes)[i] = i < 128 ? make_uint4(0x3F803F80u, 0u, 0u, 0u) : make_uint4(0u, 0u, 0u, 0u);
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == kEpiWarps) {
+        // =================================== producer ===================================
+        if (lane == 0) {
+            const int n_rows = (h_end - h_start) + 2 * d;
+            const uint32_t bytes = (uint32_t)CG * TW * 16u;
+            for (int idx = 0; idx < n_rows; ++idx) {
+                const int slot = idx % kRing;
+                if (idx >= kRing) umma::mbar_wait(&ring_free[slot], (uint32_t)((idx / kRing - 1) & 1));
+                mbar_expect_tx(&ring_full[slot], bytes);
+                tma_load_5d(sRing + (size_t)slot * slot_bytes, &tmap_x, &ring_full[slot], 0, t0 - d, first_row + idx, 0, b);
+            }
+        }
+    } else if (warp == kEpiWarps + 1) {
+        // =================================== MMA issuer ===================================
+        if (lane == 0) {
+            const uint32_t idesc = umma::make_idesc_bf16(128, N);
+            const uint32_t ring0 = umma::smem_u32(sRing), ones0 = umma::smem_u32(sOnes), mid0 = umma::smem_u32(sMid);
+            const uint32_t w1_0 = umma::smem_u32(sW1), w2_0 = umma::smem_u32(sW2);
+            const uint32_t plane = (uint32_t)TW * 16u;
+            const int n_out = h_end - h_start;
+            // halo rows above the strip have no epilogue: stand in for their 128 residual-reader arrivals
+            for (int idx = 0; idx < d; ++idx) mbar_arrive_n(&ring_free[idx % kRing], 128);
+            for (int it = 0; it < n_out + kLag; ++it) {
+                if (it < n_out) {
+                    const int h = h_start + it;
+                    const int u = it / kAcc, a = it % kAcc;
+                    // rows h-d, h, h+d have ring indices it, it+d, it+2d
+                    for (int k = 0; k < 3; ++k) {
+                        const int idx = it + k * d;
+                        umma::mbar_wait(&ring_full[idx % kRing], (uint32_t)((idx / kRing) & 1));
+                    }
+                    if (u > 0) umma::mbar_wait(&acc1_free[a], (uint32_t)((u - 1) & 1));
+                    umma::fence_after_sync();
+                    const uint32_t acc = tmem + (uint32_t)(a * N);
+                    int m = 0;
+                    if constexpr (CG == 1) {
+                        // per tap row: (kx0, kx1) and (kx2, ones)
+                        for (int ky = 0; ky < 3; ++ky) {
+                            const uint32_t row = ring0 + (uint32_t)((it + ky * d) % kRing) * slot_bytes;
+                            const uint64_t da0 = umma::make_desc(row, (uint32_t)d * 16u, 128u);
+                            const uint64_t db0 = umma::make_desc(w1_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
+                            umma::mma_bf16(acc, da0, db0, idesc, m > 0);
+                            ++m;
+                            const uint32_t a2 = row + (uint32_t)(2 * d) * 16u;
+                            // the partner K group is the ones operand: bias weights for ky = 0, zero weights otherwise
+                            // (never an arbitrary neighbour: stale shared memory times zero could be NaN)
+                            const uint64_t da1 = umma::make_desc(a2, ones0 - a2, 128u);
+                            const uint64_t db1 = umma::make_desc(w1_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
+                            umma::mma_bf16(acc, da1, db1, idesc, true);
+                            ++m;
+                        }
+                    } else {
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const uint32_t row = ring0 + (uint32_t)((it + (tap / 3) * d) % kRing) * slot_bytes + (uint32_t)((tap % 3) * d) * 16u;
+                            for (int q = 0; q < CG / 2; ++q) {
+                                const uint64_t da = umma::make_desc(row + (uint32_t)(2 * q) * plane, plane, 128u);
+                                const uint64_t db = umma::make_desc(w1_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
+                                umma::mma_bf16(acc, da, db, idesc, m > 0);
+                                ++m;
+                            }
+                        }
+                        const uint64_t da = umma::make_desc(ones0, 2048u, 128u);
+                        const uint64_t db = umma::make_desc(w1_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
+                        umma::mma_bf16(acc, da, db, idesc, true);
+                    }
+                    umma::commit(&acc1_full[a]);
+                    umma::commit(&ring_free[it % kRing]);            // row h-d: this was its last 3x3 use
+                    (void)h;
+                }
+                const int it2 = it - kLag;
+                if (it2 >= 0) {
+                    const int u = it2 / kAcc, a = it2 % kAcc;
+                    umma::mbar_wait(&mid_full[a], (uint32_t)(u & 1));
+                    umma::fence_after_sync();
+                    const uint32_t acc = tmem + (uint32_t)((kAcc + a) * N);
+                    const uint32_t mid = mid0 + (uint32_t)a * S::kMidSlot;
+                    if constexpr (CG == 1) {
+                        const uint64_t da = umma::make_desc(mid, ones0 - mid, 128u);
+                        const uint64_t db = umma::make_desc(w2_0, N * 16u, 128u);
+                        umma::mma_bf16(acc, da, db, idesc, false);
+                    } else {
+                        int m = 0;
+                        for (int q = 0; q < CG / 2; ++q) {
+                            const uint64_t da = umma::make_desc(mid + (uint32_t)(2 * q) * 2048u, 2048u, 128u);
+                            const uint64_t db = umma::make_desc(w2_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
+                            umma::mma_bf16(acc, da, db, idesc, m > 0);
+                            ++m;
+                        }
+                        const uint64_t da = umma::make_desc(ones0, 2048u, 128u);
+                        const uint64_t db = umma::make_desc(w2_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
+                        umma::mma_bf16(acc, da, db, idesc, true);
+                    }
+                    umma::commit(&acc2_full[a]);
+                }
+            }
+        }
+    } else {
+        // =================================== epilogue groups ===================================
+        const int quad = warp & 3, g = warp >> 2;
+        const int j = quad * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        const bool t_ok = t0 + j < p.T;
+        const int n_out = h_end - h_start;
+        constexpr int NV = NREAL >= 16 ? 16 : NREAL;                  // columns per TMEM load
+        for (int it = g; it < n_out; it += kAcc) {
+            const int u = it / kAcc;
+            const int h = h_start + it;
+            // ---- 3x3 accumulator -> ELU -> bf16 intermediate (A operand of the 1x1 conv) ----
+            umma::mbar_wait(&acc1_full[g], (uint32_t)(u & 1));
+            umma::fence_after_sync();
+            uint8_t* mid = sMid + (size_t)g * S::kMidSlot + (size_t)j * 16u;
+#pragma unroll
+            for (int c0 = 0; c0 < NREAL; c0 += NV) {
+                float v[NV];
+                tmem_load<NV>(lane_addr + (uint32_t)(g * N + c0), v);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) v[k] = elu_f(v[k]);
+#pragma unroll
+                for (int k = 0; k < NV; k += 8) {
+                    uint4 o;
+                    o.x = pack2(v[k], v[k + 1]);
+                    o.y = pack2(v[k + 2], v[k + 3]);
+                    if constexpr (NV >= 8) { o.z = pack2(v[k + 4], v[k + 5]); o.w = pack2(v[k + 6], v[k + 7]); }
+                    else { o.z = 0u; o.w = 0u; }
+                    *reinterpret_cast<uint4*>(mid + (size_t)((c0 + k) >> 3) * 2048u) = o;
+                    if constexpr (NV < 8) break;
+                }
+            }
+            umma::fence_before_sync();
+            mbar_arrive(&acc1_free[g]);
+            umma::fence_proxy_async();
+            mbar_arrive(&mid_full[g]);
+            // ---- 1x1 accumulator -> ELU -> + x -> bf16 -> global ----
+            umma::mbar_wait(&acc2_full[g], (uint32_t)(u & 1));
+            umma::fence_after_sync();
+            const int ridx = it + d;                                   // ring index of row h
+            const uint8_t* res = sRing + (size_t)(ridx % kRing) * slot_bytes + (size_t)(j + d) * 16u;
+#pragma unroll
+            for (int c0 = 0; c0 < NREAL; c0 += NV) {
+                float v[NV];
+                tmem_load<NV>(lane_addr + (uint32_t)((kAcc + g) * N + c0), v);
+#pragma unroll
+                for (int k = 0; k < NV; k += 8) {
+                    const int cg = (c0 + k) >> 3;
+                    const uint4 rx = *reinterpret_cast<const uint4*>(res + (size_t)cg * TW * 16u);
+                    const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rx);
+                    float r[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(rh[e]);
+                        r[2 * e] = f.x;
+                        r[2 * e + 1] = f.y;
+                    }
+                    constexpr int NE = NV >= 8 ? 8 : NV;
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) r[e] += elu_f(v[k + e]);
+                    uint4 o;
+                    o.x = pack2(r[0], r[1]);
+                    o.y = pack2(r[2], r[3]);
+                    if constexpr (NE >= 8) { o.z = pack2(r[4], r[5]); o.w = pack2(r[6], r[7]); }
+                    else { o.z = 0u; o.w = 0u; }
+                    if (t_ok) reinterpret_cast<uint4*>(p.y)[(((size_t)b * CG + cg) * p.H + h) * p.T + t0 + j] = o;
+                    if constexpr (NV < 8) break;
+                }
+            }
+            umma::fence_before_sync();
+            mbar_arrive(&ring_free[ridx % kRing]);
+        }
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+// ---- host ------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// C8 planar activations (B, CG, H, T, 8) bf16 as a 5-D tensor (8, T, H, CG, B); one box = one row: (8, TW, 1, CG, 1)
+static int make_row_map(CUtensorMap* map, const void* x, int B, int CG, int H, int T, int TW) {
+    EncodeTiledFn fn = encode_fn();
+    TT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[5] = {8, (cuuint64_t)T, (cuuint64_t)H, (cuuint64_t)CG, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {16, (cuuint64_t)T * 16, (cuuint64_t)H * T * 16, (cuuint64_t)CG * H * T * 16};
+    const cuuint32_t box[5] = {8, (cuuint32_t)TW, 1, (cuuint32_t)CG, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return TT_OK;
+}
+
+template <int CG, int NREAL>
+static int launch_strip(const CUtensorMap& map, const ResStripParams& p, cudaStream_t stream) {
+    const int smem = StripSmem<CG>::total(p.d);
+    static int configured = 0;
+    if (smem > configured) {
+        TT_CUDA_CHECK(cudaFuncSetAttribute(res_strip_kernel<CG, NREAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    dim3 grid((p.T + kStripTileT - 1) / kStripTileT, (p.H + p.rows_per_strip - 1) / p.rows_per_strip, p.B);
+    res_strip_kernel<CG, NREAL><<<grid, kStripThreads, smem, stream>>>(map, p);
+    TT_CUDA_CHECK(cudaGetLastError());
+    tt_count_launches(1);
+    return TT_OK;
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int tt_res_block_strip(const void* x, void* y, const void* w1, const void* w2, int B, int C, int c_real, int H, int T,
+                                  int dilation, void* stream) {
+    TT_REQUIRE(x && y && w1 && w2, "null argument");
+    TT_REQUIRE(C == 8 || C == 16 || C == 32, "res block: padded channel count must be 8, 16 or 32 (got %d)", C);
+    TT_REQUIRE(dilation >= 1 && dilation <= 3, "dilation must be in [1,3]");
+    TT_REQUIRE(c_real >= 1 && c_real <= C, "bad real channel count");
+    if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
+    ResStripParams p;
+    p.y = (__nv_bfloat16*)y; p.w1 = (const __nv_bfloat16*)w1; p.w2 = (const __nv_bfloat16*)w2;
+    p.B = B; p.H = H; p.T = T; p.d = dilation;
+    // whole-height strips when the batch alone fills the GPU, shorter ones otherwise (each strip re-reads 2d halo rows)
+    const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
+    int rows = H;
+    const int target = 2 * 148;
+    if (tiles < target) {
+        const int splits = (int)std::min<long long>((target + tiles - 1) / tiles, (H + 7) / 8);
+        rows = (H + splits - 1) / splits;
+    }
+    const char* env = getenv("TT_STRIP_ROWS");
+    if (env) rows = std::max(1, atoi(env));
+    p.rows_per_strip = std::min(rows, H);
+    CUtensorMap map;
+    const int CG = C / 8;
+    const int rc = make_row_map(&map, x, B, CG, H, T, kStripTileT + 2 * dilation);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (C == 8) return c_real <= 4 ? launch_strip<1, 4>(map, p, s) : launch_strip<1, 8>(map, p, s);
+    if (C == 16) return launch_strip<2, 16>(map, p, s);
+    return launch_strip<4, 32>(map, p, s);
+}

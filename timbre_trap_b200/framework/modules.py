@@ -59,13 +59,12 @@ class ResidualConv2dBlock(nn.Module):
 
     def _packed(self):
         c1, c2 = self.conv1[0], self.conv2[0]
-        n = _n16(self.channels)
         return self._cache.get((c1.weight, c1.bias, c2.weight, c2.bias),
-                               lambda: (P.pack_res3x3(c1.weight), P.pad_vec(c1.bias, n), P.pack_res1x1(c2.weight), P.pad_vec(c2.bias, n)))
+                               lambda: P.pack_res_strip(c1.weight, c1.bias, c2.weight, c2.bias))
 
     def forward_c8(self, x, out=None):
-        w1, b1, w2, b2 = self._packed()
-        return ops.res_block(x, w1, b1, w2, b2, self.dilation, out=out)
+        w1, w2 = self._packed()
+        return ops.res_block_strip(x, w1, w2, self.channels, self.dilation, out=out)
 
     def forward(self, x):
         """(B, C, H, W) -> (B, C, H, W) fp32 (API parity; the fast paths stay in C8 planar)."""

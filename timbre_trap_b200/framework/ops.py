@@ -88,3 +88,13 @@ def conv_out(x, w, b, c):
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().tt_conv_out(_p(x), _p(y), _p(w), _p(b), B, c, F, T, _s(x)))
     return y
+
+
+def res_block_strip(x, w1, w2, c_real, dilation, out=None):
+    """Row-pipelined fused residual block (csrc/res_strip.cu); weights from packing.pack_res_strip."""
+    _check_c8(x)
+    B, CG, H, T, _ = x.shape
+    y = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_res_block_strip(_p(x), _p(y), _p(w1), _p(w2), B, CG * 8, c_real, H, T, dilation, _s(x)))
+    return y

@@ -12,7 +12,7 @@ The C8 planar activation layout is (B, ceil(C/8), H, T, 8) bf16.
 
 import torch
 
-__all__ = ['pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
+__all__ = ['pack_res_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
            'pad_vec']
 
 
@@ -130,3 +130,43 @@ def pack_deconv_in(w, b, latent_pad):
     bias[0, :, :C0] = b.detach().float()[None, :]
     bias[1, :, :C0] = b.detach().float()[None, :] + wf[D].t()
     return packed, bias
+
+
+def _bias_group(b, N):
+    """(N, 8) K group that, against the kernel's constant (1, 1, 0, ..., 0) operand, adds b as bf16 hi + lo (fp32-accurate)."""
+    g = torch.zeros((N, 8), dtype=torch.float32, device=b.device)
+    bf = b.detach().float()
+    hi = bf.to(torch.bfloat16).float()
+    g[:bf.numel(), 0] = hi
+    g[:bf.numel(), 1] = bf - hi
+    return g
+
+
+def pack_res_strip(w1, b1, w2, b2):
+    """
+    Weights of one ResidualConv2dBlock for csrc/res_strip.cu (biases ride along as an extra K group):
+      C <= 8 : W1 K groups per tap row ky: tap(ky,0), tap(ky,1), tap(ky,2), X_ky with X_0 = bias, X_1 = X_2 = 0  (12 groups);
+               W2 K groups: the 8 input channels, bias                                                          (2 groups)
+      C >= 16: W1 K groups: (tap, channel group) tap-major, then bias, then zeros  (9 C/8 + 2);  W2: channel groups, bias, zeros
+    Returns (w1_packed, w2_packed) in the B-operand layout [K/8][N][8] bf16, N = max(16, C padded to 8).
+    """
+    Co, Ci = w1.shape[:2]
+    Cp = pad8(Ci)
+    N = max(16, Cp)
+    CG = Cp // 8
+    taps = torch.zeros((N, 9, Cp), dtype=torch.float32, device=w1.device)
+    taps[:Co, :, :Ci] = w1.detach().float().permute(0, 2, 3, 1).reshape(Co, 9, Ci)
+    zero = torch.zeros((N, 8), dtype=torch.float32, device=w1.device)
+    if CG == 1:
+        groups = []
+        for ky in range(3):
+            groups += [taps[:, 3 * ky + kx, :] for kx in range(3)]
+            groups.append(_bias_group(b1, N) if ky == 0 else zero)
+    else:
+        groups = [taps[:, t, 8 * g: 8 * g + 8] for t in range(9) for g in range(CG)] + [_bias_group(b1, N), zero]
+    w1p = torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)          # (KG, N, 8)
+    k2 = torch.zeros((N, Cp), dtype=torch.float32, device=w2.device)
+    k2[:Co, :Ci] = w2.detach().float().reshape(Co, Ci)
+    groups2 = [k2[:, 8 * g: 8 * g + 8] for g in range(CG)] + [_bias_group(b2, N)] + ([] if CG == 1 else [zero])
+    w2p = torch.stack(groups2, dim=0).contiguous().to(torch.bfloat16)
+    return w1p, w2p
