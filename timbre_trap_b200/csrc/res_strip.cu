@@ -5,9 +5,9 @@
 //
 //   warp 16 (producer)  one TMA box per input row (all channel groups, 128 + 2d frames, zero-filled outside the image)
 //                       into a 16-slot shared-memory ring; every input row is fetched once per strip (no row halo re-reads)
-//   warp 17 (MMA)       for row h: the 3x3 taps are start-address offsets into the ring slots of rows h-d, h, h+d
-//                       (implicit GEMM, M = 128 frames, N = C, K = 9 C) -> TMEM accumulator acc1[h % 4];
-//                       two rows later the 1x1 conv of row h-2 from the bf16 intermediate in shared memory -> acc2[(h-2) % 4].
+//   warps 17, 18 (3x3)  (even / odd rows) for row h: the 3x3 taps are start-address offsets into the ring slots of rows h-d, h, h+d
+//                       (implicit GEMM, M = 128 frames, N = C, K = 9 C) -> TMEM accumulator acc1[h % 4]
+//   warp 19 (1x1 MMA)   the 1x1 conv of row h from the bf16 intermediate in shared memory -> acc2[h % 4].
 //                       The biases ride along as one extra K group against a constant "ones" operand (bias split into
 //                       bf16 hi + lo, so it is fp32-accurate), which removes the bias adds from the epilogues.
 //   warps 0-15          four epilogue groups (row h -> group h % 4; warp quadrant = TMEM lane quadrant):
@@ -31,9 +31,8 @@ namespace tt {
 
 constexpr int kRing = 16;          // input-row ring slots
 constexpr int kAcc = 4;            // accumulator / intermediate slots = epilogue groups
-constexpr int kLag = 2;            // rows between issuing the 3x3 MMAs of row h and the 1x1 MMAs of row h - kLag
 constexpr int kEpiWarps = 16;
-constexpr int kStripThreads = (kEpiWarps + 2) * 32;
+constexpr int kStripThreads = (kEpiWarps + 4) * 32;   // + producer, two 3x3 MMA issuers (even / odd rows), 1x1 MMA issuer
 constexpr int kStripTileT = 128;
 
 struct ResStripParams {
@@ -62,7 +61,19 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
-__device__ __forceinline__ float elu_f(float v) { return v > 0.f ? v : __expf(v) - 1.f; }
+// ELU with the hardware exp2 directly (ex2.approx.ftz: one MUFU op, no denormal fix-up code)
+__device__ __forceinline__ float elu_f(float v) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+    return v > 0.f ? v : e - 1.f;
+}
+
+// descriptor pieces: the low word holds (address >> 4) in bits 0-13 and (LBO >> 4) in bits 16-29, the high word (SBO >> 4)
+// in bits 0-13 and the version bit 14; shared-memory addresses stay below 2^18, so adding (delta >> 4) to a low word moves
+// the start address without touching the LBO field
+__device__ __forceinline__ uint32_t desc_lo(uint32_t addr, uint32_t lbo) { return ((addr >> 4) & 0x3FFFu) | (((lbo >> 4) & 0x3FFFu) << 16); }
+constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);     // SBO = 128 B, version 1
+__device__ __forceinline__ uint64_t desc64(uint32_t lo) { return ((uint64_t)kDescHi << 32) | lo; }
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __gri
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
     uint64_t* ring_full = bars;                 // [kRing]  TMA landed
-    uint64_t* ring_free = bars + kRing;         // [kRing]  1 commit (last 3x3 user) + 128 residual readers
+    uint64_t* ring_free = bars + kRing;         // [kRing]  3 commits (the 3x3 MMAs of the three rows using it) + 128 residual readers
     uint64_t* acc1_full = bars + 2 * kRing;     // [kAcc]
     uint64_t* acc1_free = acc1_full + kAcc;     // [kAcc]   128 arrivals
     uint64_t* mid_full = acc1_free + kAcc;      // [kAcc]   128 arrivals
@@ -144,7 +155,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __gri
     if (tid == 32) {
         for (int i = 0; i < kRing; ++i) {
             umma::mbar_init(&ring_full[i], 1);
-            umma::mbar_init(&ring_free[i], 129);
+            umma::mbar_init(&ring_free[i], 131);
         }
         for (int i = 0; i < kAcc; ++i) {
             umma::mbar_init(&acc1_full[i], 1);
@@ -177,89 +188,99 @@ __global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __gri
                 tma_load_5d(sRing + (size_t)slot * slot_bytes, &tmap_x, &ring_full[slot], 0, t0 - d, first_row + idx, 0, b);
             }
         }
-    } else if (warp == kEpiWarps + 1) {
-        // =================================== MMA issuer ===================================
-        if (lane == 0) {
-            const uint32_t idesc = umma::make_idesc_bf16(128, N);
-            const uint32_t ring0 = umma::smem_u32(sRing), ones0 = umma::smem_u32(sOnes), mid0 = umma::smem_u32(sMid);
-            const uint32_t w1_0 = umma::smem_u32(sW1), w2_0 = umma::smem_u32(sW2);
-            const uint32_t plane = (uint32_t)TW * 16u;
-            const int n_out = h_end - h_start;
-            // halo rows above the strip have no epilogue: stand in for their 128 residual-reader arrivals
+    } else if (warp == kEpiWarps + 1 || warp == kEpiWarps + 2) {
+        // =================================== 3x3 MMA issuers (rows it = par, par + 2, ...) ===================================
+        // The whole warp runs the loop (warp-uniform control flow and descriptor arithmetic); one lane issues.
+        const int par = warp - (kEpiWarps + 1);
+        const bool issuer = lane == 0;
+        const uint32_t idesc = umma::make_idesc_bf16(128, N);
+        const uint32_t ring0 = umma::smem_u32(sRing), ones0 = umma::smem_u32(sOnes), w1_0 = umma::smem_u32(sW1);
+        const uint32_t plane = (uint32_t)TW * 16u;
+        const int n_out = h_end - h_start;
+        const uint32_t b_lo0 = desc_lo(w1_0, N * 16u), b_step = (2u * N * 16u) >> 4;
+        if (par == 0 && issuer) {
+            // ring row r is released by 131 arrivals: the commits of the 3x3 MMAs of output rows r, r-d, r-2d (ring indices) and the
+            // 128 residual readers of its own epilogue.  Rows near the top of the strip lack some of those users: stand in for them.
             for (int idx = 0; idx < d; ++idx) mbar_arrive_n(&ring_free[idx % kRing], 128);
-            for (int it = 0; it < n_out + kLag; ++it) {
-                if (it < n_out) {
-                    const int h = h_start + it;
-                    const int u = it / kAcc, a = it % kAcc;
-                    // rows h-d, h, h+d have ring indices it, it+d, it+2d
-                    for (int k = 0; k < 3; ++k) {
-                        const int idx = it + k * d;
-                        umma::mbar_wait(&ring_full[idx % kRing], (uint32_t)((idx / kRing) & 1));
-                    }
-                    if (u > 0) umma::mbar_wait(&acc1_free[a], (uint32_t)((u - 1) & 1));
-                    umma::fence_after_sync();
-                    const uint32_t acc = tmem + (uint32_t)(a * N);
-                    int m = 0;
-                    if constexpr (CG == 1) {
-                        // per tap row: (kx0, kx1) and (kx2, ones)
-                        for (int ky = 0; ky < 3; ++ky) {
-                            const uint32_t row = ring0 + (uint32_t)((it + ky * d) % kRing) * slot_bytes;
-                            const uint64_t da0 = umma::make_desc(row, (uint32_t)d * 16u, 128u);
-                            const uint64_t db0 = umma::make_desc(w1_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
-                            umma::mma_bf16(acc, da0, db0, idesc, m > 0);
-                            ++m;
-                            const uint32_t a2 = row + (uint32_t)(2 * d) * 16u;
-                            // the partner K group is the ones operand: bias weights for ky = 0, zero weights otherwise
-                            // (never an arbitrary neighbour: stale shared memory times zero could be NaN)
-                            const uint64_t da1 = umma::make_desc(a2, ones0 - a2, 128u);
-                            const uint64_t db1 = umma::make_desc(w1_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
-                            umma::mma_bf16(acc, da1, db1, idesc, true);
-                            ++m;
-                        }
-                    } else {
-                        for (int tap = 0; tap < 9; ++tap) {
-                            const uint32_t row = ring0 + (uint32_t)((it + (tap / 3) * d) % kRing) * slot_bytes + (uint32_t)((tap % 3) * d) * 16u;
-                            for (int q = 0; q < CG / 2; ++q) {
-                                const uint64_t da = umma::make_desc(row + (uint32_t)(2 * q) * plane, plane, 128u);
-                                const uint64_t db = umma::make_desc(w1_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
-                                umma::mma_bf16(acc, da, db, idesc, m > 0);
-                                ++m;
-                            }
-                        }
-                        const uint64_t da = umma::make_desc(ones0, 2048u, 128u);
-                        const uint64_t db = umma::make_desc(w1_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
-                        umma::mma_bf16(acc, da, db, idesc, true);
-                    }
-                    umma::commit(&acc1_full[a]);
-                    umma::commit(&ring_free[it % kRing]);            // row h-d: this was its last 3x3 use
-                    (void)h;
-                }
-                const int it2 = it - kLag;
-                if (it2 >= 0) {
-                    const int u = it2 / kAcc, a = it2 % kAcc;
-                    umma::mbar_wait(&mid_full[a], (uint32_t)(u & 1));
-                    umma::fence_after_sync();
-                    const uint32_t acc = tmem + (uint32_t)((kAcc + a) * N);
-                    const uint32_t mid = mid0 + (uint32_t)a * S::kMidSlot;
-                    if constexpr (CG == 1) {
-                        const uint64_t da = umma::make_desc(mid, ones0 - mid, 128u);
-                        const uint64_t db = umma::make_desc(w2_0, N * 16u, 128u);
-                        umma::mma_bf16(acc, da, db, idesc, false);
-                    } else {
-                        int m = 0;
-                        for (int q = 0; q < CG / 2; ++q) {
-                            const uint64_t da = umma::make_desc(mid + (uint32_t)(2 * q) * 2048u, 2048u, 128u);
-                            const uint64_t db = umma::make_desc(w2_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
-                            umma::mma_bf16(acc, da, db, idesc, m > 0);
-                            ++m;
-                        }
-                        const uint64_t da = umma::make_desc(ones0, 2048u, 128u);
-                        const uint64_t db = umma::make_desc(w2_0 + (uint32_t)m * 2u * N * 16u, N * 16u, 128u);
-                        umma::mma_bf16(acc, da, db, idesc, true);
-                    }
-                    umma::commit(&acc2_full[a]);
-                }
+            for (int v = -2 * d; v < 0; ++v)
+                for (int k = 0; k < 3; ++k)
+                    if (v + k * d >= 0) mbar_arrive(&ring_free[(v + k * d) % kRing]);
+        }
+        for (int it = par; it < n_out; it += 2) {
+            const int u = it / kAcc, a = it % kAcc;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int idx = it + k * d;
+                umma::mbar_wait(&ring_full[idx % kRing], (uint32_t)((idx / kRing) & 1));
             }
+            if (u > 0) umma::mbar_wait(&acc1_free[a], (uint32_t)((u - 1) & 1));
+            umma::fence_after_sync();
+            const uint32_t acc = tmem + (uint32_t)(a * N);
+            uint32_t b_lo = b_lo0;
+            if constexpr (CG == 1) {
+                // per tap row: (kx0, kx1) and (kx2, ones); the ones operand carries the bias for ky = 0 and meets zero
+                // weights otherwise (never an arbitrary neighbour: stale shared memory times zero could be NaN)
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t row = ring0 + (uint32_t)((it + ky * d) % kRing) * slot_bytes;
+                    const uint32_t a2 = row + (uint32_t)(2 * d) * 16u;
+                    if (issuer) {
+                        umma::mma_bf16(acc, desc64(desc_lo(row, (uint32_t)d * 16u)), desc64(b_lo), idesc, ky > 0);
+                        umma::mma_bf16(acc, desc64(desc_lo(a2, ones0 - a2)), desc64(b_lo + b_step), idesc, true);
+                    }
+                    b_lo += 2 * b_step;
+                }
+            } else {
+                const uint32_t a_lbo = ((plane >> 4) & 0x3FFFu) << 16;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const uint32_t row_lo = (((ring0 + (uint32_t)((it + ky * d) % kRing) * slot_bytes) >> 4) & 0x3FFFu) | a_lbo;
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                        for (int q = 0; q < CG / 2; ++q) {
+                            if (issuer)
+                                umma::mma_bf16(acc, desc64(row_lo + (uint32_t)(kx * d) + (uint32_t)(2 * q) * (plane >> 4)), desc64(b_lo), idesc,
+                                               (ky | kx | q) != 0);
+                            b_lo += b_step;
+                        }
+                    }
+                }
+                if (issuer) umma::mma_bf16(acc, desc64(desc_lo(ones0, 2048u)), desc64(b_lo), idesc, true);
+            }
+            if (issuer) {
+                umma::commit(&acc1_full[a]);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) umma::commit(&ring_free[(it + k * d) % kRing]);
+            }
+            __syncwarp();
+        }
+    } else if (warp == kEpiWarps + 3) {
+        // =================================== 1x1 MMA issuer ===================================
+        const bool issuer = lane == 0;
+        const uint32_t idesc = umma::make_idesc_bf16(128, N);
+        const uint32_t ones0 = umma::smem_u32(sOnes), mid0 = umma::smem_u32(sMid), w2_0 = umma::smem_u32(sW2);
+        const uint32_t b_lo0 = desc_lo(w2_0, N * 16u), b_step = (2u * N * 16u) >> 4;
+        const int n_out = h_end - h_start;
+        for (int it = 0; it < n_out; ++it) {
+            const int u = it / kAcc, a = it % kAcc;
+            umma::mbar_wait(&mid_full[a], (uint32_t)(u & 1));
+            umma::fence_after_sync();
+            const uint32_t acc = tmem + (uint32_t)((kAcc + a) * N);
+            const uint32_t mid = mid0 + (uint32_t)a * S::kMidSlot;
+            if (issuer) {
+                if constexpr (CG == 1) {
+                    umma::mma_bf16(acc, desc64(desc_lo(mid, ones0 - mid)), desc64(b_lo0), idesc, false);
+                } else {
+                    const uint32_t a_lo = desc_lo(mid, 2048u);
+#pragma unroll
+                    for (int q = 0; q < CG / 2; ++q)
+                        umma::mma_bf16(acc, desc64(a_lo + (uint32_t)(2 * q) * (2048u >> 4)), desc64(b_lo0 + (uint32_t)q * b_step), idesc, q > 0);
+                    umma::mma_bf16(acc, desc64(desc_lo(ones0, 2048u)), desc64(b_lo0 + (uint32_t)(CG / 2) * b_step), idesc, true);
+                }
+                umma::commit(&acc2_full[a]);
+            }
+            __syncwarp();
         }
     } else {
         // =================================== epilogue groups ===================================
