@@ -1,0 +1,102 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol, the product's filter-bank
+tables equal the oracle's, module/state_dict structure matches the reference, chunk slicing matches the reference loop."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    from timbre_trap_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'timbre_trap_b200.h')).read()
+    declared = set(re.findall(r'\b(tt_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(handle, name), f'{name} declared in the header but not exported'
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert _lib.lib().tt_version() == 1
+
+
+@pytest.mark.parametrize('cfg', [(9, 60, 22050, 3), (6, 12, 8000, 0.5), (8, 24, 16000, 1.0), (7, 36, 44100, 1.5)])
+def test_filter_bank_matches_oracle(cfg):
+    from oracle.nsgt_ref import make_tables
+    from timbre_trap_b200.nsgt_tables import FilterBank
+    a, b = FilterBank(cfg[0], cfg[1], cfg[2], int(cfg[3] * cfg[2])), make_tables(*cfg)
+    assert a.max_window_length == b.max_window_length and a.n_taps == b.n_taps
+    for k in ('start', 'length', 'first', 'offset'):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.abs(a.win - b.win_packed).max() < 1e-7
+    assert np.abs(a.dual - b.dual_packed).max() <= 1e-7 * b.dual_packed.max()
+
+
+def test_geometry_and_state_dict_match_reference(golden_dir):
+    from oracle import model_ref as R
+    from timbre_trap_b200.framework import CQT, TimbreTrap
+    geo = json.load(open(os.path.join(golden_dir, 'geometry.json')))
+    for g in geo.values():
+        cfg = g['cfg']
+        c = CQT(cfg['n_octaves'], cfg['bins_per_octave'], cfg['sample_rate'], cfg['secs_per_block'])
+        assert (c.block_length, c.max_window_length, c.n_bins, c.hop_length) == (g['block_length'], g['max_window_length'], g['n_bins'], g['hop_length'])
+        assert abs(c.midi_freqs[0] - g['midi_first']) < 1e-9 and abs(c.get_midi_freqs()[-1] - g['midi_last']) < 1e-9
+        for p, v in g['expected_frames'].items():
+            assert c.get_expected_frames(int(p)) == v
+        for t, v in g['expected_samples'].items():
+            assert c.get_expected_samples(float(t)) == v
+        for p, v in g['padded_len'].items():
+            assert c.pad_to_block_length(torch.zeros(1, 1, int(p))).size(-1) == v
+        np.testing.assert_allclose(c.get_times(6), g['times_head'], rtol=1e-12)
+    m = TimbreTrap(22050, 9, 60, 3, latent_size=128, model_complexity=2)
+    sd = R.init_state_dict(540, 128, 2, 0)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    assert sum(p.numel() for p in m.parameters()) == 614490
+    # reference checkpoints carry cqt_pytorch's buffers under sliCQ.*: accepted and dropped
+    sd2 = dict(sd)
+    sd2['sliCQ.windows'] = torch.zeros(540, 1024)
+    sd2['sliCQ.windows_range_indices'] = torch.zeros(540, 1024, dtype=torch.long)
+    m.load_state_dict(sd2)
+    ms = TimbreTrap(22050, 9, 60, 3, skip_connections=True)
+    assert 'skip_weights' in ms.state_dict() and ms.sliCQ.n_bins == 540
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from timbre_trap_b200._lib import TimbreTrapB200Error
+    from timbre_trap_b200.framework import TimbreTrap
+    m = TimbreTrap(8000, 6, 12, 0.5)
+    with pytest.raises(TimbreTrapB200Error):
+        m.transcribe(torch.zeros(1, 1, 4000))
+    with pytest.raises(TimbreTrapB200Error):
+        m.sliCQ(torch.zeros(1, 1, 4000))
+
+
+def test_chunk_slicing_matches_reference_loop():
+    """TimbreTrap._chunks must produce exactly the slices of modules.py:226-253."""
+    from timbre_trap_b200.framework import TimbreTrap
+    m = TimbreTrap(8000, 6, 12, 0.5)
+    L = m.sliCQ.block_length
+    audio = torch.arange(2 * int(2.3 * L), dtype=torch.float32).reshape(2, 1, -1)
+    chunks, n_chunks = m._chunks(audio)
+    padded = torch.nn.functional.pad(m.sliCQ.pad_to_block_length(audio), [L // 2] * 2)
+    assert n_chunks == (padded.size(-1) - L // 2) // (L // 2) == 7
+    for b in range(2):
+        for i in range(n_chunks):
+            assert torch.equal(chunks[b * n_chunks + i, 0], padded[b, 0, i * (L // 2): i * (L // 2) + L])
+
+
+def test_weight_packing_shapes():
+    from timbre_trap_b200.framework import packing as P
+    for C, kg1, kg2, n in ((4, 12, 2, 16), (8, 12, 2, 16), (16, 20, 4, 16), (32, 38, 6, 32)):
+        w1, w2 = P.pack_res_strip(torch.randn(C, C, 3, 3), torch.randn(C), torch.randn(C, C, 1, 1), torch.randn(C))
+        assert tuple(w1.shape) == (kg1, n, 8) and tuple(w2.shape) == (kg2, n, 8) and w1.dtype == torch.bfloat16
+    w, b = torch.randn(129, 64, 31, 1), torch.randn(64)
+    packed, tables = P.pack_deconv_in(w, b, 128)
+    assert tuple(packed.shape) == (31, 16, 64, 8) and tuple(tables.shape) == (2, 31, 64)
+    assert torch.allclose(tables[1] - tables[0], w[128, :, :, 0].t(), atol=1e-6)
+    x = torch.randn(2, 5, 7, 16)
+    assert torch.equal(P.from_c8(P.to_c8(x), 5), x.to(torch.bfloat16).float())

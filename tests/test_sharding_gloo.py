@@ -1,0 +1,42 @@
+"""
+World-size-2 (gloo, CPU) check of the sharded `reconstruct` normalisation: every rank synthesises its shard WITHOUT
+normalising, the per-rank peaks are MAX-all-reduced, each rank scales locally - the result must equal the reference's
+batch-global `audio /= audio.abs().max()` (cqtwrapper.py:209-211).  Uses the CPU oracle for the synthesis; the GPU
+path runs the identical three steps (TimbreTrap._decode_shared_peak) over NCCL.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oracle.model_ref import CQTRef
+    from tests.helpers import tonal_clip
+    cqt = CQTRef(6, 12, 8000, 0.5)
+    audio = tonal_clip(2 * cqt.block_length, 8000, seed=3, n_batch=4) * torch.tensor([0.2, 1.0, 0.5, 0.7]).view(4, 1, 1)
+    coeffs = cqt(audio)
+    shard = coeffs[rank * 2:(rank + 1) * 2]                        # block sharding: 2 items per rank
+    raw = cqt.decode_raw(shard)
+    peak = raw.abs().max().reshape(1)
+    dist.all_reduce(peak, op=dist.ReduceOp.MAX)
+    local = raw / peak if float(peak) else raw
+    want = cqt.decode(coeffs)[rank * 2:(rank + 1) * 2]             # the reference semantics on the whole batch
+    np.save(os.path.join(out_dir, f'err{rank}.npy'), np.array([float((local - want).abs().max()), float(local.abs().max())]))
+    dist.destroy_process_group()
+
+
+def test_sharded_peak_normalise_equals_global(tmp_path):
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    errs = [np.load(os.path.join(tmp_path, f'err{r}.npy')) for r in range(2)]
+    assert max(e[0] for e in errs) < 1e-6
+    assert abs(max(e[1] for e in errs) - 1.0) < 1e-6               # exactly one shard holds the global peak
