@@ -130,6 +130,18 @@ int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, 
 int tt_conv_out(const void* x, float* coeffs, const float* w, const float* bias, int B, int C, int H, int T, void* stream);
 
 /*
+ * ---- objectives (timbre_trap/framework/objectives.py), deterministic two-stage reductions ------------------------
+ * scratch: tt_loss_scratch_floats() floats of device memory.
+ */
+int tt_loss_scratch_floats(void);
+/* compute_reconstruction_loss / compute_consistency_loss (objectives.py:11-33, 77-104): *out = scale * sum((a-b)^2);
+ * the caller passes scale = 1 / (B*T) (sum over C and F, mean over B and T).  a, b: same memory order, n floats. */
+int tt_sum_sq_diff(const float* a, const float* b, int64_t n, double scale, float* out, float* scratch, void* stream);
+/* compute_transcription_loss (objectives.py:36-74): estimate, target (B, F, T) contiguous fp32 */
+int tt_transcription_loss(const float* estimate, const float* target, int B, int F, int T, int weight_positive_class,
+                          float* out, float* scratch, void* stream);
+
+/*
  * Self-test of the tcgen05 / TMEM plumbing the conv kernels are built on (no reference counterpart):
  * D (128 x n, fp32) = A (128 x k, bf16, row-major) * B (n x k, bf16, row-major)^T on one CTA.
  * swap_lbo_sbo = 1 encodes the shared-memory descriptors with the two stride fields exchanged (must FAIL).

@@ -1,7 +1,9 @@
 """Mirror of `timbre_trap.framework` (reference: timbre_trap/framework/__init__.py:1-4)."""
 
+from .objectives import *       # noqa: F401,F403
+from .objectives import __all__ as _objectives_all
 from .cqt import CQT
 from .modules import *          # noqa: F401,F403
 from .modules import __all__ as _modules_all
 
-__all__ = ['CQT'] + list(_modules_all)
+__all__ = list(_objectives_all) + ['CQT'] + list(_modules_all)
