@@ -61,7 +61,7 @@ namespace tt {
 constexpr int kColsPerCta = 14;   // A1 / S3: real columns per CTA (even: two per complex transform)
 constexpr int kRowsPerCta = 16;   // A2 / S2: rows per CTA (16 complex = 128 B runs in S)
 constexpr int kFftThreads = 256;
-constexpr int kBinWarps = 8;      // A3 / S1: warps (= bins) per CTA
+constexpr int kBinWarps = 4;      // A3 / S1: warps (= bins) per CTA (small CTAs: 5 per SM at 88 registers)
 
 // ---------------------------------------------------------------------------------------------
 // A1: forward column transforms
@@ -589,7 +589,11 @@ struct tt_cqt_plan {
     float *d_win, *d_dual;
     float2 *d_tw_n1, *d_tw_n2, *d_tw_L, *d_tw_m_inv, *d_tw_m_fwd;
     // scratch
-    float2 *d_T, *d_S;
+    // two scratch sets + two internal streams: consecutive groups of blocks run on alternating lanes, so the FFT front end of
+    // group g+1 overlaps the HBM-bound per-bin kernel of group g
+    float2 *d_T[2], *d_S[2];
+    cudaStream_t lane[2];
+    cudaEvent_t ev_start, ev_done[2];
     int64_t scratch_bytes;
 };
 
@@ -698,9 +702,14 @@ extern "C" int tt_cqt_plan_create(tt_cqt_plan** out, int block_length, int n_bin
 
     const size_t t_bytes = (size_t)p->max_blocks * p->K1 * p->N2 * sizeof(float2);
     const size_t s_bytes = (size_t)p->max_blocks * p->SP * sizeof(float2);
-    TT_CUDA_CHECK(cudaMalloc((void**)&p->d_T, t_bytes));
-    TT_CUDA_CHECK(cudaMalloc((void**)&p->d_S, s_bytes));
-    p->scratch_bytes = (int64_t)(t_bytes + s_bytes);
+    for (int i = 0; i < 2; ++i) {
+        TT_CUDA_CHECK(cudaMalloc((void**)&p->d_T[i], t_bytes));
+        TT_CUDA_CHECK(cudaMalloc((void**)&p->d_S[i], s_bytes));
+        TT_CUDA_CHECK(cudaStreamCreateWithFlags(&p->lane[i], cudaStreamNonBlocking));
+        TT_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
+    }
+    TT_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
+    p->scratch_bytes = (int64_t)(2 * (t_bytes + s_bytes));
 
     TT_REQUIRE(cols_smem(p) <= 200 * 1024 && rows_smem(p) <= 200 * 1024, "block_length %d needs too much shared memory", L);
     TT_CUDA_CHECK(cudaFuncSetAttribute(cols_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem(p)));
@@ -723,7 +732,12 @@ extern "C" int tt_cqt_plan_destroy(tt_cqt_plan* p) {
     cudaFree(p->d_start); cudaFree(p->d_length); cudaFree(p->d_first); cudaFree(p->d_offset);
     cudaFree(p->d_win); cudaFree(p->d_dual);
     cudaFree(p->d_tw_n1); cudaFree(p->d_tw_n2); cudaFree(p->d_tw_L); cudaFree(p->d_tw_m_inv); cudaFree(p->d_tw_m_fwd);
-    cudaFree(p->d_T); cudaFree(p->d_S);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(p->d_T[i]); cudaFree(p->d_S[i]);
+        if (p->lane[i]) cudaStreamDestroy(p->lane[i]);
+        if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
+    }
+    if (p->ev_start) cudaEventDestroy(p->ev_start);
     delete p;
     return TT_OK;
 }
@@ -740,31 +754,41 @@ static BinTables bin_tables(const tt_cqt_plan* p) {
 extern "C" int tt_cqt_forward(tt_cqt_plan* p, const float* audio, int batch, int n_blocks, float* coeffs, void* stream_) {
     TT_REQUIRE(p && audio && coeffs, "null argument");
     TT_REQUIRE(batch >= 0 && n_blocks >= 0, "negative sizes");
-    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaStream_t user = (cudaStream_t)stream_;
     const long long total = (long long)batch * n_blocks;
     const BinTables tab = bin_tables(p);
-    for (long long b0 = 0; b0 < total; b0 += p->max_blocks) {
+    if (total == 0) return TT_OK;
+    const int n_groups = (int)((total + p->max_blocks - 1) / p->max_blocks);
+    const int n_lanes = n_groups > 1 ? 2 : 1;
+    TT_CUDA_CHECK(cudaEventRecord(p->ev_start, user));
+    for (int i = 0; i < n_lanes; ++i) TT_CUDA_CHECK(cudaStreamWaitEvent(p->lane[i], p->ev_start, 0));
+    int g = 0;
+    for (long long b0 = 0; b0 < total; b0 += p->max_blocks, ++g) {
         const int nb = (int)std::min<long long>(p->max_blocks, total - b0);
+        cudaStream_t stream = p->lane[g & 1];
+        float2 *T = p->d_T[g & 1], *S = p->d_S[g & 1];
         dim3 g1((p->N2 + kColsPerCta - 1) / kColsPerCta, nb);
-        cols_fwd_kernel<<<g1, kFftThreads, cols_smem(p), stream>>>(audio + (size_t)b0 * p->L, p->d_T, p->spec_n1, p->N2,
+        cols_fwd_kernel<<<g1, kFftThreads, cols_smem(p), stream>>>(audio + (size_t)b0 * p->L, T, p->spec_n1, p->N2,
                                                                     p->K1, p->L, p->d_tw_n1, p->d_tw_L);
         dim3 g2((p->K1 + kRowsPerCta - 1) / kRowsPerCta, nb);
-        rows_fwd_kernel<<<g2, kFftThreads, rows_smem(p), stream>>>(p->d_T, p->d_S, p->spec_n2, p->N1, p->K1, p->L, p->SP,
-                                                                    p->d_tw_n2);
+        rows_fwd_kernel<<<g2, kFftThreads, rows_smem(p), stream>>>(T, S, p->spec_n2, p->N1, p->K1, p->L, p->SP, p->d_tw_n2);
         if (p->M == 1024) {
             const long long warps = (long long)nb * p->F;
             const unsigned g3 = (unsigned)((warps + kBinWarps - 1) / kBinWarps);
-            bins_fwd_kernel<<<g3, kBinWarps * 32, bins_smem(), stream>>>(p->d_S, coeffs, tab, p->F, p->SP, n_blocks,
-                                                                          (int)b0, nb, p->d_tw_m_inv);
+            bins_fwd_kernel<<<g3, kBinWarps * 32, bins_smem(), stream>>>(S, coeffs, tab, p->F, p->SP, n_blocks, (int)b0, nb,
+                                                                          p->d_tw_m_inv);
         } else {
             dim3 g3(p->F, nb);
-            bins_fwd_generic_kernel<<<g3, 128, 3 * p->M * sizeof(float2), stream>>>(p->d_S, coeffs, tab, p->F, p->SP,
-                                                                                     n_blocks, (int)b0, p->spec_m,
-                                                                                     p->d_tw_m_fwd);
+            bins_fwd_generic_kernel<<<g3, 128, 3 * p->M * sizeof(float2), stream>>>(S, coeffs, tab, p->F, p->SP, n_blocks,
+                                                                                     (int)b0, p->spec_m, p->d_tw_m_fwd);
         }
         tt_count_launches(3);
     }
     TT_CUDA_CHECK(cudaGetLastError());
+    for (int i = 0; i < n_lanes; ++i) {
+        TT_CUDA_CHECK(cudaEventRecord(p->ev_done[i], p->lane[i]));
+        TT_CUDA_CHECK(cudaStreamWaitEvent(user, p->ev_done[i], 0));
+    }
     return TT_OK;
 }
 
@@ -783,33 +807,44 @@ extern "C" int tt_cqt_inverse(tt_cqt_plan* p, const float* coeffs, int batch, in
                               int normalise, void* stream_) {
     TT_REQUIRE(p && coeffs && audio && peak, "null argument");
     TT_REQUIRE(batch >= 0 && n_blocks >= 0, "negative sizes");
-    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaStream_t user = (cudaStream_t)stream_;
     const long long total = (long long)batch * n_blocks;
     const BinTables tab = bin_tables(p);
-    TT_CUDA_CHECK(cudaMemsetAsync(peak, 0, sizeof(float), stream));
-    for (long long b0 = 0; b0 < total; b0 += p->max_blocks) {
+    TT_CUDA_CHECK(cudaMemsetAsync(peak, 0, sizeof(float), user));
+    if (total == 0) return TT_OK;
+    const int n_groups = (int)((total + p->max_blocks - 1) / p->max_blocks);
+    const int n_lanes = n_groups > 1 ? 2 : 1;
+    TT_CUDA_CHECK(cudaEventRecord(p->ev_start, user));
+    for (int i = 0; i < n_lanes; ++i) TT_CUDA_CHECK(cudaStreamWaitEvent(p->lane[i], p->ev_start, 0));
+    int g = 0;
+    for (long long b0 = 0; b0 < total; b0 += p->max_blocks, ++g) {
         const int nb = (int)std::min<long long>(p->max_blocks, total - b0);
-        TT_CUDA_CHECK(cudaMemsetAsync(p->d_S, 0, (size_t)nb * p->SP * sizeof(float2), stream));
+        cudaStream_t stream = p->lane[g & 1];
+        float2 *T = p->d_T[g & 1], *S = p->d_S[g & 1];
+        TT_CUDA_CHECK(cudaMemsetAsync(S, 0, (size_t)nb * p->SP * sizeof(float2), stream));
         if (p->M == 1024) {
             const long long warps = (long long)nb * p->F;
             const unsigned g1 = (unsigned)((warps + kBinWarps - 1) / kBinWarps);
-            bins_inv_kernel<<<g1, kBinWarps * 32, bins_smem(), stream>>>(coeffs, p->d_S, tab, p->F, p->SP, n_blocks,
-                                                                          (int)b0, nb, p->d_tw_m_inv);
+            bins_inv_kernel<<<g1, kBinWarps * 32, bins_smem(), stream>>>(coeffs, S, tab, p->F, p->SP, n_blocks, (int)b0, nb,
+                                                                          p->d_tw_m_inv);
         } else {
             dim3 g1(p->F, nb);
-            bins_inv_generic_kernel<<<g1, 128, 3 * p->M * sizeof(float2), stream>>>(coeffs, p->d_S, tab, p->F, p->SP,
-                                                                                     n_blocks, (int)b0, p->spec_m,
-                                                                                     p->d_tw_m_fwd);
+            bins_inv_generic_kernel<<<g1, 128, 3 * p->M * sizeof(float2), stream>>>(coeffs, S, tab, p->F, p->SP, n_blocks,
+                                                                                     (int)b0, p->spec_m, p->d_tw_m_fwd);
         }
         dim3 g2((p->K1 + kRowsPerCta - 1) / kRowsPerCta, nb);
-        rows_inv_kernel<<<g2, kFftThreads, rows_smem(p), stream>>>(p->d_S, p->d_T, p->spec_n2, p->N1, p->K1, p->L, p->SP,
-                                                                    p->d_tw_n2, p->d_tw_L);
+        rows_inv_kernel<<<g2, kFftThreads, rows_smem(p), stream>>>(S, T, p->spec_n2, p->N1, p->K1, p->L, p->SP, p->d_tw_n2,
+                                                                    p->d_tw_L);
         dim3 g3((p->N2 + kColsPerCta - 1) / kColsPerCta, nb);
-        cols_inv_kernel<<<g3, kFftThreads, cols_smem(p), stream>>>(p->d_T, audio + (size_t)b0 * p->L, p->spec_n1, p->N2,
-                                                                    p->K1, p->L, p->d_tw_n1, (unsigned int*)peak);
+        cols_inv_kernel<<<g3, kFftThreads, cols_smem(p), stream>>>(T, audio + (size_t)b0 * p->L, p->spec_n1, p->N2, p->K1, p->L,
+                                                                    p->d_tw_n1, (unsigned int*)peak);
         tt_count_launches(3);
     }
     TT_CUDA_CHECK(cudaGetLastError());
+    for (int i = 0; i < n_lanes; ++i) {
+        TT_CUDA_CHECK(cudaEventRecord(p->ev_done[i], p->lane[i]));
+        TT_CUDA_CHECK(cudaStreamWaitEvent(user, p->ev_done[i], 0));
+    }
     if (normalise) return tt_scale_by_peak(audio, total * p->L, peak, stream_);
     return TT_OK;
 }
