@@ -5,9 +5,9 @@
 //
 //   warp 16 (producer)  one TMA box per input row (all channel groups, 128 + 2d frames, zero-filled outside the image)
 //                       into a 16-slot shared-memory ring; every input row is fetched once per strip (no row halo re-reads)
-//   warps 17, 18 (3x3)  (even / odd rows) for row h: the 3x3 taps are start-address offsets into the ring slots of rows h-d, h, h+d
+//   warps 17-20 (3x3)   (row h -> issuer h % 4) for row h: the 3x3 taps are start-address offsets into the ring slots of rows h-d, h, h+d
 //                       (implicit GEMM, M = 128 frames, N = C, K = 9 C) -> TMEM accumulator acc1[h % 4]
-//   warp 19 (1x1 MMA)   the 1x1 conv of row h from the bf16 intermediate in shared memory -> acc2[h % 4].
+//   warps 21-22 (1x1)   the 1x1 conv of row h from the bf16 intermediate in shared memory -> acc2[h % 4].
 //                       The biases ride along as one extra K group against a constant "ones" operand (bias split into
 //                       bf16 hi + lo, so it is fp32-accurate), which removes the bias adds from the epilogues.
 //   warps 0-15          four epilogue groups (row h -> group h % 4; warp quadrant = TMEM lane quadrant):
@@ -29,10 +29,14 @@
 
 namespace tt {
 
-constexpr int kRing = 16;          // input-row ring slots
-constexpr int kAcc = 4;            // accumulator / intermediate slots = epilogue groups
+constexpr int kGroups = 4;         // epilogue warp groups (row it -> group it % 4)
 constexpr int kEpiWarps = 16;
-constexpr int kStripThreads = (kEpiWarps + 4) * 32;   // + producer, two 3x3 MMA issuers (even / odd rows), 1x1 MMA issuer
+// Warps issuing the 3x3 MMAs (row it -> issuer it % kIssuers1).  The waits, descriptor arithmetic and commits of one row cost
+// ~1500 cycles of a single warp's time - far more than the tensor pipe needs for the MMAs themselves - so the issue work is
+// spread over several warps; small-C layers (cheap rows, many of them) get more.
+template <int CG> constexpr int issuers1() { return CG == 1 ? 8 : 4; }
+constexpr int kIssuers2 = 2;       // warps issuing the 1x1 MMAs
+template <int CG> constexpr int strip_threads() { return (kEpiWarps + 1 + issuers1<CG>() + kIssuers2) * 32; }
 constexpr int kStripTileT = 128;
 
 struct ResStripParams {
@@ -104,25 +108,35 @@ __device__ __forceinline__ void tmem_load(uint32_t taddr, float (&v)[NV]) {
 // shared-memory plan (bytes)
 template <int CG>
 struct StripSmem {
+    // input-row ring slots: 2d+1 rows are pinned by the 3x3 window and ~5 by the epilogue lag; the rest is prefetch depth,
+    // i.e. HBM bytes in flight per CTA (small-C rows are only 2-4 KB, so they get many more slots)
+    static constexpr int kRing = CG == 1 ? 32 : (CG == 2 ? 14 : 16);
+    // accumulator / intermediate slots (row it -> slot it % kSlots).  The kernel is latency-bound per row (MMA -> commit -> epilogue
+    // -> MMA -> commit -> epilogue is ~3000 cycles), so throughput = rows in flight / latency: 8 slots where shared memory allows
+    static constexpr int kSlots = CG == 4 ? 4 : 8;
     static constexpr int N = CG >= 4 ? 8 * CG : 16;                  // MMA N (padded)
     static constexpr int KG1 = CG == 1 ? 12 : 9 * CG + 2;            // K groups of W1 incl. the bias / padding groups
     static constexpr int KG2 = CG == 1 ? 2 : CG + 2;
-    static constexpr int kBars = 0;                                  // 64 mbarriers
-    static constexpr int kTmemSlot = 512;
+    static constexpr int kBars = 0;                                  // 2 * kRing + 16 mbarriers (< 960 bytes)
+    static constexpr int kTmemSlot = 960;
     static constexpr int kW1 = 1024;
     static constexpr int kW2 = kW1 + KG1 * N * 16;
     static constexpr int kMid = (kW2 + KG2 * N * 16 + 127) / 128 * 128;
     static constexpr int kMidSlot = CG * 2048;
-    static constexpr int kRingBase = kMid + kAcc * kMidSlot;
+    static constexpr int kRingBase = kMid + kSlots * kMidSlot;
     __host__ __device__ static constexpr int slot_bytes(int d) { return (CG * (kStripTileT + 2 * d) * 16 + 127) / 128 * 128; }
     __host__ __device__ static constexpr int ones_off(int d) { return kRingBase + kRing * slot_bytes(d); }
     __host__ __device__ static constexpr int total(int d) { return ones_off(d) + 4096; }
 };
 
 template <int CG, int NREAL>
-__global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResStripParams p) {
+__global__ void __launch_bounds__(strip_threads<CG>(), CG <= 2 ? 2 : 1) res_strip_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResStripParams p) {
     using S = StripSmem<CG>;
     constexpr int N = S::N;
+    constexpr int kRing = S::kRing;
+    constexpr int kAcc = S::kSlots;
+    constexpr int kIssuers1 = issuers1<CG>();
+    constexpr int kStripThreads = strip_threads<CG>();
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBars);
     uint64_t* ring_full = bars;                 // [kRing]  TMA landed
@@ -188,8 +202,8 @@ __global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __gri
                 tma_load_5d(sRing + (size_t)slot * slot_bytes, &tmap_x, &ring_full[slot], 0, t0 - d, first_row + idx, 0, b);
             }
         }
-    } else if (warp == kEpiWarps + 1 || warp == kEpiWarps + 2) {
-        // =================================== 3x3 MMA issuers (rows it = par, par + 2, ...) ===================================
+    } else if (warp > kEpiWarps && warp <= kEpiWarps + kIssuers1) {
+        // =================================== 3x3 MMA issuers (rows it = par, par + kIssuers1, ...) ===================================
         // The whole warp runs the loop (warp-uniform control flow and descriptor arithmetic); one lane issues.
         const int par = warp - (kEpiWarps + 1);
         const bool issuer = lane == 0;
@@ -206,7 +220,7 @@ __global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __gri
                 for (int k = 0; k < 3; ++k)
                     if (v + k * d >= 0) mbar_arrive(&ring_free[(v + k * d) % kRing]);
         }
-        for (int it = par; it < n_out; it += 2) {
+        for (int it = par; it < n_out; it += kIssuers1) {
             const int u = it / kAcc, a = it % kAcc;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -255,14 +269,15 @@ __global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __gri
             }
             __syncwarp();
         }
-    } else if (warp == kEpiWarps + 3) {
-        // =================================== 1x1 MMA issuer ===================================
+    } else if (warp > kEpiWarps + kIssuers1) {
+        // =================================== 1x1 MMA issuers (rows it = par2, par2 + kIssuers2, ...) ===================================
+        const int par2 = warp - (kEpiWarps + kIssuers1 + 1);
         const bool issuer = lane == 0;
         const uint32_t idesc = umma::make_idesc_bf16(128, N);
         const uint32_t ones0 = umma::smem_u32(sOnes), mid0 = umma::smem_u32(sMid), w2_0 = umma::smem_u32(sW2);
         const uint32_t b_lo0 = desc_lo(w2_0, N * 16u), b_step = (2u * N * 16u) >> 4;
         const int n_out = h_end - h_start;
-        for (int it = 0; it < n_out; ++it) {
+        for (int it = par2; it < n_out; it += kIssuers2) {
             const int u = it / kAcc, a = it % kAcc;
             umma::mbar_wait(&mid_full[a], (uint32_t)(u & 1));
             umma::fence_after_sync();
@@ -290,17 +305,16 @@ __global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __gri
         const bool t_ok = t0 + j < p.T;
         const int n_out = h_end - h_start;
         constexpr int NV = NREAL >= 16 ? 16 : NREAL;                  // columns per TMEM load
-        for (int it = g; it < n_out; it += kAcc) {
-            const int u = it / kAcc;
-            const int h = h_start + it;
-            // ---- 3x3 accumulator -> ELU -> bf16 intermediate (A operand of the 1x1 conv) ----
-            umma::mbar_wait(&acc1_full[g], (uint32_t)(u & 1));
+        // ---- 3x3 accumulator -> ELU -> bf16 intermediate (A operand of the 1x1 conv) ----
+        auto epi1 = [&](int it) {
+            const int u = it / kAcc, a = it % kAcc;
+            umma::mbar_wait(&acc1_full[a], (uint32_t)(u & 1));
             umma::fence_after_sync();
-            uint8_t* mid = sMid + (size_t)g * S::kMidSlot + (size_t)j * 16u;
+            uint8_t* mid = sMid + (size_t)a * S::kMidSlot + (size_t)j * 16u;
 #pragma unroll
             for (int c0 = 0; c0 < NREAL; c0 += NV) {
                 float v[NV];
-                tmem_load<NV>(lane_addr + (uint32_t)(g * N + c0), v);
+                tmem_load<NV>(lane_addr + (uint32_t)(a * N + c0), v);
 #pragma unroll
                 for (int k = 0; k < NV; ++k) v[k] = elu_f(v[k]);
 #pragma unroll
@@ -315,18 +329,22 @@ __global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __gri
                 }
             }
             umma::fence_before_sync();
-            mbar_arrive(&acc1_free[g]);
+            mbar_arrive(&acc1_free[a]);
             umma::fence_proxy_async();
-            mbar_arrive(&mid_full[g]);
-            // ---- 1x1 accumulator -> ELU -> + x -> bf16 -> global ----
-            umma::mbar_wait(&acc2_full[g], (uint32_t)(u & 1));
+            mbar_arrive(&mid_full[a]);
+        };
+        // ---- 1x1 accumulator -> ELU -> + x -> bf16 -> global ----
+        auto epi2 = [&](int it) {
+            const int u = it / kAcc, a = it % kAcc;
+            const int h = h_start + it;
+            umma::mbar_wait(&acc2_full[a], (uint32_t)(u & 1));
             umma::fence_after_sync();
             const int ridx = it + d;                                   // ring index of row h
             const uint8_t* res = sRing + (size_t)(ridx % kRing) * slot_bytes + (size_t)(j + d) * 16u;
 #pragma unroll
             for (int c0 = 0; c0 < NREAL; c0 += NV) {
                 float v[NV];
-                tmem_load<NV>(lane_addr + (uint32_t)((kAcc + g) * N + c0), v);
+                tmem_load<NV>(lane_addr + (uint32_t)((kAcc + a) * N + c0), v);
 #pragma unroll
                 for (int k = 0; k < NV; k += 8) {
                     const int cg = (c0 + k) >> 3;
@@ -353,6 +371,21 @@ __global__ void __launch_bounds__(kStripThreads, 1) res_strip_kernel(const __gri
             }
             umma::fence_before_sync();
             mbar_arrive(&ring_free[ridx % kRing]);
+        };
+        if constexpr (kAcc >= 2 * kGroups) {
+            // two slot sets per group: the 1x1 round trip of row it overlaps the first epilogue of the group's next row
+            int prev = -1;
+            for (int it = g; it < n_out; it += kGroups) {
+                epi1(it);
+                if (prev >= 0) epi2(prev);
+                prev = it;
+            }
+            if (prev >= 0) epi2(prev);
+        } else {
+            for (int it = g; it < n_out; it += kGroups) {
+                epi1(it);
+                epi2(it);
+            }
         }
     }
 
@@ -401,7 +434,7 @@ static int launch_strip(const CUtensorMap& map, const ResStripParams& p, cudaStr
         configured = smem;
     }
     dim3 grid((p.T + kStripTileT - 1) / kStripTileT, (p.H + p.rows_per_strip - 1) / p.rows_per_strip, p.B);
-    res_strip_kernel<CG, NREAL><<<grid, kStripThreads, smem, stream>>>(map, p);
+    res_strip_kernel<CG, NREAL><<<grid, strip_threads<CG>(), smem, stream>>>(map, p);
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;
