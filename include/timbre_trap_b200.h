@@ -119,6 +119,10 @@ int tt_res_block_strip(const void* x, void* y, const void* w1, const void* w2, i
 int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int T, void* stream);
 /* DecoderBlock.tconv + ELU (modules.py:685-688): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding); Hout = 2 Hin + 2 + out_pad */
 int tt_conv_up(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int out_pad, int T, void* stream);
+/* The same two layers as row-pipelined kernels (csrc/updown_strip.cu); weights from packing.pack_down_strip / pack_up_strip
+ * (bias folded in).  Supported padded channel pairs: down 8->8, 8->16, 16->32, 32->64; up 64->32, 32->16, 16->8, 8->8. */
+int tt_conv_down_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int T, void* stream);
+int tt_conv_up_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int out_pad, int T, void* stream);
 /* Encoder.convlat (modules.py:446,478): Conv2d(C4, latent, (H4,1)), no activation; lat is C8 planar with H = 1 */
 int tt_conv_lat(const void* x, void* lat, const void* w, const float* bias, int B, int C4, int H4, int NL, int T, void* stream);
 /* Decoder.convin + ELU (modules.py:533-536) with TimbreTrap.decode's indicator channel (modules.py:139-142) folded into

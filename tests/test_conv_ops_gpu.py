@@ -78,6 +78,36 @@ def test_conv_down(Cin, Cout, H, T, B):
     _assert_close(P.from_c8(y, Cout).cpu(), want)
 
 
+@pytest.mark.parametrize('Cin,Cout,H,T,B', [(4, 8, 540, 128, 1), (8, 16, 269, 256, 2), (16, 32, 133, 128, 1), (32, 64, 65, 256, 2),
+                                              (2, 4, 20, 100, 1), (8, 16, 7, 128, 1)])
+@pytest.mark.parametrize('strip_rows', [None, 5])
+def test_conv_down_strip(Cin, Cout, H, T, B, strip_rows, monkeypatch):
+    from timbre_trap_b200.framework import ops, packing as P
+    if strip_rows:
+        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+    x = _bf(_rand((B, Cin, H, T), 11))
+    w, b = _bf(_rand((Cout, Cin, 4, 1), 12, 0.3)), _rand((Cout,), 13, 0.3)
+    want = F.elu(F.conv2d(x, w, b, stride=(2, 1)))
+    y = ops.conv_down_strip(P.to_c8(x.cuda()), P.pack_down_strip(w.cuda(), b.cuda()), P.pad8(Cout))
+    assert y.shape[2] == want.shape[2]
+    _assert_close(P.from_c8(y, Cout).cpu(), want)
+
+
+@pytest.mark.parametrize('Cin,Cout,H,T,op,B', [(64, 32, 31, 128, 1, 2), (32, 16, 65, 256, 1, 1), (16, 8, 133, 128, 1, 2),
+                                                 (8, 4, 269, 256, 0, 1), (4, 2, 9, 100, 1, 1), (16, 8, 5, 128, 0, 1)])
+@pytest.mark.parametrize('strip_rows', [None, 3])
+def test_conv_up_strip(Cin, Cout, H, T, op, B, strip_rows, monkeypatch):
+    from timbre_trap_b200.framework import ops, packing as P
+    if strip_rows:
+        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+    x = _bf(_rand((B, Cin, H, T), 21))
+    w, b = _bf(_rand((Cin, Cout, 4, 1), 22, 0.3)), _rand((Cout,), 23, 0.3)
+    want = F.elu(F.conv_transpose2d(x, w, b, stride=(2, 1), output_padding=(op, 0)))
+    y = ops.conv_up_strip(P.to_c8(x.cuda()), P.pack_up_strip(w.cuda(), b.cuda()), P.pad8(Cout), op)
+    assert y.shape[2] == want.shape[2]
+    _assert_close(P.from_c8(y, Cout).cpu(), want)
+
+
 @pytest.mark.parametrize('Cin,Cout,H,T,op,B', [(64, 32, 31, 128, 1, 2), (32, 16, 65, 256, 1, 1), (16, 8, 33, 128, 1, 2),
                                                  (8, 4, 29, 256, 0, 1), (4, 2, 9, 100, 1, 1), (16, 8, 5, 128, 0, 1)])
 def test_conv_up(Cin, Cout, H, T, op, B):
@@ -111,7 +141,7 @@ def test_conv_lat_and_deconv_in(C4, H4, D, T, B):
         _assert_close(P.from_c8(y, C4).cpu(), wantd)
 
 
-@pytest.mark.parametrize('C0,H,T,B', [(4, 60, 300, 2), (2, 33, 128, 1), (8, 17, 64, 1)])
+@pytest.mark.parametrize('C0,H,T,B', [(4, 60, 300, 2), (2, 33, 128, 1), (8, 17, 64, 1), (4, 5, 1024, 1), (3, 9, 516, 2)])
 def test_conv_in_out(C0, H, T, B):
     from timbre_trap_b200.framework import ops, packing as P
     x = _rand((B, 2, H, T), 41)

@@ -560,81 +560,119 @@ __global__ void __launch_bounds__(128) conv_lat_kernel(const __nv_bfloat16* __re
 // Decoder.convout (modules.py:543): Conv2d(C, 2, 3, 'same'), C8 planar bf16 -> fp32 interleaved (B, F, T, 2),
 // optionally scaled by a per-frame window and accumulated (chunk cross-fade of modules.py:259-263).
 // =========================================================================================================
-__global__ void __launch_bounds__(256) conv_in_kernel(const float2* __restrict__ x, __nv_bfloat16* __restrict__ y,
+// Each thread produces 4 consecutive frames of one row: the 3 x 6 input window is loaded once and reused by the 4 outputs.
+template <int NC>   // output channels computed (4 or 8)
+__global__ void __launch_bounds__(128) conv_in_kernel(const float2* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                       const float* __restrict__ w /* [C0][2][3][3] */,
                                                       const float* __restrict__ bias, int C0, int H, int T) {
-    __shared__ float sw[8 * 18 + 8];
-    for (int i = threadIdx.x; i < 8 * 18 + 8; i += 256) {
+    __shared__ float sw[NC * 18 + NC];
+    for (int i = threadIdx.x; i < NC * 18 + NC; i += 128) {
         float v = 0.f;
-        if (i < 8 * 18) { if (i < C0 * 18) v = w[i]; }
-        else if (i - 8 * 18 < C0) v = bias[i - 8 * 18];
+        if (i < NC * 18) { if (i < C0 * 18) v = w[i]; }
+        else if (i - NC * 18 < C0) v = bias[i - NC * 18];
         sw[i] = v;
     }
     __syncthreads();
-    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int t0 = (blockIdx.x * 128 + threadIdx.x) * 4;
     const int h = blockIdx.y, b = blockIdx.z;
-    if (t >= T) return;
-    float acc[8];
+    if (t0 >= T) return;
+    float acc[4][NC];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = sw[8 * 18 + c];
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[o][c] = sw[NC * 18 + c];
     const float2* xb = x + (size_t)b * H * T;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int hh = h + ky - 1;
         if (hh < 0 || hh >= H) continue;
+        float2 v[6];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int tt_ = t + kx - 1;
-            if (tt_ < 0 || tt_ >= T) continue;
-            const float2 v = __ldg(xb + (size_t)hh * T + tt_);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                acc[c] = fmaf(sw[c * 18 + ky * 3 + kx], v.x, acc[c]);
-                acc[c] = fmaf(sw[c * 18 + 9 + ky * 3 + kx], v.y, acc[c]);
-            }
+        for (int i = 0; i < 6; ++i) {
+            const int tt_ = t0 - 1 + i;
+            v[i] = (tt_ >= 0 && tt_ < T) ? __ldg(xb + (size_t)hh * T + tt_) : make_float2(0.f, 0.f);
         }
-    }
 #pragma unroll
-    for (int c = 0; c < 8; ++c) acc[c] = c < C0 ? elu(acc[c]) : 0.f;
-    reinterpret_cast<uint4*>(y)[((size_t)b * H + h) * T + t] = pack8(acc);
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const float wr = sw[c * 18 + ky * 3 + kx], wi = sw[c * 18 + 9 + ky * 3 + kx];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) acc[o][c] = fmaf(wi, v[o + kx].y, fmaf(wr, v[o + kx].x, acc[o][c]));
+            }
+    }
+    uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)b * H + h) * T + t0;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        if (t0 + o >= T) break;
+        float r[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) r[c] = (c < NC && c < C0) ? elu(acc[o][c < NC ? c : 0]) : 0.f;
+        dst[o] = pack8(r);
+    }
 }
 
-__global__ void __launch_bounds__(256) conv_out_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ y,
+template <int NC>   // input channels read (4 or 8)
+__global__ void __launch_bounds__(128) conv_out_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ y,
                                                        const float* __restrict__ w /* [2][C][3][3] */,
                                                        const float* __restrict__ bias, int C, int H, int T) {
-    __shared__ float sw[2 * 8 * 9 + 2];
-    for (int i = threadIdx.x; i < 2 * 8 * 9 + 2; i += 256) {
+    __shared__ float sw[2 * NC * 9 + 2];
+    for (int i = threadIdx.x; i < 2 * NC * 9 + 2; i += 128) {
         float v = 0.f;
-        if (i < 144) {
-            const int o = i / 72, c = (i % 72) / 9, k = i % 9;
+        if (i < 2 * NC * 9) {
+            const int o = i / (NC * 9), c = (i % (NC * 9)) / 9, k = i % 9;
             if (c < C) v = w[(o * C + c) * 9 + k];
-        } else v = bias[i - 144];
+        } else v = bias[i - 2 * NC * 9];
         sw[i] = v;
     }
     __syncthreads();
-    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int t0 = (blockIdx.x * 128 + threadIdx.x) * 4;
     const int h = blockIdx.y, b = blockIdx.z;
-    if (t >= T) return;
-    float a0 = sw[144], a1 = sw[145];
+    if (t0 >= T) return;
+    float a0[4], a1[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { a0[o] = sw[2 * NC * 9]; a1[o] = sw[2 * NC * 9 + 1]; }
     const uint4* xb = reinterpret_cast<const uint4*>(x) + (size_t)b * H * T;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
         const int hh = h + ky - 1;
         if (hh < 0 || hh >= H) continue;
+        float v[6][NC];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const int tt_ = t + kx - 1;
-            if (tt_ < 0 || tt_ >= T) continue;
-            float v[8];
-            unpack8(__ldg(xb + (size_t)hh * T + tt_), v);
+        for (int i = 0; i < 6; ++i) {
+            const int tt_ = t0 - 1 + i;
+            const bool ok = tt_ >= 0 && tt_ < T;
+            if constexpr (NC == 4) {
+                const uint2 raw = ok ? __ldg(reinterpret_cast<const uint2*>(xb + (size_t)hh * T + tt_)) : make_uint2(0u, 0u);
+                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+                v[i][0] = f0.x; v[i][1] = f0.y; v[i][2] = f1.x; v[i][3] = f1.y;
+            } else {
+                float tmp[8];
+                unpack8(ok ? __ldg(xb + (size_t)hh * T + tt_) : make_uint4(0u, 0u, 0u, 0u), tmp);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                a0 = fmaf(sw[c * 9 + ky * 3 + kx], v[c], a0);
-                a1 = fmaf(sw[72 + c * 9 + ky * 3 + kx], v[c], a1);
+                for (int c = 0; c < NC; ++c) v[i][c] = tmp[c];
             }
         }
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const float w0 = sw[c * 9 + ky * 3 + kx], w1 = sw[NC * 9 + c * 9 + ky * 3 + kx];
+#pragma unroll
+                for (int o = 0; o < 4; ++o) {
+                    a0[o] = fmaf(w0, v[o + kx][c], a0[o]);
+                    a1[o] = fmaf(w1, v[o + kx][c], a1[o]);
+                }
+            }
     }
-    y[((size_t)b * H + h) * T + t] = make_float2(a0, a1);
+    float2* dst = y + ((size_t)b * H + h) * T + t0;
+    if (t0 + 3 < T) {
+        reinterpret_cast<float4*>(dst)[0] = make_float4(a0[0], a1[0], a0[1], a1[1]);
+        reinterpret_cast<float4*>(dst)[1] = make_float4(a0[2], a1[2], a0[3], a1[3]);
+    } else {
+        for (int o = 0; o < 4 && t0 + o < T; ++o) dst[o] = make_float2(a0[o], a1[o]);
+    }
 }
 
 }  // namespace tt
@@ -667,8 +705,10 @@ extern "C" int tt_conv_in(const float* coeffs, void* y, const float* w, const fl
     TT_REQUIRE(coeffs && y && w && bias, "null argument");
     TT_REQUIRE(C0 >= 1 && C0 <= 8, "conv_in: at most 8 output channels");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
-    dim3 grid((T + 255) / 256, H, B);
-    conv_in_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T);
+    TT_REQUIRE(T % 4 == 0, "conv_in: the frame count must be a multiple of 4 (got %d)", T);
+    dim3 grid((T / 4 + 127) / 128, H, B);
+    if (C0 <= 4) conv_in_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T);
+    else conv_in_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
@@ -678,8 +718,10 @@ extern "C" int tt_conv_out(const void* x, float* coeffs, const float* w, const f
     TT_REQUIRE(x && coeffs && w && bias, "null argument");
     TT_REQUIRE(C >= 1 && C <= 8, "conv_out: at most 8 input channels");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
-    dim3 grid((T + 255) / 256, H, B);
-    conv_out_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T);
+    TT_REQUIRE(T % 4 == 0, "conv_out: the frame count must be a multiple of 4 (got %d)", T);
+    dim3 grid((T / 4 + 127) / 128, H, B);
+    if (C <= 4) conv_out_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T);
+    else conv_out_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;

@@ -93,8 +93,8 @@ class EncoderBlock(nn.Module):
         b = self.block2.forward_c8(a)
         a = self.block3.forward_c8(b, out=a)
         c = self.sconv[0]
-        w, bias = self._cache.get((c.weight, c.bias), lambda: (P.pack_down(c.weight), P.pad_vec(c.bias, _n16(self.out_channels))))
-        return ops.conv_down(a, w, bias, P.pad8(self.out_channels))
+        (w,) = self._cache.get((c.weight, c.bias), lambda: (P.pack_down_strip(c.weight, c.bias),))
+        return ops.conv_down_strip(a, w, P.pad8(self.out_channels))
 
     def forward(self, x):
         return P.from_c8(self.forward_c8(P.to_c8(x)), self.out_channels)
@@ -121,8 +121,8 @@ class DecoderBlock(nn.Module):
 
     def forward_c8(self, x):
         c = self.tconv[0]
-        w, bias = self._cache.get((c.weight, c.bias), lambda: (P.pack_up(c.weight), P.pack_up_bias(c.bias, self.out_channels)))
-        a = ops.conv_up(x, w, bias, P.pad8(self.out_channels), self.out_pad)
+        (w,) = self._cache.get((c.weight, c.bias), lambda: (P.pack_up_strip(c.weight, c.bias),))
+        a = ops.conv_up_strip(x, w, P.pad8(self.out_channels), self.out_pad)
         b = self.block1.forward_c8(a)
         a = self.block2.forward_c8(b, out=a)
         return self.block3.forward_c8(a, out=b)

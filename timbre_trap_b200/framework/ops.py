@@ -98,3 +98,21 @@ def res_block_strip(x, w1, w2, c_real, dilation, out=None):
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().tt_res_block_strip(_p(x), _p(y), _p(w1), _p(w2), B, CG * 8, c_real, H, T, dilation, _s(x)))
     return y
+
+
+def conv_down_strip(x, w, cout_pad):
+    _check_c8(x)
+    B, CG, H, T, _ = x.shape
+    y = torch.empty((B, cout_pad // 8, (H - 4) // 2 + 1, T, 8), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_conv_down_strip(_p(x), _p(y), _p(w), B, CG * 8, cout_pad, H, T, _s(x)))
+    return y
+
+
+def conv_up_strip(x, w, cout_pad, out_pad):
+    _check_c8(x)
+    B, CG, H, T, _ = x.shape
+    y = torch.empty((B, cout_pad // 8, 2 * H + 2 + out_pad, T, 8), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_conv_up_strip(_p(x), _p(y), _p(w), B, CG * 8, cout_pad, H, out_pad, T, _s(x)))
+    return y

@@ -12,7 +12,7 @@ The C8 planar activation layout is (B, ceil(C/8), H, T, 8) bf16.
 
 import torch
 
-__all__ = ['pack_res_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
+__all__ = ['pack_down_strip', 'pack_up_strip', 'pack_res_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
            'pad_vec']
 
 
@@ -170,3 +170,49 @@ def pack_res_strip(w1, b1, w2, b2):
     groups2 = [k2[:, 8 * g: 8 * g + 8] for g in range(CG)] + [_bias_group(b2, N)] + ([] if CG == 1 else [zero])
     w2p = torch.stack(groups2, dim=0).contiguous().to(torch.bfloat16)
     return w1p, w2p
+
+
+def _rows_to_groups(rows_nc, bias_group, N):
+    """rows_nc: list over input rows of (N, Cin_pad) weight slabs -> packed (KG, N, 8) for csrc/updown_strip.cu."""
+    Cp = rows_nc[0].shape[1]
+    CG = Cp // 8
+    zero = torch.zeros((N, 8), dtype=torch.float32, device=rows_nc[0].device)
+    groups = []
+    if CG == 1:
+        for k, r in enumerate(rows_nc):
+            groups += [r, bias_group if k == 0 else zero]
+    else:
+        for r in rows_nc:
+            groups += [r[:, 8 * g: 8 * g + 8] for g in range(CG)]
+        groups += [bias_group, zero]
+    return torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)
+
+
+def pack_down_strip(w, b):
+    """sconv.0.weight (Cout, Cin, 4, 1), bias -> K groups (kh, channel group) [+ bias group], N = max(16, Cout padded)."""
+    Co, Ci = w.shape[:2]
+    Cp, N = pad8(Ci), max(16, pad8(Co))
+    rows = []
+    for kh in range(4):
+        r = torch.zeros((N, Cp), dtype=torch.float32, device=w.device)
+        r[:Co, :Ci] = w.detach().float()[:, :, kh, 0]
+        rows.append(r)
+    return _rows_to_groups(rows, _bias_group(b, N), N)
+
+
+def pack_up_strip(w, b):
+    """tconv.0.weight (Cin, Cout, 4, 1), bias -> polyphase N = (r, co); K rows: input row q-1 (taps r+2), then row q (taps r)."""
+    Ci, Co = w.shape[:2]
+    Cip, Cop = pad8(Ci), pad8(Co)
+    N = max(16, 2 * Cop)
+    wf = w.detach().float()[..., 0]                      # (Ci, Co, 4)
+    rows = []
+    for a in range(2):
+        r = torch.zeros((N, Cip), dtype=torch.float32, device=w.device)
+        for par in range(2):
+            r[par * Cop: par * Cop + Co, :Ci] = wf[:, :, par + 2 - 2 * a].t()
+        rows.append(r)
+    bias2 = torch.zeros(N, dtype=torch.float32, device=w.device)
+    bias2[:Co] = b.detach().float()
+    bias2[Cop:Cop + Co] = b.detach().float()
+    return _rows_to_groups(rows, _bias_group(bias2, N), N)
