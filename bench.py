@@ -230,7 +230,7 @@ def run_ours(args, rank, world, local_rank):
         ms_k = time_kernel(lambda: blk.forward_c8(x32, out=y32), iters=10)
         flops = 2.0 * (9 * 32 * 32 + 32 * 32) * 65 * M * n_chunks
         achieved = flops / (ms_k * 1e-3) / 1e12
-        roofline = dict(kernel='conv_rows_kernel<32,32> (fused ResidualConv2dBlock, C=32, dilation 2)', bound='tensor', achieved=achieved,
+        roofline = dict(kernel='res_strip_kernel<4,32> (fused ResidualConv2dBlock, C=32, dilation 2)', bound='tensor', achieved=achieved,
                         peak=pk['bf16_burst'], unit='TFLOP/s', frac=achieved / pk['bf16_burst'], traffic=None,
                         peak_source=f"{pk['source']} bf16 burst (kernel timed alone)", us_per_launch=ms_k * 1e3,
                         flops_per_launch=flops)
