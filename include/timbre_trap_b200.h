@@ -114,7 +114,10 @@ int tt_res_block(const void* x, void* y, const void* w1, const float* b1, const 
 /* The same block as a warp-specialised, row-pipelined kernel (TMA row ring -> tcgen05 -> TMEM -> epilogue warps);
  * weights from packing.pack_res_strip (biases folded in as a K group); c_real = un-padded channel count. */
 int tt_res_block_strip(const void* x, void* y, const void* w1, const void* w2, int B, int C, int c_real, int H, int T,
-                       int dilation, void* stream);
+                       int dilation, int packed4, void* stream);
+/* packed4 = 1: x / y are the packed 4-channel layout (B, H, T, 4) bf16 used by the first encoder / last decoder stage
+ * (8 bytes per frame instead of 16: the channel padding of C8 planar would double that stage's HBM traffic); pass C = 8 and
+ * weights from packing.pack_res_strip_pairs. */
 /* EncoderBlock.sconv + ELU (modules.py:626-629): Conv2d(Cin, Cout, (4,1), stride (2,1)); Hout = (Hin-4)/2 + 1 */
 int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int T, void* stream);
 /* DecoderBlock.tconv + ELU (modules.py:685-688): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding); Hout = 2 Hin + 2 + out_pad */

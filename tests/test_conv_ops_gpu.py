@@ -78,6 +78,26 @@ def test_conv_down(Cin, Cout, H, T, B):
     _assert_close(P.from_c8(y, Cout).cpu(), want)
 
 
+@pytest.mark.parametrize('C,H,T,d,B', [(4, 37, 256, 1, 2), (4, 30, 512, 2, 1), (4, 540, 256, 3, 1), (2, 20, 200, 1, 1), (3, 9, 260, 3, 2),
+                                         (4, 3, 1024, 2, 1)])
+@pytest.mark.parametrize('strip_rows', [None, 7])
+def test_res_block_strip_packed4(C, H, T, d, B, strip_rows, monkeypatch):
+    from timbre_trap_b200.framework import ops, packing as P
+    if strip_rows:
+        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+    x = _bf(_rand((B, C, H, T), 1))
+    w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
+    w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
+    mid = _bf(F.elu(F.conv2d(x, w1, b1, padding=d, dilation=d)))
+    want = x + F.elu(F.conv2d(mid, w2, b2))
+    w1p, w2p = P.pack_res_strip_pairs(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), d)
+    y = ops.res_block_strip_p4(P.to_p4(x.cuda()), w1p, w2p, d)
+    torch.cuda.synchronize()
+    _assert_close(P.from_p4(y, C).cpu(), want)
+    if C < 4:
+        assert float(y[..., C:].float().abs().max()) == 0.0
+
+
 @pytest.mark.parametrize('Cin,Cout,H,T,B', [(4, 8, 540, 128, 1), (8, 16, 269, 256, 2), (16, 32, 133, 128, 1), (32, 64, 65, 256, 2),
                                               (2, 4, 20, 100, 1), (8, 16, 7, 128, 1)])
 @pytest.mark.parametrize('strip_rows', [None, 5])

@@ -41,7 +41,11 @@ struct ResStripParams {
     const __nv_bfloat16* w1;   // packed, see packing.pack_res_strip
     const __nv_bfloat16* w2;
     int B, H, T;
-    int d;                     // dilation
+    int d;                     // dilation (rows)
+    int halo;                  // column halo in 16-byte units (= d; for the packed 4-channel layout, where a unit is a pixel PAIR, ceil((d+1)/2))
+    int col_step;              // distance between the K groups of one tap row, in 16-byte units (= d; 1 for the packed layout)
+    int groups_per_row;        // K groups per tap row (3; 3 or 5 for the packed layout), CG = 1 only
+    int kg1;                   // K groups in the packed W1
     int rows_per_strip;
 };
 
@@ -55,7 +59,7 @@ struct StripSmem {
     // -> MMA -> commit -> epilogue is ~3000 cycles), so throughput = rows in flight / latency: 8 slots where shared memory allows
     static constexpr int kSlots = CG == 4 ? 4 : 8;
     static constexpr int N = CG >= 4 ? 8 * CG : 16;                  // MMA N (padded)
-    static constexpr int KG1 = CG == 1 ? 12 : 9 * CG + 2;            // K groups of W1 incl. the bias / padding groups
+    static constexpr int KG1 = CG == 1 ? 18 : 9 * CG + 2;            // K groups of W1 incl. the bias / padding groups (CG = 1: room for 3 x 6)
     static constexpr int KG2 = CG == 1 ? 2 : CG + 2;
     static constexpr int kBars = 0;                                  // 2 * kRing + 16 mbarriers (< 960 bytes)
     static constexpr int kTmemSlot = 960;
@@ -64,7 +68,7 @@ struct StripSmem {
     static constexpr int kMid = (kW2 + KG2 * N * 16 + 127) / 128 * 128;
     static constexpr int kMidSlot = CG * 2048;
     static constexpr int kRingBase = kMid + kSlots * kMidSlot;
-    __host__ __device__ static constexpr int slot_bytes(int d) { return (CG * (kStripTileT + 2 * d) * 16 + 127) / 128 * 128; }
+    __host__ __device__ static constexpr int slot_bytes(int halo) { return (CG * (kStripTileT + 2 * halo) * 16 + 127) / 128 * 128; }
     __host__ __device__ static constexpr int ones_off(int d) { return kRingBase + kRing * slot_bytes(d); }
     __host__ __device__ static constexpr int total(int d) { return ones_off(d) + 4096; }
 };
@@ -88,14 +92,14 @@ __global__ void __launch_bounds__(strip_threads<CG>(), CG <= 2 ? 2 : 1) res_stri
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S::kTmemSlot);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int d = p.d;
-    const int TW = kStripTileT + 2 * d;
-    const int slot_bytes = S::slot_bytes(d);
+    const int d = p.d, halo = p.halo;
+    const int TW = kStripTileT + 2 * halo;
+    const int slot_bytes = S::slot_bytes(halo);
     uint8_t* sW1 = smem + S::kW1;
     uint8_t* sW2 = smem + S::kW2;
     uint8_t* sMid = smem + S::kMid;
     uint8_t* sRing = smem + S::kRingBase;
-    uint8_t* sOnes = smem + S::ones_off(d);
+    uint8_t* sOnes = smem + S::ones_off(halo);
 
     const int t0 = blockIdx.x * kStripTileT;
     const int h_start = blockIdx.y * p.rows_per_strip;
@@ -119,7 +123,7 @@ __global__ void __launch_bounds__(strip_threads<CG>(), CG <= 2 ? 2 : 1) res_stri
         }
         umma::mbar_fence_init();
     }
-    for (int i = tid; i < S::KG1 * N; i += kStripThreads) reinterpret_cast<uint4*>(sW1)[i] = __ldg(reinterpret_cast<const uint4*>(p.w1) + i);
+    for (int i = tid; i < p.kg1 * N; i += kStripThreads) reinterpret_cast<uint4*>(sW1)[i] = __ldg(reinterpret_cast<const uint4*>(p.w1) + i);
     for (int i = tid; i < S::KG2 * N; i += kStripThreads) reinterpret_cast<uint4*>(sW2)[i] = __ldg(reinterpret_cast<const uint4*>(p.w2) + i);
     // "ones" operand: plane 0 rows = (1, 1, 0, ..., 0), plane 1 = zeros
     for (int i = tid; i < 256; i += kStripThreads)
@@ -139,7 +143,7 @@ __global__ void __launch_bounds__(strip_threads<CG>(), CG <= 2 ? 2 : 1) res_stri
                 const int slot = idx % kRing;
                 if (idx >= kRing) umma::mbar_wait(&ring_free[slot], (uint32_t)((idx / kRing - 1) & 1));
                 mbar_expect_tx(&ring_full[slot], bytes);
-                tma_load_5d(sRing + (size_t)slot * slot_bytes, &tmap_x, &ring_full[slot], 0, t0 - d, first_row + idx, 0, b);
+                tma_load_5d(sRing + (size_t)slot * slot_bytes, &tmap_x, &ring_full[slot], 0, t0 - halo, first_row + idx, 0, b);
             }
         }
     } else if (warp > kEpiWarps && warp <= kEpiWarps + kIssuers1) {
@@ -172,17 +176,21 @@ __global__ void __launch_bounds__(strip_threads<CG>(), CG <= 2 ? 2 : 1) res_stri
             const uint32_t acc = tmem + (uint32_t)(a * N);
             uint32_t b_lo = b_lo0;
             if constexpr (CG == 1) {
-                // per tap row: (kx0, kx1) and (kx2, ones); the ones operand carries the bias for ky = 0 and meets zero
-                // weights otherwise (never an arbitrary neighbour: stale shared memory times zero could be NaN)
+                // per tap row: G K groups at column offsets g * col_step, consumed as pairs (g, g+1); an unpaired last group meets the
+                // ones operand, which carries the bias for ky = 0 and zero weights otherwise (never an arbitrary neighbour: stale
+                // shared memory times zero could be NaN)
+                const uint32_t cs = (uint32_t)p.col_step * 16u;
+                bool first = true;
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
                     const uint32_t row = ring0 + (uint32_t)((it + ky * d) % kRing) * slot_bytes;
-                    const uint32_t a2 = row + (uint32_t)(2 * d) * 16u;
-                    if (issuer) {
-                        umma::mma_bf16(acc, desc64(desc_lo(row, (uint32_t)d * 16u)), desc64(b_lo), idesc, ky > 0);
-                        umma::mma_bf16(acc, desc64(desc_lo(a2, ones0 - a2)), desc64(b_lo + b_step), idesc, true);
+                    for (int g = 0; g < p.groups_per_row; g += 2) {
+                        const uint32_t a = row + (uint32_t)g * cs;
+                        const uint32_t lbo = g + 1 < p.groups_per_row ? cs : ones0 - a;
+                        if (issuer) umma::mma_bf16(acc, desc64(desc_lo(a, lbo)), desc64(b_lo), idesc, !first);
+                        first = false;
+                        b_lo += b_step;
                     }
-                    b_lo += 2 * b_step;
                 }
             } else {
                 const uint32_t a_lbo = ((plane >> 4) & 0x3FFFu) << 16;
@@ -280,7 +288,7 @@ __global__ void __launch_bounds__(strip_threads<CG>(), CG <= 2 ? 2 : 1) res_stri
             umma::mbar_wait(&acc2_full[a], (uint32_t)(u & 1));
             umma::fence_after_sync();
             const int ridx = it + d;                                   // ring index of row h
-            const uint8_t* res = sRing + (size_t)(ridx % kRing) * slot_bytes + (size_t)(j + d) * 16u;
+            const uint8_t* res = sRing + (size_t)(ridx % kRing) * slot_bytes + (size_t)(j + halo) * 16u;
 #pragma unroll
             for (int c0 = 0; c0 < NREAL; c0 += NV) {
                 float v[NV];
@@ -336,7 +344,7 @@ __global__ void __launch_bounds__(strip_threads<CG>(), CG <= 2 ? 2 : 1) res_stri
 
 template <int CG, int NREAL>
 static int launch_strip(const CUtensorMap& map, const ResStripParams& p, cudaStream_t stream) {
-    const int smem = StripSmem<CG>::total(p.d);
+    const int smem = StripSmem<CG>::total(p.halo);
     static int configured = 0;
     if (smem > configured) {
         TT_CUDA_CHECK(cudaFuncSetAttribute(res_strip_kernel<CG, NREAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -354,15 +362,23 @@ static int launch_strip(const CUtensorMap& map, const ResStripParams& p, cudaStr
 using namespace tt;
 
 extern "C" int tt_res_block_strip(const void* x, void* y, const void* w1, const void* w2, int B, int C, int c_real, int H, int T,
-                                  int dilation, void* stream) {
+                                  int dilation, int packed4, void* stream) {
     TT_REQUIRE(x && y && w1 && w2, "null argument");
     TT_REQUIRE(C == 8 || C == 16 || C == 32, "res block: padded channel count must be 8, 16 or 32 (got %d)", C);
+    TT_REQUIRE(!packed4 || (C == 8 && c_real <= 4 && T % 2 == 0), "packed layout: at most 4 channels and an even frame count");
     TT_REQUIRE(dilation >= 1 && dilation <= 3, "dilation must be in [1,3]");
     TT_REQUIRE(c_real >= 1 && c_real <= C, "bad real channel count");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
     ResStripParams p;
     p.y = (__nv_bfloat16*)y; p.w1 = (const __nv_bfloat16*)w1; p.w2 = (const __nv_bfloat16*)w2;
+    // packed4: memory is (B, H, T, 4) bf16; a 16-byte unit is a PAIR of frames (e, 4 channels), so the kernel sees an 8-channel
+    // tensor with T/2 "frames" whose taps are the pair offsets -halo..halo (Toeplitz-expanded weights, packing.pack_res_strip_pairs)
+    if (packed4) T /= 2;
     p.B = B; p.H = H; p.T = T; p.d = dilation;
+    p.halo = packed4 ? (dilation + 1) / 2 : dilation;
+    p.col_step = packed4 ? 1 : dilation;
+    p.groups_per_row = packed4 ? 2 * p.halo + 1 : 3;
+    p.kg1 = C == 8 ? 3 * (p.groups_per_row + 1) : 9 * (C / 8) + 2;
     // whole-height strips when the batch alone fills the GPU, shorter ones otherwise (each strip re-reads 2d halo rows)
     const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
     int rows = H;
@@ -376,10 +392,10 @@ extern "C" int tt_res_block_strip(const void* x, void* y, const void* w1, const 
     p.rows_per_strip = std::min(rows, H);
     CUtensorMap map;
     const int CG = C / 8;
-    const int rc = make_row_map(&map, x, B, CG, H, T, kStripTileT + 2 * dilation);
+    const int rc = make_row_map(&map, x, B, CG, H, T, kStripTileT + 2 * p.halo);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    if (C == 8) return c_real <= 4 ? launch_strip<1, 4>(map, p, s) : launch_strip<1, 8>(map, p, s);
+    if (C == 8) return (c_real <= 4 && !packed4) ? launch_strip<1, 4>(map, p, s) : launch_strip<1, 8>(map, p, s);
     if (C == 16) return launch_strip<2, 16>(map, p, s);
     return launch_strip<4, 32>(map, p, s);
 }

@@ -96,7 +96,23 @@ def res_block_strip(x, w1, w2, c_real, dilation, out=None):
     B, CG, H, T, _ = x.shape
     y = torch.empty_like(x) if out is None else out
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_res_block_strip(_p(x), _p(y), _p(w1), _p(w2), B, CG * 8, c_real, H, T, dilation, _s(x)))
+        _lib.check(_lib.lib().tt_res_block_strip(_p(x), _p(y), _p(w1), _p(w2), B, CG * 8, c_real, H, T, dilation, 0, _s(x)))
+    return y
+
+
+def _check_p4(x, name='x'):
+    _lib.require_cuda(x, name)
+    if x.dtype != torch.bfloat16 or x.dim() != 4 or x.size(-1) != 4 or x.size(-2) % 2 or not x.is_contiguous():
+        raise ValueError(f'{name} must be a contiguous packed 4-channel bf16 tensor (B, H, T, 4) with even T, got {tuple(x.shape)} {x.dtype}')
+
+
+def res_block_strip_p4(x, w1, w2, dilation, out=None):
+    """The residual block on the packed 4-channel layout (B, H, T, 4); weights from packing.pack_res_strip_pairs."""
+    _check_p4(x)
+    B, H, T, _ = x.shape
+    y = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_res_block_strip(_p(x), _p(y), _p(w1), _p(w2), B, 8, 4, H, T, dilation, 1, _s(x)))
     return y
 
 

@@ -12,7 +12,7 @@ The C8 planar activation layout is (B, ceil(C/8), H, T, 8) bf16.
 
 import torch
 
-__all__ = ['pack_down_strip', 'pack_up_strip', 'pack_res_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
+__all__ = ['pack_res_strip_pairs', 'to_p4', 'from_p4', 'pack_down_strip', 'pack_up_strip', 'pack_res_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
            'pad_vec']
 
 
@@ -216,3 +216,58 @@ def pack_up_strip(w, b):
     bias2[:Co] = b.detach().float()
     bias2[Cop:Cop + Co] = b.detach().float()
     return _rows_to_groups(rows, _bias_group(bias2, N), N)
+
+
+# ---- packed 4-channel layout (first encoder / last decoder stage): memory (B, H, T, 4) bf16 ----------------------------
+
+def to_p4(x):
+    """(B, C <= 4, H, T) -> (B, H, T, 4) bf16, zero-padded channels (test/plumbing helper)."""
+    B, C, H, T = x.shape
+    if C < 4:
+        x = torch.nn.functional.pad(x, (0, 0, 0, 0, 0, 4 - C))
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def from_p4(y, C):
+    return y.permute(0, 3, 1, 2)[:, :C].float()
+
+
+def pack_res_strip_pairs(w1, b1, w2, b2, dilation):
+    """
+    Weights of one ResidualConv2dBlock with C <= 4 for the packed layout.  A GEMM row is a PAIR of frames (2j, 2j+1), a K group
+    is (frame parity e_in, 4 channels) of one input pair, N = (e_out, co).  The tap (ky, kx) with column shift s = (kx-1)*d feeds
+    output parity e_out from the input pair at offset o and parity e_in where 2*o + e_in - e_out = s, o in [-hp, hp],
+    hp = ceil((d+1)/2) ... i.e. the 3x3 kernel is Toeplitz-expanded over the pair.  K groups per tap row: o = -hp..hp, then one
+    filler group (the bias for ky = 0, zeros otherwise) so that groups pair up into K = 16 MMAs.  W2: block-diagonal in e, + bias.
+    """
+    Co, Ci = w1.shape[:2]
+    assert Co <= 4 and Ci <= 4
+    d = int(dilation)
+    hp = (d + 1) // 2
+    N = 16
+    dev = w1.device
+    w = w1.detach().float()
+    zero = torch.zeros((N, 8), dtype=torch.float32, device=dev)
+    bias1 = torch.zeros(N, dtype=torch.float32, device=dev)
+    bias2 = torch.zeros(N, dtype=torch.float32, device=dev)
+    for e in range(2):
+        bias1[4 * e: 4 * e + Co] = b1.detach().float()
+        bias2[4 * e: 4 * e + Co] = b2.detach().float()
+    groups = []
+    for ky in range(3):
+        for o in range(-hp, hp + 1):
+            g = torch.zeros((N, 8), dtype=torch.float32, device=dev)
+            for e_out in range(2):
+                for e_in in range(2):
+                    s_ = 2 * o + e_in - e_out
+                    for kx in range(3):
+                        if (kx - 1) * d == s_:
+                            g[4 * e_out: 4 * e_out + Co, 4 * e_in: 4 * e_in + Ci] = w[:, :, ky, kx]
+            groups.append(g)
+        groups.append(_bias_group(bias1, N) if ky == 0 else zero)
+    w1p = torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)
+    g2 = torch.zeros((N, 8), dtype=torch.float32, device=dev)
+    for e in range(2):
+        g2[4 * e: 4 * e + Co, 4 * e: 4 * e + Ci] = w2.detach().float().reshape(Co, Ci)
+    w2p = torch.stack([g2, _bias_group(bias2, N)], dim=0).contiguous().to(torch.bfloat16)
+    return w1p, w2p
