@@ -124,17 +124,21 @@ int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B
 int tt_conv_up(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int out_pad, int T, void* stream);
 /* The same two layers as row-pipelined kernels (csrc/updown_strip.cu); weights from packing.pack_down_strip / pack_up_strip
  * (bias folded in).  Supported padded channel pairs: down 8->8, 8->16, 16->32, 32->64; up 64->32, 32->16, 16->8, 8->8. */
-int tt_conv_down_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int T, void* stream);
-int tt_conv_up_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int out_pad, int T, void* stream);
+/* packed4_in / packed4_out = 1: the input (down, 4 -> 8 channels, weights from packing.pack_down_pairs) / the output (up, 8 -> 4
+ * channels) is the packed 4-channel layout (B, H, T, 4) bf16; pass the padded channel counts 8 -> 8. */
+int tt_conv_down_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int T, int packed4_in, void* stream);
+int tt_conv_up_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int out_pad, int T, int packed4_out,
+                     void* stream);
 /* Encoder.convlat (modules.py:446,478): Conv2d(C4, latent, (H4,1)), no activation; lat is C8 planar with H = 1 */
 int tt_conv_lat(const void* x, void* lat, const void* w, const float* bias, int B, int C4, int H4, int NL, int T, void* stream);
 /* Decoder.convin + ELU (modules.py:533-536) with TimbreTrap.decode's indicator channel (modules.py:139-142) folded into
  * the per-row bias table bias[H0][C0] (one table per switch setting) */
 int tt_deconv_in(const void* lat, void* y, const void* w, const float* bias, int B, int Clat, int C0, int H0, int T, void* stream);
-/* Encoder.convin + ELU (modules.py:430-433): fp32 interleaved coefficients (B,F,T,2) -> C8 planar; w fp32 [C0][2][3][3] */
-int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, int B, int C0, int H, int T, void* stream);
-/* Decoder.convout (modules.py:543): C8 planar -> fp32 interleaved coefficients (B,F,T,2); w fp32 [2][C][3][3] */
-int tt_conv_out(const void* x, float* coeffs, const float* w, const float* bias, int B, int C, int H, int T, void* stream);
+/* Encoder.convin + ELU (modules.py:430-433): fp32 interleaved coefficients (B,F,T,2) -> C8 planar (packed4 = 0) or the packed
+ * 4-channel layout (B,F,T,4) (packed4 = 1, C0 <= 4); w fp32 [C0][2][3][3] */
+int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, int B, int C0, int H, int T, int packed4, void* stream);
+/* Decoder.convout (modules.py:543): C8 planar or packed 4-channel input -> fp32 interleaved coefficients (B,F,T,2); w fp32 [2][C][3][3] */
+int tt_conv_out(const void* x, float* coeffs, const float* w, const float* bias, int B, int C, int H, int T, int packed4, void* stream);
 
 /*
  * ---- objectives (timbre_trap/framework/objectives.py), deterministic two-stage reductions ------------------------

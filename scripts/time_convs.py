@@ -24,11 +24,12 @@ enc, dec = m.encoder, m.decoder
 shapes = [(4, 540), (8, 269), (16, 133), (32, 65)]
 for i, (C, H) in enumerate(shapes):
     blk = getattr(enc, f'block{i+1}')
-    x = c8(C, H); y = torch.empty_like(x)
+    x = torch.randn((B, H, T, 4), device='cuda').to(torch.bfloat16) if (i == 0 and enc.packed4) else c8(C, H)
+    y = torch.empty_like(x)
     for d, rb in ((1, blk.block1), (2, blk.block2), (3, blk.block3)):
         ms = timeit(lambda: rb.forward_c8(x, out=y))
         fl = 2.0 * (9 * C * C + C * C) * H * T * B
-        by = 2.0 * x.numel() * 2
+        by = 2.0 * B * H * T * C * 2          # algorithmic: un-padded channels, read + write
         rows.append((f'res C={C} d={d}', ms, fl / ms / 1e9, by / ms / 1e6))
     ms = timeit(lambda: blk.forward_c8(x))
     rows.append((f'enc block{i+1} (3 res + down)', ms, 0, 0))

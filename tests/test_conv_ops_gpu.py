@@ -113,6 +113,45 @@ def test_conv_down_strip(Cin, Cout, H, T, B, strip_rows, monkeypatch):
     _assert_close(P.from_c8(y, Cout).cpu(), want)
 
 
+@pytest.mark.parametrize('Cin,Cout,H,T,B', [(4, 8, 540, 256, 1), (2, 4, 20, 100, 2), (3, 7, 31, 516, 1)])
+def test_conv_down_packed4_input(Cin, Cout, H, T, B):
+    from timbre_trap_b200.framework import ops, packing as P
+    x = _bf(_rand((B, Cin, H, T), 11))
+    w, b = _bf(_rand((Cout, Cin, 4, 1), 12, 0.3)), _rand((Cout,), 13, 0.3)
+    want = F.elu(F.conv2d(x, w, b, stride=(2, 1)))
+    y = ops.conv_down_strip(P.to_p4(x.cuda()), P.pack_down_pairs(w.cuda(), b.cuda()), 8)
+    assert y.shape == (B, 1, want.shape[2], T, 8)
+    _assert_close(P.from_c8(y, Cout).cpu(), want)
+
+
+@pytest.mark.parametrize('Cin,Cout,H,T,op,B', [(8, 4, 269, 256, 0, 1), (4, 2, 9, 100, 1, 2), (8, 3, 17, 128, 1, 1)])
+def test_conv_up_packed4_output(Cin, Cout, H, T, op, B):
+    from timbre_trap_b200.framework import ops, packing as P
+    x = _bf(_rand((B, Cin, H, T), 21))
+    w, b = _bf(_rand((Cin, Cout, 4, 1), 22, 0.3)), _rand((Cout,), 23, 0.3)
+    want = F.elu(F.conv_transpose2d(x, w, b, stride=(2, 1), output_padding=(op, 0)))
+    y = ops.conv_up_strip(P.to_c8(x.cuda()), P.pack_up_strip(w.cuda(), b.cuda()), 8, op, packed4_out=True)
+    assert y.shape == (B, want.shape[2], T, 4)
+    _assert_close(P.from_p4(y, Cout).cpu(), want)
+    if Cout < 4:
+        assert float(y[..., Cout:].float().abs().max()) == 0.0
+
+
+def test_conv_in_out_packed4():
+    from timbre_trap_b200.framework import ops, packing as P
+    B, C0, H, T = 2, 4, 33, 260
+    x = _rand((B, 2, H, T), 41)
+    w, b = _rand((C0, 2, 3, 3), 42, 0.4), _rand((C0,), 43, 0.3)
+    want = F.elu(F.conv2d(x, w, b, padding=1))
+    y = ops.conv_in(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda().contiguous(), b.cuda(), C0, packed4=True)
+    assert y.shape == (B, H, T, 4)
+    _assert_close(P.from_p4(y, C0).cpu(), want)
+    xo = _bf(_rand((B, C0, H, T), 44))
+    wo, bo = _rand((2, C0, 3, 3), 45, 0.4), _rand((2,), 46, 0.3)
+    yo = ops.conv_out(P.to_p4(xo.cuda()), wo.cuda().contiguous(), bo.cuda(), C0)
+    _assert_close(yo.permute(0, 3, 1, 2).cpu(), F.conv2d(xo, wo, bo, padding=1), tol=1e-5)
+
+
 @pytest.mark.parametrize('Cin,Cout,H,T,op,B', [(64, 32, 31, 128, 1, 2), (32, 16, 65, 256, 1, 1), (16, 8, 133, 128, 1, 2),
                                                  (8, 4, 269, 256, 0, 1), (4, 2, 9, 100, 1, 1), (16, 8, 5, 128, 0, 1)])
 @pytest.mark.parametrize('strip_rows', [None, 3])

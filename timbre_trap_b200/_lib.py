@@ -33,14 +33,14 @@ SIGNATURES = {
     'tt_chunk_crossfade': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'tt_res_block': (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     'tt_res_block_strip': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
-    'tt_conv_down_strip': (c_int, [c_void_p] * 3 + [c_int] * 5 + [c_void_p]),
-    'tt_conv_up_strip': (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
+    'tt_conv_down_strip': (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
+    'tt_conv_up_strip': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     'tt_conv_down': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'tt_conv_up': (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     'tt_conv_lat': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'tt_deconv_in': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
-    'tt_conv_in': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
-    'tt_conv_out': (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
+    'tt_conv_in': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
+    'tt_conv_out': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'tt_loss_scratch_floats': (c_int, []),
     'tt_sum_sq_diff': (c_int, [c_void_p, c_void_p, c_int64, ctypes.c_double, c_void_p, c_void_p, c_void_p]),
     'tt_transcription_loss': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(128) conv_lat_kernel(const __nv_bfloat16* __re
 template <int NC>   // output channels computed (4 or 8)
 __global__ void __launch_bounds__(128) conv_in_kernel(const float2* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                       const float* __restrict__ w /* [C0][2][3][3] */,
-                                                      const float* __restrict__ bias, int C0, int H, int T) {
+                                                      const float* __restrict__ bias, int C0, int H, int T, int packed4) {
     __shared__ float sw[NC * 18 + NC];
     for (int i = threadIdx.x; i < NC * 18 + NC; i += 128) {
         float v = 0.f;
@@ -601,6 +601,18 @@ __global__ void __launch_bounds__(128) conv_in_kernel(const float2* __restrict__
                 for (int o = 0; o < 4; ++o) acc[o][c] = fmaf(wi, v[o + kx].y, fmaf(wr, v[o + kx].x, acc[o][c]));
             }
     }
+    if (packed4) {
+        // (B, H, T, 4) bf16: 4 frames x 4 channels = 32 contiguous bytes per thread (T % 4 == 0)
+        float r[16];
+#pragma unroll
+        for (int o = 0; o < 4; ++o)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) r[4 * o + c] = (c < NC && c < C0) ? elu(acc[o][c < NC ? c : 0]) : 0.f;
+        uint4* dst4 = reinterpret_cast<uint4*>(reinterpret_cast<uint2*>(y) + ((size_t)b * H + h) * T + t0);
+        dst4[0] = pack8(r);
+        dst4[1] = pack8(r + 8);
+        return;
+    }
     uint4* dst = reinterpret_cast<uint4*>(y) + ((size_t)b * H + h) * T + t0;
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
@@ -615,7 +627,7 @@ __global__ void __launch_bounds__(128) conv_in_kernel(const float2* __restrict__
 template <int NC>   // input channels read (4 or 8)
 __global__ void __launch_bounds__(128) conv_out_kernel(const __nv_bfloat16* __restrict__ x, float2* __restrict__ y,
                                                        const float* __restrict__ w /* [2][C][3][3] */,
-                                                       const float* __restrict__ bias, int C, int H, int T) {
+                                                       const float* __restrict__ bias, int C, int H, int T, int packed4) {
     __shared__ float sw[2 * NC * 9 + 2];
     for (int i = threadIdx.x; i < 2 * NC * 9 + 2; i += 128) {
         float v = 0.f;
@@ -643,7 +655,9 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const __nv_bfloat16* __re
             const int tt_ = t0 - 1 + i;
             const bool ok = tt_ >= 0 && tt_ < T;
             if constexpr (NC == 4) {
-                const uint2 raw = ok ? __ldg(reinterpret_cast<const uint2*>(xb + (size_t)hh * T + tt_)) : make_uint2(0u, 0u);
+                const uint2* src = packed4 ? reinterpret_cast<const uint2*>(x) + ((size_t)b * H + hh) * T + tt_
+                                           : reinterpret_cast<const uint2*>(xb + (size_t)hh * T + tt_);
+                const uint2 raw = ok ? __ldg(src) : make_uint2(0u, 0u);
                 const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
                 const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
                 v[i][0] = f0.x; v[i][1] = f0.y; v[i][2] = f1.x; v[i][3] = f1.y;
@@ -701,27 +715,31 @@ extern "C" int tt_conv_lat(const void* x, void* lat, const void* w, const float*
     return TT_OK;
 }
 
-extern "C" int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, int B, int C0, int H, int T, void* stream) {
+extern "C" int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, int B, int C0, int H, int T, int packed4,
+                          void* stream) {
     TT_REQUIRE(coeffs && y && w && bias, "null argument");
     TT_REQUIRE(C0 >= 1 && C0 <= 8, "conv_in: at most 8 output channels");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
     TT_REQUIRE(T % 4 == 0, "conv_in: the frame count must be a multiple of 4 (got %d)", T);
     dim3 grid((T / 4 + 127) / 128, H, B);
-    if (C0 <= 4) conv_in_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T);
-    else conv_in_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T);
+    TT_REQUIRE(!packed4 || C0 <= 4, "conv_in: the packed layout holds at most 4 channels");
+    if (C0 <= 4) conv_in_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T, packed4);
+    else conv_in_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T, 0);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }
 
-extern "C" int tt_conv_out(const void* x, float* coeffs, const float* w, const float* bias, int B, int C, int H, int T, void* stream) {
+extern "C" int tt_conv_out(const void* x, float* coeffs, const float* w, const float* bias, int B, int C, int H, int T, int packed4,
+                           void* stream) {
     TT_REQUIRE(x && coeffs && w && bias, "null argument");
     TT_REQUIRE(C >= 1 && C <= 8, "conv_out: at most 8 input channels");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
     TT_REQUIRE(T % 4 == 0, "conv_out: the frame count must be a multiple of 4 (got %d)", T);
     dim3 grid((T / 4 + 127) / 128, H, B);
-    if (C <= 4) conv_out_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T);
-    else conv_out_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T);
+    TT_REQUIRE(!packed4 || C <= 4, "conv_out: the packed layout holds at most 4 channels");
+    if (C <= 4) conv_out_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T, packed4);
+    else conv_out_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T, 0);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;

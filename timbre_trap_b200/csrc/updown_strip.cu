@@ -45,7 +45,9 @@ struct UdSmem {
     __host__ __device__ static constexpr int total(int rows) { return ones_off(rows) + 4096; }
 };
 
-template <int CGIN, int N, int NCOL, bool UP>
+// P4 (packed 4-channel layout on one side): DOWN reads it - a GEMM row is a frame PAIR, the 16 output columns are (frame parity, 8
+// channels) and go to two consecutive frames of the C8 planar output; UP writes it - only the first 4 channels of each output row.
+template <int CGIN, int N, int NCOL, bool UP, bool P4>
 __global__ void __launch_bounds__(kUdThreads, 1) updown_strip_kernel(const __grid_constant__ CUtensorMap tmap_x, const UpDownParams p) {
     using S = UdSmem<CGIN, N>;
     constexpr int kRing = S::kRing;
@@ -179,8 +181,17 @@ __global__ void __launch_bounds__(kUdThreads, 1) updown_strip_kernel(const __gri
                     o.y = pack2(elu_f(v[k + 2]), elu_f(v[k + 3]));
                     o.z = pack2(elu_f(v[k + 4]), elu_f(v[k + 5]));
                     o.w = pack2(elu_f(v[k + 6]), elu_f(v[k + 7]));
-                    if (t_ok && cg < p.CGout && ho < p.Hout)
-                        reinterpret_cast<uint4*>(p.y)[(((size_t)b * p.CGout + cg) * p.Hout + ho) * p.T + t0 + j] = o;
+                    if constexpr (P4 && !UP) {
+                        // pair j -> frames 2 (t0 + j) + (c >> 3) of the 8-channel output (p.T counts pairs)
+                        if (t_ok && ho < p.Hout)
+                            reinterpret_cast<uint4*>(p.y)[((size_t)b * p.Hout + ho) * (2 * (size_t)p.T) + 2 * (size_t)(t0 + j) + (c >> 3)] = o;
+                    } else if constexpr (P4 && UP) {
+                        if (t_ok && ho < p.Hout)
+                            reinterpret_cast<uint2*>(p.y)[((size_t)b * p.Hout + ho) * p.T + t0 + j] = make_uint2(o.x, o.y);
+                    } else {
+                        if (t_ok && cg < p.CGout && ho < p.Hout)
+                            reinterpret_cast<uint4*>(p.y)[(((size_t)b * p.CGout + cg) * p.Hout + ho) * p.T + t0 + j] = o;
+                    }
                 }
             }
             umma::fence_before_sync();
@@ -193,7 +204,7 @@ __global__ void __launch_bounds__(kUdThreads, 1) updown_strip_kernel(const __gri
     if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
-template <int CGIN, int N, int NCOL, bool UP>
+template <int CGIN, int N, int NCOL, bool UP, bool P4 = false>
 static int launch_updown(const void* x, const UpDownParams& p, cudaStream_t stream) {
     using S = UdSmem<CGIN, N>;
     constexpr int R = UP ? 2 : 4;
@@ -203,11 +214,11 @@ static int launch_updown(const void* x, const UpDownParams& p, cudaStream_t stre
     const int smem = S::total(R);
     static bool configured = false;
     if (!configured) {
-        TT_CUDA_CHECK(cudaFuncSetAttribute(updown_strip_kernel<CGIN, N, NCOL, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        TT_CUDA_CHECK(cudaFuncSetAttribute(updown_strip_kernel<CGIN, N, NCOL, UP, P4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     dim3 grid((p.T + kStripTileT - 1) / kStripTileT, (p.groups + p.groups_per_strip - 1) / p.groups_per_strip, p.B);
-    updown_strip_kernel<CGIN, N, NCOL, UP><<<grid, kUdThreads, smem, stream>>>(map, p);
+    updown_strip_kernel<CGIN, N, NCOL, UP, P4><<<grid, kUdThreads, smem, stream>>>(map, p);
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;
@@ -230,8 +241,11 @@ static int strip_groups(int B, int T, int groups) {
 
 using namespace tt;
 
-extern "C" int tt_conv_down_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int T, void* stream) {
+extern "C" int tt_conv_down_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int T, int packed4_in,
+                                  void* stream) {
     TT_REQUIRE(x && y && w, "null argument");
+    TT_REQUIRE(!packed4_in || (Cin == 8 && Cout == 8 && T % 2 == 0), "packed input: 4 -> 8 channels only, even frame count");
+    if (packed4_in) T /= 2;                 // the kernel works on frame pairs
     if (B <= 0 || T <= 0) return TT_OK;
     const int Hout = (Hin - 4) / 2 + 1;
     TT_REQUIRE(Hout >= 1, "conv_down: input too short");
@@ -240,6 +254,7 @@ extern "C" int tt_conv_down_strip(const void* x, void* y, const void* w, int B, 
     p.B = B; p.Hin = Hin; p.Hout = Hout; p.T = T; p.CGout = Cout / 8; p.groups = Hout;
     p.groups_per_strip = strip_groups(B, T, p.groups);
     cudaStream_t s = (cudaStream_t)stream;
+    if (packed4_in) return launch_updown<1, 16, 16, false, true>(x, p, s);
     if (Cin == 8 && Cout == 8) return launch_updown<1, 16, 8, false>(x, p, s);
     if (Cin == 8 && Cout == 16) return launch_updown<1, 16, 16, false>(x, p, s);
     if (Cin == 16 && Cout == 32) return launch_updown<2, 32, 32, false>(x, p, s);
@@ -249,8 +264,9 @@ extern "C" int tt_conv_down_strip(const void* x, void* y, const void* w, int B, 
 }
 
 extern "C" int tt_conv_up_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int out_pad, int T,
-                                void* stream) {
+                                int packed4_out, void* stream) {
     TT_REQUIRE(x && y && w, "null argument");
+    TT_REQUIRE(!packed4_out || (Cin == 8 && Cout == 8), "packed output: 8 -> 4 channels only");
     if (B <= 0 || T <= 0 || Hin <= 0) return TT_OK;
     UpDownParams p;
     p.y = (__nv_bfloat16*)y; p.w = (const __nv_bfloat16*)w;
@@ -260,6 +276,7 @@ extern "C" int tt_conv_up_strip(const void* x, void* y, const void* w, int B, in
     if (Cin == 64 && Cout == 32) return launch_updown<8, 64, 64, true>(x, p, s);
     if (Cin == 32 && Cout == 16) return launch_updown<4, 32, 32, true>(x, p, s);
     if (Cin == 16 && Cout == 8) return launch_updown<2, 16, 16, true>(x, p, s);
+    if (packed4_out) return launch_updown<1, 16, 16, true, true>(x, p, s);
     if (Cin == 8 && Cout == 8) return launch_updown<1, 16, 16, true>(x, p, s);
     tt_set_error("conv_up_strip: unsupported channel pair %d -> %d", Cin, Cout);
     return TT_ERR_UNSUPPORTED;

@@ -55,19 +55,27 @@ class ResidualConv2dBlock(nn.Module):
         self.conv2 = nn.Sequential(nn.Conv2d(out_channels, out_channels, kernel_size=1), nn.ELU(inplace=True))
         self.dilation = dilation
         self.channels = in_channels
+        self.packed4 = False        # set by Encoder / Decoder for the first / last stage: (B, H, T, 4) activations
         self._cache = _PackedCache()
 
     def _packed(self):
         c1, c2 = self.conv1[0], self.conv2[0]
+        if self.packed4:
+            return self._cache.get((c1.weight, c1.bias, c2.weight, c2.bias),
+                                   lambda: P.pack_res_strip_pairs(c1.weight, c1.bias, c2.weight, c2.bias, self.dilation))
         return self._cache.get((c1.weight, c1.bias, c2.weight, c2.bias),
                                lambda: P.pack_res_strip(c1.weight, c1.bias, c2.weight, c2.bias))
 
     def forward_c8(self, x, out=None):
         w1, w2 = self._packed()
+        if self.packed4:
+            return ops.res_block_strip_p4(x, w1, w2, self.dilation, out=out)
         return ops.res_block_strip(x, w1, w2, self.channels, self.dilation, out=out)
 
     def forward(self, x):
-        """(B, C, H, W) -> (B, C, H, W) fp32 (API parity; the fast paths stay in C8 planar)."""
+        """(B, C, H, W) -> (B, C, H, W) fp32 (API parity; the fast paths stay in the internal layouts)."""
+        if self.packed4:
+            return P.from_p4(self.forward_c8(P.to_p4(x)), self.channels)
         return P.from_c8(self.forward_c8(P.to_c8(x)), self.channels)
 
 
@@ -85,19 +93,28 @@ class EncoderBlock(nn.Module):
         self.win = 2 * stride
         self.sconv = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size=(self.win, 1), stride=(self.hop, 1)),
                                    nn.ELU(inplace=True))
+        self.in_channels = in_channels
         self.out_channels = out_channels
+        self.packed4 = False
         self._cache = _PackedCache()
+
+    def set_packed4(self, flag):
+        """Input activations (and the three residual blocks) in the packed 4-channel layout; the output stays C8 planar."""
+        self.packed4 = flag
+        for blk in (self.block1, self.block2, self.block3):
+            blk.packed4 = flag
 
     def forward_c8(self, x):
         a = self.block1.forward_c8(x)
         b = self.block2.forward_c8(a)
         a = self.block3.forward_c8(b, out=a)
         c = self.sconv[0]
-        (w,) = self._cache.get((c.weight, c.bias), lambda: (P.pack_down_strip(c.weight, c.bias),))
+        pack = P.pack_down_pairs if self.packed4 else P.pack_down_strip
+        (w,) = self._cache.get((c.weight, c.bias), lambda: (pack(c.weight, c.bias),))
         return ops.conv_down_strip(a, w, P.pad8(self.out_channels))
 
     def forward(self, x):
-        return P.from_c8(self.forward_c8(P.to_c8(x)), self.out_channels)
+        return P.from_c8(self.forward_c8(P.to_p4(x) if self.packed4 else P.to_c8(x)), self.out_channels)
 
 
 class DecoderBlock(nn.Module):
@@ -117,18 +134,26 @@ class DecoderBlock(nn.Module):
         self.block3 = ResidualConv2dBlock(out_channels, out_channels, kernel_size=3, dilation=3)
         self.out_channels = out_channels
         self.out_pad = padding
+        self.packed4 = False
         self._cache = _PackedCache()
+
+    def set_packed4(self, flag):
+        """Output activations (and the three residual blocks) in the packed 4-channel layout; the input stays C8 planar."""
+        self.packed4 = flag
+        for blk in (self.block1, self.block2, self.block3):
+            blk.packed4 = flag
 
     def forward_c8(self, x):
         c = self.tconv[0]
         (w,) = self._cache.get((c.weight, c.bias), lambda: (P.pack_up_strip(c.weight, c.bias),))
-        a = ops.conv_up_strip(x, w, P.pad8(self.out_channels), self.out_pad)
+        a = ops.conv_up_strip(x, w, P.pad8(self.out_channels), self.out_pad, packed4_out=self.packed4)
         b = self.block1.forward_c8(a)
         a = self.block2.forward_c8(b, out=a)
         return self.block3.forward_c8(a, out=b)
 
     def forward(self, x):
-        return P.from_c8(self.forward_c8(P.to_c8(x)), self.out_channels)
+        y = self.forward_c8(P.to_c8(x))
+        return P.from_p4(y, self.out_channels) if self.packed4 else P.from_c8(y, self.out_channels)
 
 
 def _channels(model_complexity):
@@ -157,6 +182,9 @@ class Encoder(nn.Module):
         self.channels = channels
         self.latent_size = latent_size
         self.latent_pad = (latent_size + 15) // 16 * 16
+        # first stage in the packed 4-channel layout (8 B per frame instead of the 16 B of channel-padded C8 planar)
+        self.packed4 = channels[0] <= 4 and channels[1] <= 8
+        self.block1.set_packed4(self.packed4)
         self._cache = _PackedCache()
 
     def _packed(self):
@@ -168,7 +196,7 @@ class Encoder(nn.Module):
     def forward_c8(self, coeffs_bft2):
         """coeffs (B, F, T, 2) fp32 interleaved -> (latents C8 (B, Dp/8, 1, T, 8), [5 embeddings C8])."""
         w_in, b_in, w_lat, b_lat = self._packed()
-        emb = [ops.conv_in(coeffs_bft2, w_in, b_in, self.channels[0])]
+        emb = [ops.conv_in(coeffs_bft2, w_in, b_in, self.channels[0], packed4=self.packed4)]
         for blk in (self.block1, self.block2, self.block3, self.block4):
             emb.append(blk.forward_c8(emb[-1]))
         return ops.conv_lat(emb[-1], w_lat, b_lat, self.latent_pad), emb
@@ -179,7 +207,7 @@ class Encoder(nn.Module):
         with torch.no_grad():
             lat, emb = self.forward_c8(_interleave(coefficients))
             latents = P.from_c8(lat, self.latent_size).squeeze(-2)
-            embeddings = [P.from_c8(e, c) for e, c in zip(emb, self.channels)]
+            embeddings = [P.from_p4(e, c) if e.dim() == 4 else P.from_c8(e, c) for e, c in zip(emb, self.channels)]
         return latents, embeddings, dict()
 
 
@@ -207,7 +235,16 @@ class Decoder(nn.Module):
         self.latent_size = latent_size
         self.latent_pad = (latent_size + 15) // 16 * 16
         self.embedding_size = embedding_size
+        self.packed4 = channels[4] <= 4 and channels[3] <= 8
+        self.block4.set_packed4(self.packed4)
         self._cache = _PackedCache()
+
+    def _embeddings_internal(self, encoder_embeddings):
+        """(B, C, H, T) encoder embeddings (API form) -> the internal layouts the decoder stages use."""
+        out = [P.to_c8(e) for e in encoder_embeddings]
+        if self.packed4:
+            out[0] = P.to_p4(encoder_embeddings[0])
+        return out
 
     def _packed(self):
         ci, co = self.convin[0], self.convout
@@ -239,7 +276,7 @@ class Decoder(nn.Module):
                 raise ValueError('the indicator channel must be all ones (reconstruct) or all zeros (transcribe), as '
                                  'TimbreTrap.decode builds it (modules.py:139-142)')
             lat = _latents_to_c8(latents[:, :-1], self.latent_pad)
-            skips = None if encoder_embeddings is None else [P.to_c8(e) for e in encoder_embeddings]
+            skips = None if encoder_embeddings is None else self._embeddings_internal(encoder_embeddings)
             return self.forward_c8(lat, is_one, skips).permute(0, 3, 1, 2)
 
 
@@ -303,7 +340,7 @@ class TimbreTrap(nn.Module):
         _lib.require_cuda(latents, 'latents')
         with torch.no_grad():
             lat = _latents_to_c8(latents, self.decoder.latent_pad)
-            skips = None if embeddings is None else [P.to_c8(e) for e in embeddings]
+            skips = None if embeddings is None else self.decoder._embeddings_internal(embeddings)
             return self.decoder.forward_c8(lat, not transcribe, skips).permute(0, 3, 1, 2)
 
     def _inference(self, audio, transcribe=False):

@@ -70,23 +70,28 @@ def deconv_in(lat, w, bias_table, c0_pad, h0):
     return y
 
 
-def conv_in(coeffs_bft2, w, b, c0):
-    """coeffs (B, F, T, 2) fp32 interleaved -> C8 planar (B, 1, F, T, 8)."""
+def conv_in(coeffs_bft2, w, b, c0, packed4=False):
+    """coeffs (B, F, T, 2) fp32 interleaved -> C8 planar (B, 1, F, T, 8), or the packed 4-channel layout (B, F, T, 4)."""
     _lib.require_cuda(coeffs_bft2, 'coefficients')
     B, F, T, _ = coeffs_bft2.shape
-    y = torch.empty((B, 1, F, T, 8), dtype=torch.bfloat16, device=coeffs_bft2.device)
+    y = torch.empty((B, F, T, 4) if packed4 else (B, 1, F, T, 8), dtype=torch.bfloat16, device=coeffs_bft2.device)
     with torch.cuda.device(y.device):
-        _lib.check(_lib.lib().tt_conv_in(_p(coeffs_bft2), _p(y), _p(w), _p(b), B, c0, F, T, _s(y)))
+        _lib.check(_lib.lib().tt_conv_in(_p(coeffs_bft2), _p(y), _p(w), _p(b), B, c0, F, T, int(packed4), _s(y)))
     return y
 
 
 def conv_out(x, w, b, c):
-    """C8 planar (B, 1, F, T, 8) -> coeffs (B, F, T, 2) fp32 interleaved."""
-    _check_c8(x)
-    B, _, F, T, _ = x.shape
+    """C8 planar (B, 1, F, T, 8) or packed 4-channel (B, F, T, 4) -> coeffs (B, F, T, 2) fp32 interleaved."""
+    packed4 = x.dim() == 4
+    if packed4:
+        _check_p4(x)
+        B, F, T, _ = x.shape
+    else:
+        _check_c8(x)
+        B, _, F, T, _ = x.shape
     y = torch.empty((B, F, T, 2), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_conv_out(_p(x), _p(y), _p(w), _p(b), B, c, F, T, _s(x)))
+        _lib.check(_lib.lib().tt_conv_out(_p(x), _p(y), _p(w), _p(b), B, c, F, T, int(packed4), _s(x)))
     return y
 
 
@@ -117,18 +122,27 @@ def res_block_strip_p4(x, w1, w2, dilation, out=None):
 
 
 def conv_down_strip(x, w, cout_pad):
-    _check_c8(x)
-    B, CG, H, T, _ = x.shape
+    """C8 planar input, or the packed 4-channel layout (B, H, T, 4) with weights from packing.pack_down_pairs (4 -> 8 channels)."""
+    packed4 = x.dim() == 4
+    if packed4:
+        _check_p4(x)
+        B, H, T, _ = x.shape
+        cin = 8
+    else:
+        _check_c8(x)
+        B, CG, H, T, _ = x.shape
+        cin = CG * 8
     y = torch.empty((B, cout_pad // 8, (H - 4) // 2 + 1, T, 8), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_conv_down_strip(_p(x), _p(y), _p(w), B, CG * 8, cout_pad, H, T, _s(x)))
+        _lib.check(_lib.lib().tt_conv_down_strip(_p(x), _p(y), _p(w), B, cin, cout_pad, H, T, int(packed4), _s(x)))
     return y
 
 
-def conv_up_strip(x, w, cout_pad, out_pad):
+def conv_up_strip(x, w, cout_pad, out_pad, packed4_out=False):
     _check_c8(x)
     B, CG, H, T, _ = x.shape
-    y = torch.empty((B, cout_pad // 8, 2 * H + 2 + out_pad, T, 8), dtype=torch.bfloat16, device=x.device)
+    Hout = 2 * H + 2 + out_pad
+    y = torch.empty((B, Hout, T, 4) if packed4_out else (B, cout_pad // 8, Hout, T, 8), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_conv_up_strip(_p(x), _p(y), _p(w), B, CG * 8, cout_pad, H, out_pad, T, _s(x)))
+        _lib.check(_lib.lib().tt_conv_up_strip(_p(x), _p(y), _p(w), B, CG * 8, cout_pad, H, out_pad, T, int(packed4_out), _s(x)))
     return y

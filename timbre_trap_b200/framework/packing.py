@@ -12,7 +12,7 @@ The C8 planar activation layout is (B, ceil(C/8), H, T, 8) bf16.
 
 import torch
 
-__all__ = ['pack_res_strip_pairs', 'to_p4', 'from_p4', 'pack_down_strip', 'pack_up_strip', 'pack_res_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
+__all__ = ['pack_down_pairs', 'pack_res_strip_pairs', 'to_p4', 'from_p4', 'pack_down_strip', 'pack_up_strip', 'pack_res_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
            'pad_vec']
 
 
@@ -271,3 +271,26 @@ def pack_res_strip_pairs(w1, b1, w2, b2, dilation):
         g2[4 * e: 4 * e + Co, 4 * e: 4 * e + Ci] = w2.detach().float().reshape(Co, Ci)
     w2p = torch.stack([g2, _bias_group(bias2, N)], dim=0).contiguous().to(torch.bfloat16)
     return w1p, w2p
+
+
+def pack_down_pairs(w, b):
+    """
+    sconv.0.weight (Cout <= 8, Cin <= 4, 4, 1) for a packed 4-channel INPUT: GEMM row = frame pair, K group of tap row kh =
+    (e_in, ci), N = (e_out, co) = 16, block-diagonal in the frame parity; each tap row pairs with the ones operand (bias for kh = 0).
+    """
+    Co, Ci = w.shape[:2]
+    assert Co <= 8 and Ci <= 4
+    N = 16
+    dev = w.device
+    wf = w.detach().float()[..., 0]                      # (Co, Ci, 4)
+    zero = torch.zeros((N, 8), dtype=torch.float32, device=dev)
+    bias = torch.zeros(N, dtype=torch.float32, device=dev)
+    for e in range(2):
+        bias[8 * e: 8 * e + Co] = b.detach().float()
+    groups = []
+    for kh in range(4):
+        g = torch.zeros((N, 8), dtype=torch.float32, device=dev)
+        for e in range(2):
+            g[8 * e: 8 * e + Co, 4 * e: 4 * e + Ci] = wf[:, :, kh]
+        groups += [g, _bias_group(bias, N) if kh == 0 else zero]
+    return torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)
