@@ -21,6 +21,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "../../include/timbre_trap_b200.h"
 #include "strip_common.cuh"
@@ -180,18 +181,22 @@ __global__ void __launch_bounds__(strip_threads<CG>(), CG <= 2 ? 2 : 1) res_stri
                 // ones operand, which carries the bias for ky = 0 and zero weights otherwise (never an arbitrary neighbour: stale
                 // shared memory times zero could be NaN)
                 const uint32_t cs = (uint32_t)p.col_step * 16u;
-                bool first = true;
+                auto issue_rows = [&](auto g_tag) {
+                    constexpr int G = decltype(g_tag)::value;
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const uint32_t row = ring0 + (uint32_t)((it + ky * d) % kRing) * slot_bytes;
-                    for (int g = 0; g < p.groups_per_row; g += 2) {
-                        const uint32_t a = row + (uint32_t)g * cs;
-                        const uint32_t lbo = g + 1 < p.groups_per_row ? cs : ones0 - a;
-                        if (issuer) umma::mma_bf16(acc, desc64(desc_lo(a, lbo)), desc64(b_lo), idesc, !first);
-                        first = false;
-                        b_lo += b_step;
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const uint32_t row = ring0 + (uint32_t)((it + ky * d) % kRing) * slot_bytes;
+#pragma unroll
+                        for (int g = 0; g < G; g += 2) {
+                            const uint32_t a = row + (uint32_t)g * cs;
+                            const uint32_t lbo = g + 1 < G ? cs : ones0 - a;
+                            if (issuer) umma::mma_bf16(acc, desc64(desc_lo(a, lbo)), desc64(b_lo), idesc, (ky | g) != 0);
+                            b_lo += b_step;
+                        }
                     }
-                }
+                };
+                if (p.groups_per_row == 3) issue_rows(std::integral_constant<int, 3>{});
+                else issue_rows(std::integral_constant<int, 5>{});
             } else {
                 const uint32_t a_lbo = ((plane >> 4) & 0x3FFFu) << 16;
 #pragma unroll
