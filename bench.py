@@ -222,18 +222,36 @@ def run_ours(args, rank, world, local_rank):
     line = None
     if rank == 0:
         pk = peaks()
-        # ---- roofline of the dominant kernel: the fused residual block at C = 32 (49 % of the conv FLOPs) ----
+        # ---- roofline of the dominant kernel: the fused residual-block kernel (res_strip_kernel, ~60 % of the step).  Every
+        # instance is HBM-bound (arithmetic intensity 17..136 FLOP/B against a ridge of ~210); the line reports the first-stage
+        # instance (C = 4, packed layout, the largest tensors) against the measured copy bandwidth, and the C = 32 instance
+        # against the measured bf16 peak as `roofline_tensor` (the north star's tensor-pipe view).
         n_chunks = min(3 * n_blocks, model.MAX_CHUNKS_PER_BATCH)
+        blk4 = model.encoder.block1.block1
+        x4 = torch.randn((n_chunks, F, M, 4), device=device).to(torch.bfloat16)
+        y4 = torch.empty_like(x4)
+        ms_4 = time_kernel(lambda: blk4.forward_c8(x4, out=y4), iters=10)
+        bytes_4 = 2.0 * x4.numel() * 2                      # read x + write y, un-padded 4 channels, bf16
+        traffic = None
+        tpath = os.path.join(ROOT, 'profiles', 'r01_res_strip_c4_traffic.json')
+        if os.path.exists(tpath):
+            t = json.load(open(tpath))
+            traffic = t['dram_bytes_per_launch'] * (n_chunks / t['chunks'])
+        roofline = dict(kernel='res_strip_kernel<1,8> (fused ResidualConv2dBlock, C=4 packed layout, dilation 1, H=540)', bound='hbm',
+                        achieved=bytes_4 / (ms_4 * 1e-3) / 1e9, peak=pk['hbm'], unit='GB/s', frac=bytes_4 / (ms_4 * 1e-3) / 1e9 / pk['hbm'],
+                        traffic=traffic, peak_source=f"{pk['source']} HBM copy bandwidth", us_per_launch=ms_4 * 1e3,
+                        bytes_per_launch=bytes_4, chunks_per_launch=n_chunks)
+        del x4, y4
         blk = model.encoder.block4.block2
         x32 = torch.randn((n_chunks, 4, 65, M, 8), device=device).to(torch.bfloat16)
         y32 = torch.empty_like(x32)
         ms_k = time_kernel(lambda: blk.forward_c8(x32, out=y32), iters=10)
         flops = 2.0 * (9 * 32 * 32 + 32 * 32) * 65 * M * n_chunks
         achieved = flops / (ms_k * 1e-3) / 1e12
-        roofline = dict(kernel='res_strip_kernel<4,32> (fused ResidualConv2dBlock, C=32, dilation 2)', bound='tensor', achieved=achieved,
-                        peak=pk['bf16_burst'], unit='TFLOP/s', frac=achieved / pk['bf16_burst'], traffic=None,
-                        peak_source=f"{pk['source']} bf16 burst (kernel timed alone)", us_per_launch=ms_k * 1e3,
-                        flops_per_launch=flops)
+        roofline_tensor = dict(kernel='res_strip_kernel<4,32> (fused ResidualConv2dBlock, C=32, dilation 2, H=65)', bound='tensor',
+                               achieved=achieved, peak=pk['bf16_burst'], unit='TFLOP/s', frac=achieved / pk['bf16_burst'],
+                               peak_source=f"{pk['source']} bf16 burst (kernel timed alone)", us_per_launch=ms_k * 1e3,
+                               flops_per_launch=flops, hbm_gbs=2.0 * x32.numel() * 2 / (ms_k * 1e-3) / 1e9)
         del x32, y32
         # ---- CQT forward / inverse against the HBM roofline (BASELINE.json configs[1]: 1024 blocks) ----
         cq = {}
@@ -270,7 +288,7 @@ def run_ours(args, rank, world, local_rank):
                                          '(9 oct x 60 bpo, 22.05 kHz, latent 128, complexity 2), random init',
                                 blocks_per_gpu=n_blocks, chunks_per_gpu=3 * n_blocks, parallelism=f'dp{world} (block sharding)',
                                 l2='working set per step ~40 GB >> 126 MB L2; no explicit flush'),
-                    e2e=e2e, gpu_launches=launches, roofline=roofline, cqt=cq, cpu_baseline=cpu, clocks=clocks)
+                    e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_tensor=roofline_tensor, cqt=cq, cpu_baseline=cpu, clocks=clocks)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -385,11 +385,13 @@ extern "C" int tt_res_block_strip(const void* x, void* y, const void* w1, const 
     p.groups_per_row = packed4 ? 2 * p.halo + 1 : 3;
     p.kg1 = C == 8 ? 3 * (p.groups_per_row + 1) : 9 * (C / 8) + 2;
     // whole-height strips when the batch alone fills the GPU, shorter ones otherwise (each strip re-reads 2d halo rows)
+    // strips: whole-height when the batch alone gives >= 6 waves of CTAs (2 CTAs/SM), shorter otherwise (each extra split re-reads
+    // 2d halo rows but evens out the last wave)
     const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
     int rows = H;
-    const int target = 2 * 148;
+    const long long target = 6 * 2 * 148;
     if (tiles < target) {
-        const int splits = (int)std::min<long long>((target + tiles - 1) / tiles, (H + 7) / 8);
+        const int splits = (int)std::min<long long>((target + tiles - 1) / tiles, std::max(1, H / 32));
         rows = (H + splits - 1) / splits;
     }
     const char* env = getenv("TT_STRIP_ROWS");

@@ -227,9 +227,9 @@ static int launch_updown(const void* x, const UpDownParams& p, cudaStream_t stre
 static int strip_groups(int B, int T, int groups) {
     const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
     int per = groups;
-    const int target = 2 * 148;
+    const long long target = 6 * 2 * 148;
     if (tiles < target) {
-        const int splits = (int)std::min<long long>((target + tiles - 1) / tiles, (groups + 7) / 8);
+        const int splits = (int)std::min<long long>((target + tiles - 1) / tiles, std::max(1, groups / 16));
         per = (groups + splits - 1) / splits;
     }
     const char* env = getenv("TT_STRIP_ROWS");
