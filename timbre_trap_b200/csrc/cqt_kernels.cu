@@ -58,7 +58,7 @@ extern "C" long long tt_launch_count(int reset) {
 
 namespace tt {
 
-constexpr int kColsPerCta = 14;   // A1 / S3: real columns per CTA (even: two per complex transform)
+constexpr int kColsPerCta = 32;   // A1 / S3: real columns per CTA (even: two per complex transform; 32 floats = 128 B runs)
 constexpr int kRowsPerCta = 16;   // A2 / S2: rows per CTA (16 complex = 128 B runs in S)
 constexpr int kFftThreads = 256;
 constexpr int kBinWarps = 4;      // A3 / S1: warps (= bins) per CTA (small CTAs: 5 per SM at 88 registers)
@@ -104,8 +104,7 @@ cols_fwd_kernel(const float* __restrict__ audio, float2* __restrict__ T, FftSpec
         float2 r;
         if ((g & 1) == 0) r = cscale(cadd(a, b), 0.5f);
         else r = cscale(cmul_mi(csub(a, b)), 0.5f);
-        const long long e = ((long long)k1 * n2) % L;
-        r = cmul(r, tw_L[e]);
+        r = cmul(r, tw_L[k1 * n2]);          // k1 <= N1/2 and n2 < N2, so k1 * n2 < L/2: no reduction mod L needed
         Tb[(size_t)k1 * N2 + n2] = r;
     }
 }
@@ -440,8 +439,7 @@ rows_inv_kernel(const float2* __restrict__ S, float2* __restrict__ T, FftSpec sp
     float2* Tb = T + ((size_t)blockIdx.y * K1 + k1_0) * N2;
     for (int i = tid; i < rows * N2; i += kFftThreads) {
         const int r = i / N2, n2 = i - r * N2;
-        const long long e = ((long long)(k1_0 + r) * n2) % L;
-        Tb[i] = cmulc(Gm[i], tw_L[e]);
+        Tb[i] = cmulc(Gm[i], tw_L[(k1_0 + r) * n2]);      // (k1 <= N1/2) * (n2 < N2) < L/2
     }
 }
 
@@ -598,27 +596,26 @@ struct tt_cqt_plan {
 };
 
 static bool factor_2357(int n, FftSpec* spec) {
+    memset(spec, 0, sizeof(*spec));
     spec->n = n;
-    spec->n_passes = 0;
     int r = n;
-    const int order[] = {7, 5, 3};
+    // composite radices first (fewer shared-memory passes), then the primes; radix 4 before 2
+    const int order[] = {10, 9, 6, 7, 5, 4, 3, 2};
     for (int p : order)
         while (r % p == 0) {
             if (spec->n_passes >= kMaxPasses) return false;
             spec->radix[spec->n_passes++] = p;
             r /= p;
         }
-    while (r % 4 == 0) {
-        if (spec->n_passes >= kMaxPasses) return false;
-        spec->radix[spec->n_passes++] = 4;
-        r /= 4;
+    if (r != 1) return false;
+    int s = 1;
+    for (int i = 0; i < spec->n_passes; ++i) {
+        const unsigned per = (unsigned)(n / spec->radix[i]);
+        spec->magic_per[i] = (unsigned)(0x100000000ull / per) + 1u;
+        spec->magic_s[i] = (unsigned)(0x100000000ull / (unsigned)s) + 1u;     // unused when s == 1
+        s *= spec->radix[i];
     }
-    if (r % 2 == 0) {
-        if (spec->n_passes >= kMaxPasses) return false;
-        spec->radix[spec->n_passes++] = 2;
-        r /= 2;
-    }
-    return r == 1;
+    return true;
 }
 
 static void make_twiddles(std::vector<float2>& out, int n, int sign) {

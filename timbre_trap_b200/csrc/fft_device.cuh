@@ -18,6 +18,10 @@ struct FftSpec {
     int n;
     int n_passes;
     int radix[kMaxPasses];
+    // exact division by multiplication for the per-butterfly index split (dividends < 2^20, divisors <= 4096):
+    // x / d == __umulhi(x, magic) with magic = floor(2^32 / d) + 1
+    unsigned magic_per[kMaxPasses];    // d = n / radix   (butterflies per transform)
+    unsigned magic_s[kMaxPasses];      // d = stride of the pass
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -113,6 +117,63 @@ __device__ __forceinline__ void dft_small(float2 (&v)[R]) {
     }
 }
 
+// composite radices (6 = 2x3, 9 = 3x3, 10 = 2x5) as one in-register Cooley-Tukey step: fewer shared-memory passes
+//   X[k1 + R1 k2] = sum_n2 W_R2^{n2 k2} ( W_R^{n2 k1} sum_n1 x[R2 n1 + n2] W_R1^{n1 k1} )
+template <int R> __device__ __forceinline__ float2 comp_tw(int k);     // exp(+2 pi i k / R)
+template <> __device__ __forceinline__ float2 comp_tw<6>(int k) {
+    switch (k) { case 0: return make_float2(1.f, 0.f); case 1: return make_float2(0.5f, 0.86602540378443865f);
+                 default: return make_float2(-0.5f, 0.86602540378443865f); }
+}
+template <> __device__ __forceinline__ float2 comp_tw<9>(int k) {
+    switch (k) { case 0: return make_float2(1.f, 0.f); case 1: return make_float2(0.76604444311897804f, 0.64278760968653933f);
+                 case 2: return make_float2(0.17364817766693035f, 0.98480775301220806f);
+                 default: return make_float2(-0.93969262078590838f, 0.34202014332566873f); }   // k = 4
+}
+template <> __device__ __forceinline__ float2 comp_tw<10>(int k) {
+    switch (k) { case 0: return make_float2(1.f, 0.f); case 1: return make_float2(0.80901699437494742f, 0.58778525229247313f);
+                 case 2: return make_float2(0.30901699437494742f, 0.95105651629515357f);
+                 case 3: return make_float2(-0.30901699437494742f, 0.95105651629515357f);
+                 default: return make_float2(-0.80901699437494742f, 0.58778525229247313f); }  // k = 4
+}
+
+template <int R1, int R2, int SIGN>
+__device__ __forceinline__ void dft_composite(float2 (&v)[R1 * R2]) {
+    constexpr int R = R1 * R2;
+    float2 a[R2][R1];
+#pragma unroll
+    for (int n2 = 0; n2 < R2; ++n2) {
+        float2 t[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) t[n1] = v[R2 * n1 + n2];
+        dft_small<R1, SIGN>(t);
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            if (n2 * k1 == 0) a[n2][k1] = t[k1];
+            else {
+                const float2 w = comp_tw<R>(n2 * k1);
+                a[n2][k1] = SIGN > 0 ? cmul(t[k1], w) : cmulc(t[k1], w);
+            }
+        }
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < R1; ++k1) {
+        float2 t[R2];
+#pragma unroll
+        for (int n2 = 0; n2 < R2; ++n2) t[n2] = a[n2][k1];
+        dft_small<R2, SIGN>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) v[k1 + R1 * k2] = t[k2];
+    }
+}
+
+template <int R, int SIGN>
+__device__ __forceinline__ void dft_any(float2 (&v)[R]) {
+    if constexpr (R == 6) dft_composite<2, 3, SIGN>(v);
+    else if constexpr (R == 9) dft_composite<3, 3, SIGN>(v);
+    else if constexpr (R == 10) dft_composite<2, 5, SIGN>(v);
+    else dft_small<R, SIGN>(v);
+}
+
 // ---------------------------------------------------------------------------------------------
 // shared-memory Stockham autosort (decimation in frequency).  For the pass with remaining length
 // n, stride s and m = n / R, butterfly (p, q), p < m, q < s:
@@ -121,21 +182,22 @@ __device__ __forceinline__ void dft_small(float2 (&v)[R]) {
 // ---------------------------------------------------------------------------------------------
 template <int R, int SIGN>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ src, float2* __restrict__ dst, int N, int n,
-                                              int s, const float2* __restrict__ tw, int n_fft, int tid, int n_threads) {
+                                              int s, const float2* __restrict__ tw, int n_fft, int tid, int n_threads,
+                                              unsigned magic_per, unsigned magic_s) {
     const int m = n / R;
     const int per = N / R;
     const int total = n_fft * per;
     for (int w = tid; w < total; w += n_threads) {
-        const int f = w / per;
+        const int f = per == 1 ? w : (int)__umulhi((unsigned)w, magic_per);
         const int b = w - f * per;
-        const int p = b / s;
+        const int p = s == 1 ? b : (int)__umulhi((unsigned)b, magic_s);
         const int q = b - p * s;
         const float2* x = src + f * N;
         float2* y = dst + f * N;
         float2 v[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) v[i] = x[q + s * (p + i * m)];
-        dft_small<R, SIGN>(v);
+        dft_any<R, SIGN>(v);
         const int step = p * s;   // w_n^{p u} = w_N^{p u s}
         int ti = 0;
 #pragma unroll
@@ -158,12 +220,16 @@ __device__ __forceinline__ float2* run_passes(const FftSpec& spec, float2* a, fl
     int n = spec.n, s = 1;
     for (int i = 0; i < spec.n_passes; ++i) {
         const int r = spec.radix[i];
+        const unsigned mp = spec.magic_per[i], ms = spec.magic_s[i];
         switch (r) {
-            case 2: stockham_pass<2, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads); break;
-            case 3: stockham_pass<3, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads); break;
-            case 4: stockham_pass<4, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads); break;
-            case 5: stockham_pass<5, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads); break;
-            default: stockham_pass<7, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads); break;
+            case 2: stockham_pass<2, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads, mp, ms); break;
+            case 3: stockham_pass<3, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads, mp, ms); break;
+            case 4: stockham_pass<4, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads, mp, ms); break;
+            case 5: stockham_pass<5, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads, mp, ms); break;
+            case 6: stockham_pass<6, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads, mp, ms); break;
+            case 7: stockham_pass<7, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads, mp, ms); break;
+            case 9: stockham_pass<9, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads, mp, ms); break;
+            default: stockham_pass<10, SIGN>(a, b, spec.n, n, s, tw, n_fft, tid, n_threads, mp, ms); break;
         }
         n /= r;
         s *= r;
