@@ -35,6 +35,9 @@ def test_step_losses_match_oracle():
     want = dict(reconstruction=R.reconstruction_loss_ref(rec, coeffs), transcription=R.transcription_loss_ref(act[:2], gt, True))
     want['consistency_spectral'], want['consistency_score'] = R.consistency_loss_ref(trn_rec[:2], trn_scr[:2], trn[:2])
     want['total'] = sum(want.values())
+    # bf16 conv stack: every loss is a sum of squared differences of quantities carrying ~1e-2 relative noise, so besides a
+    # relative tolerance each loss gets an absolute floor of (noise level)^2 x the energy of the compared tensors - the
+    # consistency terms of a random-init model sit at that floor (the two decodes of one latent are almost identical)
+    energy = float(R.reconstruction_loss_ref(trn[:2], torch.zeros_like(trn[:2])))
     for k, v in want.items():
-        # bf16 conv stack: the losses are sums of squares of quantities that agree to ~1e-2 relative
-        np.testing.assert_allclose(float(got[k]), float(v), rtol=3e-2, err_msg=k)
+        np.testing.assert_allclose(float(got[k]), float(v), rtol=3e-2, atol=(1.5e-2) ** 2 * energy, err_msg=k)
