@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libtimbretrap_b200.so')
+LIB_PATH = os.environ.get('TT_LIB_PATH') or os.path.join(_HERE, 'libtimbretrap_b200.so')   # override: A/B builds while tuning
 
 _lib = None
 

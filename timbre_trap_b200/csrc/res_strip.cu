@@ -356,7 +356,20 @@ static int launch_strip(const CUtensorMap& map, const ResStripParams& p, cudaStr
         configured = smem;
     }
     dim3 grid((p.T + kStripTileT - 1) / kStripTileT, (p.H + p.rows_per_strip - 1) / p.rows_per_strip, p.B);
-    res_strip_kernel<CG, NREAL><<<grid, strip_threads<CG>(), smem, stream>>>(map, p);
+    // optional thread-block clusters along T (TT_STRIP_CLUSTER = 2 / 4 / 8): co-schedules the CTAs that own adjacent 128-frame tiles
+    // of the same rows.  Measured on B200: no gain (the kernel is bound by shared-memory operand bandwidth, not DRAM locality),
+    // so the default is 1.
+    static int cluster = -1;
+    if (cluster < 0) { const char* e = getenv("TT_STRIP_CLUSTER"); cluster = e ? atoi(e) : 1; }
+    int cx = 1;
+    for (int c = cluster; c > 1; c >>= 1) if (grid.x % c == 0) { cx = c; break; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(strip_threads<CG>()); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cx; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TT_CUDA_CHECK(cudaLaunchKernelEx(&cfg, res_strip_kernel<CG, NREAL>, map, p));
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;

@@ -12,6 +12,10 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#ifndef TT_WAIT_SLEEP
+#define TT_WAIT_SLEEP 40
+#endif
+
 namespace tt {
 namespace umma {
 
@@ -116,9 +120,24 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
         "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// probe with a suspend-time hint: the thread may be parked by the hardware until the phase completes or the hint expires
+__device__ __forceinline__ bool mbar_try_suspend(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try(bar, parity)) return;
-    while (!mbar_try(bar, parity)) __nanosleep(40);
+#ifdef TT_WAIT_SUSPEND
+    while (!mbar_try_suspend(bar, parity, TT_WAIT_SUSPEND)) {}
+#else
+    while (!mbar_try(bar, parity)) __nanosleep(TT_WAIT_SLEEP);
+#endif
 }
 
 // warp-collective wait: one lane polls (32x less traffic on the shared-memory pipe than every lane spinning), the rest of
