@@ -156,6 +156,10 @@ rows_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ S, FftSpec sp
 //       B[m0][n0] *= w1024^{(m0 + pp) n0}
 //       c[n0 + 32 n1] = sum_{m0} B[m0][n0] w32^{m0 n1}             (after a 32x32 transpose through smem)
 // ---------------------------------------------------------------------------------------------
+// The w1024 table is read with a lane stride of n0 (or lane): power-of-two strides would pile the 16 lanes of a half-warp onto a
+// few bank pairs.  Storing entry i at i ^ ((i >> 4) & 15) spreads every such stride over all 16 bank pairs.
+__device__ __forceinline__ int tw_swz(int i) { return i ^ ((i >> 4) & 15); }
+
 struct BinTables {
     const int* start;
     const int* length;
@@ -207,7 +211,7 @@ bins_fwd_kernel(const float2* __restrict__ S, float* __restrict__ coeffs, BinTab
     float2* tw = smem;                       // 1024 entries, exp(+2 pi i k / 1024)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* tile = smem + M + warp * (32 * 33);
-    for (int i = threadIdx.x; i < M; i += blockDim.x) tw[i] = tw_m[i];
+    for (int i = threadIdx.x; i < M; i += blockDim.x) tw[tw_swz(i)] = tw_m[i];
     __syncthreads();
 
     const long long w = (long long)blockIdx.x * kBinWarps + warp;
@@ -236,7 +240,7 @@ bins_fwd_kernel(const float2* __restrict__ S, float* __restrict__ coeffs, BinTab
     const int base = (lane + pp) & (M - 1);
 #pragma unroll
     for (int n0 = 0; n0 < 32; ++n0) {
-        const float2 t = tw[(base * n0) & (M - 1)];
+        const float2 t = tw[tw_swz((base * n0) & (M - 1))];
         tile[n0 * 33 + lane] = cmul(B[n0], t);
     }
     __syncwarp();
@@ -295,7 +299,7 @@ bins_inv_kernel(const float* __restrict__ coeffs, float2* __restrict__ S, BinTab
     float2* tw = smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float2* tile = smem + M + warp * (32 * 33);
-    for (int i = threadIdx.x; i < M; i += blockDim.x) tw[i] = tw_m[i];
+    for (int i = threadIdx.x; i < M; i += blockDim.x) tw[tw_swz(i)] = tw_m[i];
     __syncthreads();
 
     const long long w = (long long)blockIdx.x * kBinWarps + warp;
@@ -318,7 +322,7 @@ bins_inv_kernel(const float* __restrict__ coeffs, float2* __restrict__ S, BinTab
     const int rows = (shift + len + 31) >> 5;
 #pragma unroll
     for (int m0 = 0; m0 < 32; ++m0) {
-        const float2 t = tw[(((m0 + pp) & (M - 1)) * lane) & (M - 1)];
+        const float2 t = tw[tw_swz((((m0 + pp) & (M - 1)) * lane) & (M - 1))];
         tile[m0 * 33 + lane] = cmulc(v[brev<32>(m0)], t);
     }
     __syncwarp();
