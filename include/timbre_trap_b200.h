@@ -153,6 +153,35 @@ int tt_transcription_loss(const float* estimate, const float* target, int B, int
                           float* out, float* scratch, void* stream);
 
 /*
+ * ---- backward half of the loss step (experiments/train.py:470-496), first native version -----------------------------
+ * Generic direct-convolution gradient kernels on fp32 NCHW tensors (B, C, H, T) for a REGULAR convolution
+ *   y[b,co,ho,t] = bias[co] + sum W[co,ci,kh,kw] x[b,ci, ho*sh + kh*dh - ph, t + kw*dw - pw]     (stride / dilation in T are 1 / dw)
+ * The transposed layers use them with the roles swapped (convT forward = bwd_data, convT backward-data = fwd, convT weight
+ * gradient = bwd_weight with x := dy, dz := x); hout_override gives the row count of the dz-side tensor when output_padding
+ * makes it differ from the regular formula.  bwd_weight ACCUMULATES into dw / db.
+ */
+int tt_conv_fwd_f32(const float* x, const float* w, const float* bias, float* y, int B, int Cin, int Hin, int T, int Cout,
+                    int KH, int KW, int sh, int dh, int dw, int ph, int pw, int act_elu, void* stream);
+int tt_conv_bwd_data_f32(const float* dz, const float* w, float* dx, int B, int Cin, int Hin, int T, int Cout,
+                         int KH, int KW, int sh, int dh, int dw, int ph, int pw, int hout_override, void* stream);
+int tt_conv_bwd_weight_f32(const float* x, const float* dz, float* dw, float* db, int B, int Cin, int Hin, int T, int Cout,
+                           int KH, int KW, int sh, int dh, int dw_, int ph, int pw, int hout_override, void* stream);
+/* db[c] += sum over (b, h, t) of dz (B, C, hw): the bias gradient of the transposed layers */
+int tt_channel_sum(const float* dz, float* db, int B, int C, int64_t hw, void* stream);
+/* dz = dy * ELU'(z), through the activated output a: ELU'(z) = 1 if a > 0 else a + 1 */
+int tt_elu_bwd(const float* dy, const float* a, float* dz, int64_t n, void* stream);
+/* gradients of tt_sum_sq_diff (both arguments; either output may be NULL), tt_transcription_loss (estimate), tanh|c| */
+int tt_sum_sq_diff_bwd(const float* a, const float* b, const float* gout, double scale, float* ga, float* gb, int64_t n, void* stream);
+int tt_transcription_loss_bwd(const float* estimate, const float* target, const float* gout, int B, int F, int T,
+                              int weight_positive_class, float* gest, void* stream);
+int tt_activations_bwd(const float* coeffs, const float* dact, float* dcoeffs, int64_t n, void* stream);
+/* clip_grad_norm_ + AdamW (train.py:493-496): accumulate sum g^2 of every gradient tensor into *acc (double, zeroed by the
+ * caller), then one tt_adamw_step per tensor applies the common clip factor min(1, max_norm / (norm + 1e-6)) and the update */
+int tt_grad_sumsq(const float* g, int64_t n, double* acc, void* stream);
+int tt_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const double* sumsq, float max_norm, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
+
+/*
  * Self-test of the tcgen05 / TMEM plumbing the conv kernels are built on (no reference counterpart):
  * D (128 x n, fp32) = A (128 x k, bf16, row-major) * B (n x k, bf16, row-major)^T on one CTA.
  * swap_lbo_sbo = 1 encodes the shared-memory descriptors with the two stride fields exchanged (must FAIL).

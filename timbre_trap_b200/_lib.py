@@ -44,6 +44,16 @@ SIGNATURES = {
     'tt_loss_scratch_floats': (c_int, []),
     'tt_sum_sq_diff': (c_int, [c_void_p, c_void_p, c_int64, ctypes.c_double, c_void_p, c_void_p, c_void_p]),
     'tt_transcription_loss': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    'tt_conv_fwd_f32': (c_int, [c_void_p] * 4 + [c_int] * 13 + [c_void_p]),
+    'tt_conv_bwd_data_f32': (c_int, [c_void_p] * 3 + [c_int] * 13 + [c_void_p]),
+    'tt_conv_bwd_weight_f32': (c_int, [c_void_p] * 4 + [c_int] * 13 + [c_void_p]),
+    'tt_channel_sum': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]),
+    'tt_elu_bwd': (c_int, [c_void_p] * 3 + [c_int64, c_void_p]),
+    'tt_sum_sq_diff_bwd': (c_int, [c_void_p] * 3 + [ctypes.c_double] + [c_void_p] * 2 + [c_int64, c_void_p]),
+    'tt_transcription_loss_bwd': (c_int, [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p]),
+    'tt_activations_bwd': (c_int, [c_void_p] * 3 + [c_int64, c_void_p]),
+    'tt_grad_sumsq': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    'tt_adamw_step': (c_int, [c_void_p] * 4 + [c_int64, c_void_p] + [ctypes.c_float] * 6 + [c_int, c_void_p]),
     'tt_umma_probe': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'tt_to_decibels': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
 }

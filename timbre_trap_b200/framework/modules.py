@@ -26,12 +26,14 @@ __all__ = ['TimbreTrap', 'Encoder', 'Decoder', 'EncoderBlock', 'DecoderBlock', '
 class _PackedCache:
     """Packed (kernel-layout) copies of a module's parameters, rebuilt when a parameter is modified or moved."""
 
+    epoch = 0       # bumped by code that updates parameters outside torch's version counter (framework/train.py's AdamW kernel)
+
     def __init__(self):
         self._key = None
         self._val = None
 
     def get(self, params, build):
-        key = tuple((p.data_ptr(), p._version, p.device) for p in params)
+        key = (_PackedCache.epoch,) + tuple((p.data_ptr(), p._version, p.device) for p in params)
         if key != self._key:
             with torch.no_grad():
                 self._val = build()

@@ -1,22 +1,45 @@
 """
-Forward half of the reference's loss step (reference: experiments/train.py:393-467): everything from the batch of audio to
-the scalar losses, on the CUDA kernels.  Differences to the reference that do not change values:
-  * the CQT target is computed ONCE and shared with the model forward (the reference computes it twice, train.py:404 and
-    modules.py:366 -> :88);
-  * no per-loss `.item()` host syncs: the losses come back as 0-dim device tensors.
+The reference's loss step (reference: experiments/train.py:393-500) on the CUDA kernels.
 
-The backward half (dgrad / wgrad kernels, clip, AdamW, the NCCL gradient all-reduce) is SURVEY.md section 8 row a16's remaining
-work and is not implemented in this round: this function is for evaluation / validation losses and as the parity anchor
-(tests/test_train_losses_gpu.py) for the numbers a training step must reproduce.
+  compute_step_losses(model, audio, ground_truth)   forward half only (no graph): evaluation / validation losses
+  TrainStep(model, ...).step(audio, ground_truth)   the whole step: CQT target (once), forward with consistency, the four
+                                                    losses, backward, gradient all-reduce (NCCL, when a process group is
+                                                    given), clip_grad_norm_(10), AdamW
+
+Forward kernels are the inference kernels (tcgen05 strips); every layer is a torch.autograd.Function whose backward calls
+the native gradient kernels of csrc/train_kernels.cu (generic direct-convolution dgrad / wgrad on fp32 NCHW - first version,
+CUDA cores).  PyTorch's autograd engine only walks the graph and accumulates `.grad`; there is no cuDNN / ATen compute on the
+path except layout conversions (permute / dtype copies) between the inference layouts (C8 planar / packed4 bf16) and NCHW.
+Differences to the reference that do not change values: the CQT target is computed once (the reference computes it twice,
+train.py:404 and modules.py:366 -> :88); no `.item()` host syncs inside the step; activation gradients travel in bf16 between
+layers (the reference runs the forward under fp16 autocast).
 """
+
+import ctypes
 
 import torch
 
+from .. import _lib
+from . import ops
+from . import packing as P
+from .cqt import CQT
+from .modules import _PackedCache
 from .objectives import compute_consistency_loss, compute_reconstruction_loss, compute_transcription_loss
 
-__all__ = ['compute_step_losses']
+__all__ = ['compute_step_losses', 'TrainStep']
 
 
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _s(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# forward half without a graph
+# ---------------------------------------------------------------------------------------------------------------
 def compute_step_losses(model, audio, ground_truth, multipliers=None, late_start=False):
     """
     audio (B, 1, n*L) on the GPU, ground_truth (B_mpe, F, T) with B_mpe <= B (train.py:393-394, 429).
@@ -50,3 +73,356 @@ def compute_step_losses(model, audio, ground_truth, multipliers=None, late_start
                 total = total + mult['consistency'] * (losses['consistency_spectral'] + losses['consistency_score'])
         losses['total'] = total
     return losses
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# native gradient kernels on fp32 NCHW
+# ---------------------------------------------------------------------------------------------------------------
+def _geom(kh, kw, sh=1, dh=1, dw=1, ph=0, pw=0):
+    return dict(KH=kh, KW=kw, sh=sh, dh=dh, dw=dw, ph=ph, pw=pw)
+
+
+def _conv_fwd(x, w, bias, g, act):
+    B, Cin, Hin, T = x.shape
+    Cout = w.size(0)
+    Hout = (Hin + 2 * g['ph'] - g['dh'] * (g['KH'] - 1) - 1) // g['sh'] + 1
+    y = torch.empty((B, Cout, Hout, T), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().tt_conv_fwd_f32(_p(x), _p(w), _p(bias), _p(y), B, Cin, Hin, T, Cout, g['KH'], g['KW'], g['sh'], g['dh'],
+                                          g['dw'], g['ph'], g['pw'], int(act), _s(x)))
+    return y
+
+
+def _conv_bwd_data(dz, w, x_shape, g):
+    """dz (B, Cout, Hout, T), w (Cout, Cin, KH, KW) -> dx of shape x_shape (B, Cin, Hin, T)."""
+    B, Cin, Hin, T = x_shape
+    Cout, Hout = dz.size(1), dz.size(2)
+    dx = torch.empty(x_shape, dtype=torch.float32, device=dz.device)
+    _lib.check(_lib.lib().tt_conv_bwd_data_f32(_p(dz), _p(w), _p(dx), B, Cin, Hin, T, Cout, g['KH'], g['KW'], g['sh'], g['dh'],
+                                               g['dw'], g['ph'], g['pw'], Hout, _s(dz)))
+    return dx
+
+
+def _conv_bwd_weight(x, dz, w_shape, g, want_bias):
+    """x (B, Cin, Hin, T), dz (B, Cout, Hout, T) -> (dW of shape w_shape, db (Cout) or None)."""
+    B, Cin, Hin, T = x.shape
+    Cout, Hout = dz.size(1), dz.size(2)
+    dw = torch.zeros(w_shape, dtype=torch.float32, device=x.device)
+    db = torch.zeros(Cout, dtype=torch.float32, device=x.device) if want_bias else None
+    _lib.check(_lib.lib().tt_conv_bwd_weight_f32(_p(x), _p(dz), _p(dw), _p(db), B, Cin, Hin, T, Cout, g['KH'], g['KW'], g['sh'],
+                                                 g['dh'], g['dw'], g['ph'], g['pw'], Hout, _s(x)))
+    return dw, db
+
+
+def _elu_bwd(dy, a):
+    dz = torch.empty_like(dy)
+    _lib.check(_lib.lib().tt_elu_bwd(_p(dy), _p(a), _p(dz), dy.numel(), _s(dy)))
+    return dz
+
+
+def _channel_sum(dz):
+    B, C = dz.shape[:2]
+    db = torch.zeros(C, dtype=torch.float32, device=dz.device)
+    _lib.check(_lib.lib().tt_channel_sum(_p(dz), _p(db), B, C, dz.numel() // (B * C), _s(dz)))
+    return db
+
+
+# layout plumbing: inference layouts <-> NCHW fp32
+def _nchw(t, c):
+    """internal activation (C8 planar 5-D, packed4 4-D bf16, or interleaved coefficients (B,F,T,2) fp32) -> (B, c, H, T) fp32."""
+    if t.dtype == torch.float32:
+        return t.permute(0, 3, 1, 2).contiguous()
+    return (P.from_p4(t, c) if t.dim() == 4 else P.from_c8(t, c)).contiguous()
+
+
+def _like(nchw, ref):
+    """(B, c, H, T) fp32 gradient -> the layout / dtype of the forward tensor `ref`."""
+    if ref.dtype == torch.float32:
+        return nchw.permute(0, 2, 3, 1).contiguous()
+    return P.to_p4(nchw) if ref.dim() == 4 else P.to_c8(nchw)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# autograd Functions: fast forward kernel + native backward kernels
+# ---------------------------------------------------------------------------------------------------------------
+class _ConvFn(torch.autograd.Function):
+    """A regular conv layer (+ optional ELU): forward through `run(x)` (an inference kernel), backward generic."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, run, geom, cin, cout, act):
+        y = run(x)
+        ctx.save_for_backward(x, y, weight)
+        ctx.meta = (geom, cin, cout, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, weight = ctx.saved_tensors
+        geom, cin, cout, act = ctx.meta
+        xn, dy = _nchw(x, cin), _nchw(gy, cout)
+        dz = _elu_bwd(dy, _nchw(y, cout)) if act else dy
+        w = weight.detach().float().contiguous()
+        dw, db = _conv_bwd_weight(xn, dz, w.shape, geom, True)
+        gx = _like(_conv_bwd_data(dz, w, xn.shape, geom), x) if ctx.needs_input_grad[0] else None
+        return gx, dw, db, None, None, None, None, None
+
+
+class _ConvTFn(torch.autograd.Function):
+    """A transposed conv layer + ELU (weight (Cin, Cout, KH, KW)); optional per-row bias table handled by the caller."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, run, geom, cin, cout):
+        y = run(x)
+        ctx.save_for_backward(x, y, weight)
+        ctx.meta = (geom, cin, cout)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, weight = ctx.saved_tensors
+        geom, cin, cout = ctx.meta
+        xn = _nchw(x, cin)
+        dz = _elu_bwd(_nchw(gy, cout), _nchw(y, cout))
+        w = weight.detach().float().contiguous()               # (cin, cout, KH, KW) = the regular conv y-space -> x-space
+        # weight gradient: regular-conv roles swapped (its input is dz, its output-side gradient is x)
+        dw, _ = _conv_bwd_weight(dz, xn, w.shape, geom, False)
+        db = _channel_sum(dz)
+        gx = _like(_conv_fwd(dz, w, None, geom, False), x)
+        return gx, dw, db, None, None, None, None
+
+
+class _ResFn(torch.autograd.Function):
+    """ResidualConv2dBlock: fused forward kernel; backward recomputes the inner activation and chains the generic kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, run, c, d):
+        y = run(x)
+        ctx.save_for_backward(x, y, w1, b1, w2)
+        ctx.meta = (c, d)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, w1, b1, w2 = ctx.saved_tensors
+        c, d = ctx.meta
+        g3, g1 = _geom(3, 3, dh=d, dw=d, ph=d, pw=d), _geom(1, 1)
+        xn, yn, dy = _nchw(x, c), _nchw(y, c), _nchw(gy, c)
+        w1f, w2f = w1.detach().float().contiguous(), w2.detach().float().contiguous()
+        a1 = _conv_fwd(xn, w1f, b1.detach().float().contiguous(), g3, True).to(torch.bfloat16).float()   # as the forward kernel staged it
+        dz2 = _elu_bwd(dy, yn - xn)
+        dw2, db2 = _conv_bwd_weight(a1, dz2, w2f.shape, g1, True)
+        dz1 = _elu_bwd(_conv_bwd_data(dz2, w2f, a1.shape, g1), a1)
+        dw1, db1 = _conv_bwd_weight(xn, dz1, w1f.shape, g3, True)
+        gx = _like(dy + _conv_bwd_data(dz1, w1f, xn.shape, g3), x)
+        return gx, dw1, db1, dw2, db2, None, None, None
+
+
+class _ActivationsFn(torch.autograd.Function):
+    """TimbreTrap.to_activations (modules.py:271-289) on interleaved coefficients (B, F, T, 2) -> (B, F, T)."""
+
+    @staticmethod
+    def forward(ctx, coeffs):
+        ctx.save_for_backward(coeffs)
+        return CQT._magnitude(coeffs.permute(0, 3, 1, 2), True)
+
+    @staticmethod
+    def backward(ctx, gact):
+        (coeffs,) = ctx.saved_tensors
+        g = torch.empty_like(coeffs)
+        _lib.check(_lib.lib().tt_activations_bwd(_p(coeffs), _p(gact.contiguous()), _p(g), gact.numel(), _s(coeffs)))
+        return g
+
+
+class _SqDiffFn(torch.autograd.Function):
+    """compute_reconstruction_loss (objectives.py:11-33) on two interleaved coefficient tensors; gradients to both."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return compute_reconstruction_loss(a.permute(0, 3, 1, 2), b.permute(0, 3, 1, 2))
+
+    @staticmethod
+    def backward(ctx, gout):
+        a, b = ctx.saved_tensors
+        scale = 1.0 / (a.size(0) * a.size(2))
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        _lib.check(_lib.lib().tt_sum_sq_diff_bwd(_p(a), _p(b), _p(gout.contiguous()), scale, _p(ga), _p(gb), a.numel(), _s(a)))
+        return ga, gb
+
+
+class _TrnLossFn(torch.autograd.Function):
+    """compute_transcription_loss(estimate, target, weight_positive_class=True) (objectives.py:36-74)."""
+
+    @staticmethod
+    def forward(ctx, est, tgt):
+        ctx.save_for_backward(est, tgt)
+        return compute_transcription_loss(est, tgt, True)
+
+    @staticmethod
+    def backward(ctx, gout):
+        est, tgt = ctx.saved_tensors
+        g = torch.empty_like(est)
+        B, F, T = est.shape
+        _lib.check(_lib.lib().tt_transcription_loss_bwd(_p(est), _p(tgt), _p(gout.contiguous()), B, F, T, 1, _p(g), _s(est)))
+        return g, None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the differentiable forward (same kernels, same order as Encoder / Decoder .forward_c8)
+# ---------------------------------------------------------------------------------------------------------------
+def _res(blk, x):
+    c1, c2 = blk.conv1[0], blk.conv2[0]
+    return _ResFn.apply(x, c1.weight, c1.bias, c2.weight, c2.bias, lambda t: blk.forward_c8(t), blk.channels, blk.dilation)
+
+
+def _encoder(enc, coeffs):
+    ch = enc.channels
+    w_in, b_in, w_lat, b_lat = enc._packed()
+    ci = enc.convin[0]
+    x = _ConvFn.apply(coeffs, ci.weight, ci.bias, lambda t: ops.conv_in(t, w_in, b_in, ch[0], packed4=enc.packed4),
+                      _geom(3, 3, ph=1, pw=1), 2, ch[0], True)
+    for i, blk in enumerate((enc.block1, enc.block2, enc.block3, enc.block4)):
+        for rb in (blk.block1, blk.block2, blk.block3):
+            x = _res(rb, x)
+        sc = blk.sconv[0]
+
+        def run_down(t, blk=blk):
+            pack = P.pack_down_pairs if blk.packed4 else P.pack_down_strip
+            (w,) = blk._cache.get((blk.sconv[0].weight, blk.sconv[0].bias), lambda: (pack(blk.sconv[0].weight, blk.sconv[0].bias),))
+            return ops.conv_down_strip(t, w, P.pad8(blk.out_channels))
+        x = _ConvFn.apply(x, sc.weight, sc.bias, run_down, _geom(4, 1, sh=2), ch[i], ch[i + 1], True)
+    cl = enc.convlat
+    return _ConvFn.apply(x, cl.weight, cl.bias, lambda t: ops.conv_lat(t, w_lat, b_lat, enc.latent_pad),
+                         _geom(cl.weight.size(2), 1), ch[4], enc.latent_size, False)
+
+
+class _IndicatorFn(torch.autograd.Function):
+    """
+    Decoder.convin on latents + the constant indicator channel (modules.py:139-142, 533-536).  Forward: tt_deconv_in with the
+    indicator folded into the bias table.  Backward: transposed-conv gradients with the indicator channel written out (its weight
+    row receives a gradient, its input does not).
+    """
+
+    @staticmethod
+    def forward(ctx, lat, weight, bias, run, flag, d, c0):
+        y = run(lat)
+        ctx.save_for_backward(lat, y, weight)
+        ctx.meta = (flag, d, c0)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        lat, y, weight = ctx.saved_tensors
+        flag, d, c0 = ctx.meta
+        geom = _geom(weight.size(2), 1)
+        ln = _nchw(lat, d)                                                       # (B, D, 1, T)
+        full = torch.cat((ln, torch.full_like(ln[:, :1], flag)), dim=1)          # (B, D+1, 1, T)
+        dz = _elu_bwd(_nchw(gy, c0), _nchw(y, c0))
+        w = weight.detach().float().contiguous()                                # (D+1, C0, H0, 1)
+        dw, _ = _conv_bwd_weight(dz, full, w.shape, geom, False)
+        db = _channel_sum(dz)
+        gfull = _conv_fwd(dz, w, None, geom, False)                             # (B, D+1, 1, T)
+        return _like(gfull[:, :d].contiguous(), lat), dw, db, None, None, None, None
+
+
+def _decoder(dec, lat, reconstruct):
+    ch = dec.channels
+    w_in, tables, w_out, b_out = dec._packed()
+    ci = dec.convin[0]
+    table = tables[1 if reconstruct else 0]
+    x = _IndicatorFn.apply(lat, ci.weight, ci.bias, lambda t: ops.deconv_in(t, w_in, table, P.pad8(ch[0]), dec.embedding_size),
+                           1.0 if reconstruct else 0.0, dec.latent_size, ch[0])
+    for i, blk in enumerate((dec.block1, dec.block2, dec.block3, dec.block4)):
+        tc = blk.tconv[0]
+
+        def run_up(t, blk=blk):
+            (w,) = blk._cache.get((blk.tconv[0].weight, blk.tconv[0].bias), lambda: (P.pack_up_strip(blk.tconv[0].weight, blk.tconv[0].bias),))
+            return ops.conv_up_strip(t, w, P.pad8(blk.out_channels), blk.out_pad, packed4_out=blk.packed4)
+        x = _ConvTFn.apply(x, tc.weight, tc.bias, run_up, _geom(4, 1, sh=2), ch[i], ch[i + 1])
+        for rb in (blk.block1, blk.block2, blk.block3):
+            x = _res(rb, x)
+    co = dec.convout
+    return _ConvFn.apply(x, co.weight, co.bias, lambda t: ops.conv_out(t, w_out, b_out, ch[4]), _geom(3, 3, ph=1, pw=1), ch[4], 2, False)
+
+
+class TrainStep:
+    """
+    One optimisation step of experiments/train.py:393-500 for the base TimbreTrap (no skip connections):
+    losses as in compute_step_losses, backward, optional NCCL all-reduce of one flat gradient bucket (mean over ranks),
+    clip_grad_norm_(max_norm) and AdamW (torch defaults: betas (0.9, 0.999), eps 1e-8, weight_decay 1e-2; train.py:334).
+    """
+
+    def __init__(self, model, lr=1e-3, max_norm=10.0, multipliers=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None):
+        if model.skip_weights is not None:
+            raise NotImplementedError('TrainStep covers the base model (skip_connections=False, experiments/train.py:161)')
+        self.model = model
+        self.params = [p for p in model.parameters()]
+        self.lr, self.max_norm, self.betas, self.eps, self.wd = lr, max_norm, betas, eps, weight_decay
+        self.mult = dict(reconstruction=1, transcription=1, consistency=1)
+        self.mult.update(multipliers or {})
+        self.group = group
+        self.t = 0
+        self.m = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
+        self.v = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
+
+    def losses(self, audio, ground_truth, late_start=False):
+        """The four losses and their total, with the autograd graph attached."""
+        model = self.model
+        with torch.no_grad():
+            coeffs = model.sliCQ.encode_interleaved(audio)
+        lat = _encoder(model.encoder, coeffs)
+        rec = _decoder(model.decoder, lat, True)
+        trn = _decoder(model.decoder, lat, False)
+        act = _ActivationsFn.apply(trn)
+        n = ground_truth.size(0)
+        out = dict(reconstruction=_SqDiffFn.apply(rec, coeffs), transcription=_TrnLossFn.apply(act[:n].contiguous(), ground_truth.float().contiguous()))
+        total = self.mult['reconstruction'] * out['reconstruction']
+        if self.mult['consistency']:
+            lat_t = _encoder(model.encoder, trn)
+            trn_rec = _decoder(model.decoder, lat_t, True)
+            trn_scr = _decoder(model.decoder, lat_t, False)
+            tgt = trn[:n].contiguous()
+            out['consistency_spectral'] = _SqDiffFn.apply(trn_rec[:n].contiguous(), tgt)
+            out['consistency_score'] = _SqDiffFn.apply(trn_scr[:n].contiguous(), tgt)
+        if not late_start:
+            total = total + self.mult['transcription'] * out['transcription']
+            if self.mult['consistency']:
+                total = total + self.mult['consistency'] * (out['consistency_spectral'] + out['consistency_score'])
+        out['total'] = total
+        return out
+
+    def backward(self, total):
+        for p in self.params:
+            p.grad = None
+        total.backward()
+        if self.group is not None:
+            import torch.distributed as dist
+            flat = torch.cat([p.grad.reshape(-1) for p in self.params])          # one 2.46 MB bucket (614,490 fp32)
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            flat /= dist.get_world_size(self.group)
+            off = 0
+            for p in self.params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+
+    def optimizer_step(self):
+        self.t += 1
+        dev = self.params[0].device
+        acc = torch.zeros((), dtype=torch.float64, device=dev)
+        lib = _lib.lib()
+        for p in self.params:
+            _lib.check(lib.tt_grad_sumsq(_p(p.grad), p.numel(), _p(acc), _s(p)))
+        for p, m, v in zip(self.params, self.m, self.v):
+            _lib.check(lib.tt_adamw_step(_p(p.data), _p(p.grad), _p(m), _p(v), p.numel(), _p(acc), self.max_norm, self.lr, self.betas[0],
+                                         self.betas[1], self.eps, self.wd, self.t, _s(p)))
+        _PackedCache.epoch += 1                                                  # weights changed behind torch's back: repack lazily
+        return acc.sqrt()
+
+    def step(self, audio, ground_truth, late_start=False):
+        """Returns the losses (detached 0-dim tensors) and the pre-clip gradient norm."""
+        out = self.losses(audio, ground_truth, late_start)
+        self.backward(out['total'])
+        norm = self.optimizer_step()
+        res = {k: v.detach() for k, v in out.items()}
+        res['grad_norm'] = norm
+        return res
