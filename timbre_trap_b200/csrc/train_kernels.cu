@@ -133,6 +133,72 @@ __global__ void __launch_bounds__(256) conv_bwd_weight_f32_kernel(const float* _
     }
 }
 
+// Same reduction, specialised: the tap loops are compile-time (accumulators stay in registers without predicated updates) and one
+// CTA covers CIT input channels of one output channel (dz is loaded once per CIT * KH * KW products).
+template <int KH, int KW, int CIT>
+__global__ void __launch_bounds__(256) conv_bwd_weight_tiled_kernel(const float* __restrict__ x, const float* __restrict__ dz,
+                                                                    float* __restrict__ dw, float* __restrict__ db, ConvGeom g) {
+    constexpr int TAPS = KH * KW;
+    __shared__ float red[8][CIT * TAPS + 1];
+    const int n_cib = (g.Cin + CIT - 1) / CIT;
+    const int co = blockIdx.y / n_cib, ci0 = (blockIdx.y % n_cib) * CIT;
+    float acc[CIT][TAPS];
+    float accb = 0.f;
+#pragma unroll
+    for (int c = 0; c < CIT; ++c)
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) acc[c][k] = 0.f;
+    const long long n = (long long)g.B * g.Hout * g.T;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % g.T);
+        long long r = i / g.T;
+        const int ho = (int)(r % g.Hout);
+        const int b = (int)(r / g.Hout);
+        const float z = __ldg(dz + (((size_t)b * g.Cout + co) * g.Hout + ho) * g.T + t);
+        accb += z;
+#pragma unroll
+        for (int c = 0; c < CIT; ++c) {
+            if (ci0 + c >= g.Cin) break;
+            const float* xp = x + ((size_t)b * g.Cin + ci0 + c) * g.Hin * g.T;
+#pragma unroll
+            for (int kh = 0; kh < KH; ++kh) {
+                const int hi = ho * g.sh + kh * g.dh - g.ph;
+                const bool h_ok = hi >= 0 && hi < g.Hin;
+#pragma unroll
+                for (int kw = 0; kw < KW; ++kw) {
+                    const int ti = t + kw * g.dw - g.pw;
+                    const float v = (h_ok && ti >= 0 && ti < g.T) ? __ldg(xp + (size_t)hi * g.T + ti) : 0.f;
+                    acc[c][kh * KW + kw] = fmaf(z, v, acc[c][kh * KW + kw]);
+                }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < CIT; ++c)
+#pragma unroll
+        for (int k = 0; k < TAPS; ++k) {
+            float v = acc[c][k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) red[warp][c * TAPS + k] = v;
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) accb += __shfl_xor_sync(0xffffffffu, accb, o);
+    if (lane == 0) red[warp][CIT * TAPS] = accb;
+    __syncthreads();
+    for (int k = threadIdx.x; k <= CIT * TAPS; k += 256) {
+        float v = 0.f;
+        for (int wv = 0; wv < 8; ++wv) v += red[wv][k];
+        if (k < CIT * TAPS) {
+            const int c = k / TAPS, tap = k % TAPS;
+            if (ci0 + c < g.Cin) atomicAdd(dw + ((size_t)co * g.Cin + ci0 + c) * TAPS + tap, v);
+        } else if (db && ci0 == 0) {
+            atomicAdd(db + co, v);
+        }
+    }
+}
+
 // dz = dy * ELU'(z) expressed through the activated output a = ELU(z):  ELU'(z) = 1 (a > 0) or a + 1
 __global__ void elu_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ a, float* __restrict__ dz, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -294,8 +360,16 @@ extern "C" int tt_conv_bwd_weight_f32(const float* x, const float* dz, float* dw
     if (hout_override > 0) g.Hout = hout_override;
     const long long n = (long long)B * g.Hout * T;
     if (n == 0) return TT_OK;
-    dim3 grid((unsigned)std::max<long long>(1, std::min<long long>((n + 256 * 16 - 1) / (256 * 16), 256)), (unsigned)(Cout * Cin));
-    conv_bwd_weight_f32_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, dz, dw, db, g);
+    const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((n + 256 * 16 - 1) / (256 * 16), 256));
+    cudaStream_t s = (cudaStream_t)stream;
+#define TT_WGRAD(KH_, KW_, CIT_)                                                                               \
+    conv_bwd_weight_tiled_kernel<KH_, KW_, CIT_><<<dim3(gx, (unsigned)(Cout * ((Cin + CIT_ - 1) / CIT_))), 256, 0, s>>>(x, dz, dw, db, g)
+    if (KH == 3 && KW == 3) TT_WGRAD(3, 3, 4);
+    else if (KH == 1 && KW == 1) TT_WGRAD(1, 1, 8);
+    else if (KH == 4 && KW == 1) TT_WGRAD(4, 1, 4);
+    else if (KH == 31 && KW == 1) TT_WGRAD(31, 1, 1);
+    else conv_bwd_weight_f32_kernel<<<dim3(gx, (unsigned)(Cout * Cin)), 256, 0, s>>>(x, dz, dw, db, g);
+#undef TT_WGRAD
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;
