@@ -118,6 +118,10 @@ int tt_res_block_strip(const void* x, void* y, const void* w1, const void* w2, i
 /* packed4 = 1: x / y are the packed 4-channel layout (B, H, T, 4) bf16 used by the first encoder / last decoder stage
  * (8 bytes per frame instead of 16: the channel padding of C8 planar would double that stage's HBM traffic); pass C = 8 and
  * weights from packing.pack_res_strip_pairs. */
+/* One 3x3 dilated 'same' conv (k = 3, weights packing.pack_res3x3) or 1x1 conv (k = 1, packing.pack_res1x1), optional ELU, on C8
+ * planar tensors: building block of the backward pass (recompute + data gradients as convs with transformed weights) */
+int tt_conv_same(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,
+                 int act_elu, void* stream);
 /* EncoderBlock.sconv + ELU (modules.py:626-629): Conv2d(Cin, Cout, (4,1), stride (2,1)); Hout = (Hin-4)/2 + 1 */
 int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int T, void* stream);
 /* DecoderBlock.tconv + ELU (modules.py:685-688): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding); Hout = 2 Hin + 2 + out_pad */

@@ -213,3 +213,23 @@ def test_conv_in_out(C0, H, T, B):
     wanto = F.conv2d(xo, wo, bo, padding=1)
     yo = ops.conv_out(P.to_c8(xo.cuda()), wo.cuda().contiguous(), bo.cuda(), C0)
     _assert_close(yo.permute(0, 3, 1, 2).cpu(), wanto, tol=1e-5)
+
+
+@pytest.mark.parametrize('C,H,T,k,d,act', [(4, 37, 256, 3, 1, True), (8, 30, 128, 3, 2, False), (8, 19, 384, 1, 1, False), (16, 33, 256, 3, 3, True),
+                                            (16, 21, 128, 1, 1, True), (32, 65, 256, 3, 2, False), (32, 17, 128, 1, 1, False), (2, 7, 512, 3, 1, False),
+                                            (8, 7, 512, 3, 3, False), (4, 16, 512, 1, 1, False)])
+def test_conv_same(C, H, T, k, d, act):
+    """The single-stage tile-kernel conv used by the backward pass (recompute and data gradients); repeated to catch races."""
+    from timbre_trap_b200.framework import ops, packing as P
+    B = 3
+    x = _bf(_rand((B, C, H, T), 1))
+    w = _bf(_rand((C, C, k, k), 2, 0.3))
+    b = _rand((C,), 3, 0.3) if act else None
+    want = F.conv2d(x, w, b, padding=d if k == 3 else 0, dilation=d if k == 3 else 1)
+    want = F.elu(want) if act else want
+    n = max(16, P.pad8(C))
+    wp = P.pack_res3x3(w.cuda()) if k == 3 else P.pack_res1x1(w.cuda())
+    x8 = P.to_c8(x.cuda())
+    for _ in range(4):
+        y = ops.conv_same(x8, wp, P.pad_vec(b.cuda(), n) if b is not None else None, k, d, act=act)
+        _assert_close(P.from_c8(y, C).cpu(), want)

@@ -114,7 +114,7 @@ def test_step_gradients_match_oracle_autograd():
         if err / max(ref, 1e-12) > worst[0]:
             worst = (err / max(ref, 1e-12), k)
         # relative to the parameter's own gradient, with an absolute floor for the tiny bias vectors (bf16 noise does not shrink with them)
-        assert err <= 1e-1 * ref + 5e-3 * total_norm, (k, err, ref, total_norm)
+        assert err <= 1e-1 * ref + 1e-2 * total_norm, (k, err, ref, total_norm)
     print('global gradient rel-L2 error', (num / den) ** 0.5, 'worst parameter', worst)
     assert (num / den) ** 0.5 <= 3e-2, ((num / den) ** 0.5, worst)
 

@@ -385,6 +385,54 @@ extern "C" int tt_res_block(const void* x, void* y, const void* w1, const float*
     return C == 32 ? launch_conv_rows<32, 32>(p, s) : launch_conv_rows<16, 16>(p, s);
 }
 
+// A single 3x3 dilated 'same' conv (optionally + ELU) or 1x1 conv on C8 planar tensors through the generic tile kernel: used by
+// the backward pass (recompute of the residual block's inner activation; data gradients = convs with transformed weights).
+//   k = 3: weights from packing.pack_res3x3 (K order tap-major);  k = 1: packing.pack_res1x1.  bias may be NULL (zeros).
+extern "C" int tt_conv_same(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,
+                            int act_elu, void* stream) {
+    TT_REQUIRE(x && y && w, "null argument");
+    TT_REQUIRE(C == 8 || C == 16 || C == 32, "conv_same: padded channel count must be 8, 16 or 32 (got %d)", C);
+    TT_REQUIRE((k == 3 && dilation >= 1 && dilation <= 4) || k == 1, "conv_same: 3x3 (dilation 1..4) or 1x1");
+    if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
+    static float* zero_bias = nullptr;
+    if (!bias) {
+        if (!zero_bias) {
+            TT_CUDA_CHECK(cudaMalloc((void**)&zero_bias, 256 * sizeof(float)));
+            TT_CUDA_CHECK(cudaMemset(zero_bias, 0, 256 * sizeof(float)));
+        }
+        bias = zero_bias;
+    }
+    ConvRowsParams p;
+    const int d = k == 3 ? dilation : 0, CG = C / 8;
+    fill_common(p, x, y, w, bias, B, CG, H, T, CG, H);
+    p.groups = H;
+    p.R = std::min(C == 8 ? 16 : (C == 16 ? 8 : 4), kMaxRows);
+    p.sh = 1; p.row_lo = -d; p.in_rows = p.R + 2 * d; p.padT = d;
+    p.out_mode = 0; p.act = act_elu; p.two_stage = 0;
+    const uint32_t TW = kTileT + 2 * d, row_bytes = TW * 16, plane = (uint32_t)p.in_rows * row_bytes;
+    int m = 0;
+    if (k == 3) {
+        auto tap_addr = [&](int tap) { return (uint32_t)(((tap / 3) * d) * TW + (tap % 3) * d) * 16u; };
+        if (CG == 1) {
+            for (int t = 0; t < 10; t += 2) {
+                p.tap_off[m] = tap_addr(t);
+                p.tap_lbo[m] = t + 1 < 9 ? tap_addr(t + 1) - tap_addr(t) : 16u;
+                ++m;
+            }
+            p.kg1 = 10;
+        } else {
+            for (int t = 0; t < 9; ++t)
+                for (int q = 0; q < CG / 2; ++q) { p.tap_off[m] = tap_addr(t) + (uint32_t)(2 * q) * plane; p.tap_lbo[m] = plane; ++m; }
+            p.kg1 = 9 * CG;
+        }
+    } else {
+        if (CG == 1) { p.tap_off[m] = 0; p.tap_lbo[m] = 16u; ++m; p.kg1 = 2; }
+        else { for (int q = 0; q < CG / 2; ++q) { p.tap_off[m] = (uint32_t)(2 * q) * plane; p.tap_lbo[m] = plane; ++m; } p.kg1 = CG; }
+    }
+    p.n_mma1 = m;
+    return dispatch_n1<0>(p, std::max(16, C), (cudaStream_t)stream);
+}
+
 // EncoderBlock.sconv (+ELU): Conv2d(Cin, Cout, (4,1), stride (2,1)).  K order (kh, channel group).
 extern "C" int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int T,
                             void* stream) {

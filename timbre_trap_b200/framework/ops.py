@@ -146,3 +146,14 @@ def conv_up_strip(x, w, cout_pad, out_pad, packed4_out=False):
     with torch.cuda.device(x.device):
         _lib.check(_lib.lib().tt_conv_up_strip(_p(x), _p(y), _p(w), B, CG * 8, cout_pad, H, out_pad, T, int(packed4_out), _s(x)))
     return y
+
+
+def conv_same(x, w, bias, k, dilation=1, act=False):
+    """3x3 dilated 'same' conv (k = 3) or 1x1 conv (k = 1) on a C8 planar tensor, optional ELU (tile kernel, tensor cores)."""
+    _check_c8(x)
+    B, CG, H, T, _ = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_conv_same(_p(x), _p(y), _p(w), _p(bias) if bias is not None else None, B, CG * 8, H, T, k, dilation,
+                                           int(act), _s(x)))
+    return y

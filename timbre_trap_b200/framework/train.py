@@ -190,6 +190,17 @@ class _ConvTFn(torch.autograd.Function):
         return gx, dw, db, None, None, None, None
 
 
+def _conv_same_hi_lo(dz, wp, c, k, d):
+    """
+    Data-gradient conv on the tensor cores with the gradient operand split into bf16 hi + lo parts (two passes, summed in fp32):
+    the weights are the bf16 values the forward pass used (so they are exact for the function being differentiated), and the split
+    keeps ~16 mantissa bits of dz - weight gradients are long sums with heavy cancellation and do not tolerate 8-bit gradients.
+    """
+    hi = P.to_c8(dz)
+    lo = P.to_c8(dz - P.from_c8(hi, c))
+    return (P.from_c8(ops.conv_same(hi, wp, None, k, d), c) + P.from_c8(ops.conv_same(lo, wp, None, k, d), c)).contiguous()
+
+
 class _ResFn(torch.autograd.Function):
     """ResidualConv2dBlock: fused forward kernel; backward recomputes the inner activation and chains the generic kernels."""
 
@@ -206,13 +217,20 @@ class _ResFn(torch.autograd.Function):
         c, d = ctx.meta
         g3, g1 = _geom(3, 3, dh=d, dw=d, ph=d, pw=d), _geom(1, 1)
         xn, yn, dy = _nchw(x, c), _nchw(y, c), _nchw(gy, c)
-        w1f, w2f = w1.detach().float().contiguous(), w2.detach().float().contiguous()
-        a1 = _conv_fwd(xn, w1f, b1.detach().float().contiguous(), g3, True).to(torch.bfloat16).float()   # as the forward kernel staged it
+        w1f, w2f = w1.detach().float(), w2.detach().float()
+        n = max(16, P.pad8(c))
+        # the convolutions of the backward pass run on the tensor cores (tile kernel, bf16 operands):
+        #   inner activation a1 = ELU(W1 (*) x + b1), recomputed exactly as the forward kernel staged it (bf16);
+        #   data gradients = convs with transposed (1x1) / transposed + flipped (3x3) weights
+        x8 = x if x.dim() == 5 else P.to_c8(xn)
+        a1 = P.from_c8(ops.conv_same(x8, P.pack_res3x3(w1f), P.pad_vec(b1, n), 3, d, act=True), c).contiguous()   # the kernels take dense NCHW
         dz2 = _elu_bwd(dy, yn - xn)
         dw2, db2 = _conv_bwd_weight(a1, dz2, w2f.shape, g1, True)
-        dz1 = _elu_bwd(_conv_bwd_data(dz2, w2f, a1.shape, g1), a1)
+        da1 = _conv_same_hi_lo(dz2, P.pack_res1x1(w2f.transpose(0, 1).contiguous()), c, 1, 1)
+        dz1 = _elu_bwd(da1, a1)
         dw1, db1 = _conv_bwd_weight(xn, dz1, w1f.shape, g3, True)
-        gx = _like(dy + _conv_bwd_data(dz1, w1f, xn.shape, g3), x)
+        w1t = w1f.transpose(0, 1).flip(2, 3).contiguous()
+        gx = _like(dy + _conv_same_hi_lo(dz1, P.pack_res3x3(w1t), c, 3, d), x)
         return gx, dw1, db1, dw2, db2, None, None, None
 
 
