@@ -118,6 +118,12 @@ int tt_res_block_strip(const void* x, void* y, const void* w1, const void* w2, i
 /* packed4 = 1: x / y are the packed 4-channel layout (B, H, T, 4) bf16 used by the first encoder / last decoder stage
  * (8 bytes per frame instead of 16: the channel padding of C8 planar would double that stage's HBM traffic); pass C = 8 and
  * weights from packing.pack_res_strip_pairs. */
+/* The same block, row-stationary: every input row meets the weights of all three vertical taps in one N = 3C MMA per
+ * horizontal tap (a third of the shared-memory operand reads of tt_res_block_strip); accumulators of the output rows are TMEM
+ * rings that start out holding the fp32 bias.  Weights from packing.pack_res_rs / pack_res_rs_pairs: w1 (KG1, 3 NC, 8),
+ * w2 (KG2, NC, 8) bf16 and bias (2, NC) fp32 with NC = accumulator columns per row (16 for C <= 16, 32 for C = 32). */
+int tt_res_block_rs(const void* x, void* y, const void* w1, const void* w2, const float* bias, int B, int C, int c_real,
+                    int H, int T, int dilation, int packed4, void* stream);
 /* One 3x3 dilated 'same' conv (k = 3, weights packing.pack_res3x3) or 1x1 conv (k = 1, packing.pack_res1x1), optional ELU, on C8
  * planar tensors: building block of the backward pass (recompute + data gradients as convs with transformed weights) */
 int tt_conv_same(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,

@@ -233,3 +233,47 @@ def test_conv_same(C, H, T, k, d, act):
     for _ in range(4):
         y = ops.conv_same(x8, wp, P.pad_vec(b.cuda(), n) if b is not None else None, k, d, act=act)
         _assert_close(P.from_c8(y, C).cpu(), want)
+
+
+@pytest.mark.parametrize('C,H,T,d,B', [(4, 37, 256, 1, 2), (8, 30, 128, 2, 1), (8, 19, 384, 3, 2), (16, 33, 256, 1, 2),
+                                         (16, 21, 128, 3, 1), (32, 65, 256, 2, 1), (32, 17, 128, 3, 2), (2, 20, 200, 1, 1),
+                                         (4, 540, 128, 3, 1), (32, 5, 128, 3, 1), (16, 2, 100, 2, 3), (16, 67, 128, 2, 1),
+                                         (32, 70, 128, 1, 1)])
+@pytest.mark.parametrize('strip_rows', [None, 7, 2])
+def test_res_block_rs(C, H, T, d, B, strip_rows, monkeypatch):
+    """Row-stationary residual block (csrc/res_rs.cu): image edges, strip seams (rows per strip below the dilation included),
+    TMEM ring wrap-around (H well above the slot count)."""
+    from timbre_trap_b200.framework import ops, packing as P
+    if strip_rows:
+        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+    x = _bf(_rand((B, C, H, T), 1))
+    w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
+    w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
+    mid = _bf(F.elu(F.conv2d(x, w1, b1, padding=d, dilation=d)))
+    want = x + F.elu(F.conv2d(mid, w2, b2))
+    w1p, w2p, bias = P.pack_res_rs(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda())
+    y = ops.res_block_rs(P.to_c8(x.cuda()), w1p, w2p, bias, C, d)
+    torch.cuda.synchronize()
+    _assert_close(P.from_c8(y, C).cpu(), want)
+    if P.pad8(C) != C:
+        assert float(y.float().permute(0, 1, 4, 2, 3).reshape(B, -1, H, T)[:, C:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('C,H,T,d,B', [(4, 37, 256, 1, 2), (4, 30, 512, 2, 1), (4, 540, 256, 3, 1), (2, 20, 200, 1, 1), (3, 9, 260, 3, 2),
+                                         (4, 3, 1024, 2, 1)])
+@pytest.mark.parametrize('strip_rows', [None, 7, 1])
+def test_res_block_rs_packed4(C, H, T, d, B, strip_rows, monkeypatch):
+    from timbre_trap_b200.framework import ops, packing as P
+    if strip_rows:
+        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+    x = _bf(_rand((B, C, H, T), 1))
+    w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
+    w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
+    mid = _bf(F.elu(F.conv2d(x, w1, b1, padding=d, dilation=d)))
+    want = x + F.elu(F.conv2d(mid, w2, b2))
+    w1p, w2p, bias = P.pack_res_rs_pairs(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), d)
+    y = ops.res_block_rs(P.to_p4(x.cuda()), w1p, w2p, bias, 4, d)
+    torch.cuda.synchronize()
+    _assert_close(P.from_p4(y, C).cpu(), want)
+    if C < 4:
+        assert float(y[..., C:].float().abs().max()) == 0.0

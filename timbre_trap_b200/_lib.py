@@ -33,6 +33,7 @@ SIGNATURES = {
     'tt_chunk_crossfade': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'tt_res_block': (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     'tt_res_block_strip': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    'tt_res_block_rs': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     'tt_conv_down_strip': (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     'tt_conv_up_strip': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     'tt_conv_same': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),

@@ -1,0 +1,481 @@
+// Fused ResidualConv2dBlock (reference: timbre_trap/framework/modules.py:721-777), row-stationary form:
+//     y = x + ELU(W2 * ELU(W1 (*)_d x + b1) + b2)      (3x3 dilated 'same' conv, 1x1 conv, residual)
+//
+// The implicit GEMM of res_strip.cu (N = C per MMA, one MMA per tap) re-reads every activation row nine times from shared
+// memory, and the shared-memory operand pipe (128 B/clk/SM) is what bounds it.  Here every INPUT row is multiplied once per
+// horizontal tap against the weights of all three vertical taps at once:
+//
+//     D[128 frames][ (out row r-d | out row r | out row r+d) x C ]  +=  A[row r, shifted by kx*d][K = C] * B[kx][3C][K]
+//
+// i.e. N = 3C and a third of the operand reads.  The accumulators of the output rows live in TMEM as d rings of S slots
+// (rows of equal residue mod d are neighbours in their ring, so the three targets of one input row are adjacent columns; at the
+// ring's wrap-around the MMA is split in two).  Every MMA accumulates: a slot starts out holding the bias, written with
+// tcgen05.st by the epilogue that drained it (so the biases are fp32 and cost no operand traffic).
+//
+//   warp 16 (producer)  one TMA box per input row (all channel groups, 128 + 2 halo frames, zero-filled outside the image)
+//   warp 17 (3x3)       per input row: waits for the row and for the slot of the newest output row, issues the N = 3C MMAs
+//                       in row order (single issuer: accumulation order and the commits are then trivially ordered)
+//   warp 18 (1x1)       the 1x1 conv of output row h from the bf16 intermediate in shared memory
+//   warps 0-15          four epilogue groups (row -> group row % 4; warp quadrant = TMEM lane quadrant), as in res_strip.cu
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "../../include/timbre_trap_b200.h"
+#include "strip_common.cuh"
+
+#ifdef TT_RS_PROFILE
+#include <stdio.h>
+#define TT_PROF(...) __VA_ARGS__
+#else
+#define TT_PROF(...)
+#endif
+
+namespace tt {
+
+constexpr int kRsGroups = 4;
+constexpr int kRsEpiWarps = 16;
+// warps issuing the 3x3 MMAs (input row -> issuer row % n; one thread each).  A row costs its issuer ~1000 cycles of waits, MMA
+// hand-offs and a commit although the tensor pipe needs only ~50 cycles per MMA, so the rows are spread over several issuers;
+// three where two CTAs share an SM (register file: 2 x 21 warps x 48 registers), four for the one-CTA C = 32 plan
+template <int CG> constexpr int rs_issuers1() { return 4; }
+template <int CG> constexpr int rs_threads() { return (kRsEpiWarps + 2 + rs_issuers1<CG>()) * 32; }
+constexpr int kRsSlots = 16;       // TMEM accumulator slots (3x3 rings + 1x1 slots)
+
+struct ResRsParams {
+    __nv_bfloat16* y;
+    const __nv_bfloat16* w1;   // packed (KG1, 3 NC, 8), see packing.pack_res_rs
+    const __nv_bfloat16* w2;   // packed (KG2, NC, 8)
+    const float* bias;         // (2, NC): accumulator-column biases of the 3x3 and the 1x1 conv
+    int B, H, T;
+    int rows_per_strip;
+};
+
+// compile-time plan of one instantiation: CG channel groups, dilation D, P4 = packed 4-channel layout (a 16-byte unit is a frame pair)
+template <int CG, int D, bool P4>
+struct RsPlan {
+    static constexpr int kHalo = P4 ? (D + 1) / 2 : D;               // column halo in 16-byte units
+    static constexpr int kColStep = P4 ? 1 : D;                      // distance between the K groups of a row (CG = 1), 16-byte units
+    static constexpr int kG = P4 ? 2 * kHalo + 1 : 3;                // K groups per row (CG = 1)
+    static constexpr int kRing = CG == 1 ? 32 : (CG == 2 ? 14 : 16);
+    static constexpr int NC = CG >= 4 ? 32 : 16;                     // accumulator columns per output row (padded)
+    static constexpr int N3 = 3 * NC;
+    static constexpr int KG1 = CG == 1 ? kG + 1 : 3 * CG;
+    static constexpr int KG2 = CG == 1 ? 2 : CG;
+    // accumulator slots: the 1x1 stage gets 8 (two per epilogue group, hiding its round trip) where the 3x3 rings still fit
+    static constexpr int A2 = (CG == 4 || D == 3) ? 4 : 8;
+    static constexpr int SR = (kRsSlots - A2 > 12 ? 12 : kRsSlots - A2) / D;   // slots per residue ring
+    static constexpr int TW = kStripTileT + 2 * kHalo;
+    static constexpr int kBars = 0;                                  // 2 kRing + 40 mbarriers (<= 832 bytes)
+    static constexpr int kTmemSlot = 1008;
+    static constexpr int kBias = 1024;
+    static constexpr int kW1 = 1280;
+    static constexpr int kW2 = kW1 + KG1 * N3 * 16;
+    static constexpr int kMid = (kW2 + KG2 * NC * 16 + 127) / 128 * 128;
+    static constexpr int kMidSlot = CG * 2048;
+    static constexpr int kRingBase = kMid + A2 * kMidSlot;
+    static constexpr int kSlotBytes = (CG * TW * 16 + 127) / 128 * 128;
+    static constexpr int kZero = kRingBase + kRing * kSlotBytes;
+    static constexpr int kTotal = kZero + 2048;
+    static_assert(SR >= 3 && D * SR + A2 <= kRsSlots, "TMEM slot plan");
+};
+
+template <int NV>
+__device__ __forceinline__ void tmem_store(uint32_t taddr, const float* v) {
+    if constexpr (NV == 4) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+    } else if constexpr (NV == 8) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+                     "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+    } else {
+        static_assert(NV == 16, "tmem_store: 4, 8 or 16 columns");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                     "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]), "f"(v[10]),
+                     "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]) : "memory");
+    }
+}
+__device__ __forceinline__ void tmem_store_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int CG, int NREAL, int D, bool P4>
+__global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResRsParams p) {
+    using S_ = RsPlan<CG, D, P4>;
+    constexpr int NC = S_::NC, N3 = S_::N3, SR = S_::SR, A2 = S_::A2;
+    constexpr int kRing = S_::kRing, TW = S_::TW, halo = S_::kHalo;
+    constexpr int slot_bytes = S_::kSlotBytes;
+    constexpr int kRsIssuers1 = rs_issuers1<CG>(), kRsThreads = rs_threads<CG>();
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_::kBars);
+    uint64_t* ring_full = bars;                 // [kRing]  TMA landed
+    uint64_t* ring_free = bars + kRing;         // [kRing]  5 arrivals: the commit of the row's 3x3 MMAs + the 4 warps reading it as the residual
+    uint64_t* acc1_full = bars + 2 * kRing;     // [12]     3 arrivals: one commit per contributing input row (stand-ins at the edges)
+    uint64_t* acc1_free = acc1_full + 12;       // [12]     4 arrivals (slot drained and re-initialised with the bias)
+    uint64_t* mid_full = acc1_free + 12;        // [8]      4 arrivals
+    uint64_t* acc2_full = mid_full + 8;         // [8]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S_::kTmemSlot);
+    float* sBias = reinterpret_cast<float*>(smem + S_::kBias);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t* sW1 = smem + S_::kW1;
+    uint8_t* sW2 = smem + S_::kW2;
+    uint8_t* sMid = smem + S_::kMid;
+    uint8_t* sRing = smem + S_::kRingBase;
+    uint8_t* sZero = smem + S_::kZero;
+
+    const int t0 = blockIdx.x * kStripTileT;
+    const int h_start = blockIdx.y * p.rows_per_strip;
+    const int h_end = min(p.H, h_start + p.rows_per_strip);
+    const int n_out = h_end - h_start;
+    const int b = blockIdx.z;
+    // input rows of the strip, relative to h_start: ri_first .. ri_last (rows outside the image contribute nothing and are skipped)
+    const int ri_first = max(-D, -h_start);
+    const int ri_last = min(n_out + D - 1, p.H - 1 - h_start);
+    constexpr uint32_t ncols = kRsSlots * NC;
+    constexpr int acc2_col0 = (kRsSlots - A2) * NC;
+    // accumulator slot of output row it: ring (it % D), position (it / D) % SR; its use number (barrier phase) is (it / D) / SR
+    auto slot_of = [](int it) { return (it % D) * SR + (it / D) % SR; };
+
+    // ---- one-time setup ---------------------------------------------------------------------------------------
+    if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
+    if (tid == 32) {
+        for (int i = 0; i < kRing; ++i) {
+            umma::mbar_init(&ring_full[i], 1);
+            umma::mbar_init(&ring_free[i], 5);
+        }
+        for (int i = 0; i < 12; ++i) {
+            umma::mbar_init(&acc1_full[i], 3);
+            umma::mbar_init(&acc1_free[i], 4);
+        }
+        for (int i = 0; i < 8; ++i) {
+            umma::mbar_init(&mid_full[i], 4);
+            umma::mbar_init(&acc2_full[i], 1);
+        }
+        umma::mbar_fence_init();
+    }
+    for (int i = tid; i < S_::KG1 * N3; i += kRsThreads) reinterpret_cast<uint4*>(sW1)[i] = __ldg(reinterpret_cast<const uint4*>(p.w1) + i);
+    for (int i = tid; i < S_::KG2 * NC; i += kRsThreads) reinterpret_cast<uint4*>(sW2)[i] = __ldg(reinterpret_cast<const uint4*>(p.w2) + i);
+    for (int i = tid; i < 2 * NC; i += kRsThreads) sBias[i] = __ldg(p.bias + i);
+    for (int i = tid; i < 128; i += kRsThreads) reinterpret_cast<uint4*>(sZero)[i] = make_uint4(0u, 0u, 0u, 0u);
+    umma::fence_proxy_async();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+    constexpr int NV = CG == 4 ? 16 : (NREAL >= 8 ? 8 : NREAL);       // columns per TMEM load / store (40 registers per thread when two CTAs share an SM)
+    if (warp < kRsEpiWarps) {
+        // every accumulator slot starts out holding its bias
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int s = warp >> 2; s < kRsSlots; s += kRsGroups) {
+            const float* bsrc = sBias + (s < kRsSlots - A2 ? 0 : NC);
+#pragma unroll
+            for (int c0 = 0; c0 < NREAL; c0 += NV) tmem_store<NV>(lane_addr + (uint32_t)(s * NC + c0), bsrc + c0);
+        }
+        tmem_store_wait();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+
+    if (warp == kRsEpiWarps) {
+        // =================================== producer ===================================
+        if (lane == 0) {
+            constexpr uint32_t bytes = (uint32_t)CG * TW * 16u;
+            for (int ri = ri_first; ri <= ri_last; ++ri) {
+                const int idx = ri - ri_first, slot = idx % kRing;
+                if (idx >= kRing) umma::mbar_wait(&ring_free[slot], (uint32_t)((idx / kRing - 1) & 1));
+                mbar_expect_tx(&ring_full[slot], bytes);
+                tma_load_5d(sRing + (size_t)slot * slot_bytes, &tmap_x, &ring_full[slot], 0, t0 - halo, h_start + ri, 0, b);
+            }
+        }
+    } else if (warp > kRsEpiWarps && warp <= kRsEpiWarps + kRsIssuers1) {
+        // =================================== 3x3 MMA issuers (input rows par, par + 2, ...; one thread each) ===================================
+        // Accumulations into one TMEM slot from different issuing threads are interlocked by the tensor pipe (checked with
+        // scripts/microbench/mma_shared_acc.cu: exact sums, no lost updates), and every MMA accumulates, so the issuers need no
+        // ordering among themselves; an output row is complete when the commits of its (up to) three contributing rows have arrived.
+        if (lane == 0) {
+            const int par = warp - (kRsEpiWarps + 1);
+            constexpr uint32_t idesc1 = umma::make_idesc_bf16(128, NC), idesc2 = umma::make_idesc_bf16(128, 2 * NC), idesc3 = umma::make_idesc_bf16(128, N3);
+            const uint32_t ring0 = umma::smem_u32(sRing), zero0 = umma::smem_u32(sZero), w1_0 = umma::smem_u32(sW1);
+            constexpr uint32_t plane = (uint32_t)TW * 16u;
+            constexpr uint32_t b_step = (2u * N3 * 16u) >> 4;             // two K groups per MMA
+            const uint32_t b_base = desc_lo(w1_0, N3 * 16u);
+            TT_PROF(long long t_ring = 0, t_free = 0, t_issue = 0, t_mma = 0, tp = clock64();)
+            for (int ri = ri_first + par; ri <= ri_last; ri += kRsIssuers1) {
+                const int idx = ri - ri_first;
+                umma::mbar_wait(&ring_full[idx % kRing], (uint32_t)((idx / kRing) & 1));
+                TT_PROF(t_ring += clock64() - tp; tp = clock64();)
+                // target blocks j = 0, 1, 2 <-> output rows ri - D, ri, ri + D (vertical taps ky = 2, 1, 0)
+                const int j0 = ri >= D ? 0 : (ri >= 0 ? 1 : 2);
+                const int j1 = ri + D < n_out ? 2 : (ri < n_out ? 1 : 0);
+                // a slot must have been drained (and re-initialised with the bias) from its previous use before any MMA into it; the
+                // issuers are not ordered among themselves, so each checks all of its targets
+#pragma unroll
+                for (int j = 0; j <= 2; ++j) {
+                    const int it = ri + (j - 1) * D;
+                    if (j >= j0 && j <= j1) {
+                        const int u = (it / D) / SR;
+                        if (u > 0) umma::mbar_wait(&acc1_free[slot_of(it)], (uint32_t)((u - 1) & 1));
+                    }
+                }
+                umma::fence_after_sync();
+                TT_PROF(t_free += clock64() - tp; tp = clock64();)
+                const int res = (ri + D) % D;                            // residue class of the three targets
+                const int q1 = (ri + D) / D - 1;                         // ring sequence number of output row ri
+                const int pa = (q1 - 1 + j0) % SR;
+                const int na = min(j1 - j0 + 1, SR - pa), nb = (j1 - j0 + 1) - na;
+                const uint32_t row = ring0 + (uint32_t)(idx % kRing) * slot_bytes;
+                auto issue = [&](int pos, int jb, int nblk) {
+                    const uint32_t acc = tmem + (uint32_t)((res * SR + pos) * NC);
+                    const uint32_t idesc = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
+                    uint32_t b_lo = b_base + (uint32_t)(jb * NC);         // + jb * NC rows of 16 bytes, in 16-byte units
+                    if constexpr (CG == 1) {
+                        // kG K groups at column offsets g * kColStep, consumed as pairs (g, g+1); the unpaired last group meets a zero
+                        // operand (never an arbitrary neighbour: stale shared memory times zero could be NaN)
+                        constexpr uint32_t cs = (uint32_t)S_::kColStep * 16u;
+#pragma unroll
+                        for (int g = 0; g < S_::kG; g += 2) {
+                            const uint32_t a = row + (uint32_t)g * cs;
+                            const uint32_t lbo = g + 1 < S_::kG ? cs : zero0 - a;
+                            umma::mma_bf16(acc, desc64(desc_lo(a, lbo)), desc64(b_lo), idesc, true);
+                            b_lo += b_step;
+                        }
+                    } else {
+                        const uint32_t row_lo = ((row >> 4) & 0x3FFFu) | (((plane >> 4) & 0x3FFFu) << 16);
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                            for (int q = 0; q < CG / 2; ++q) {
+                                umma::mma_bf16(acc, desc64(row_lo + (uint32_t)(kx * D) + (uint32_t)(2 * q) * (plane >> 4)), desc64(b_lo), idesc, true);
+                                b_lo += b_step;
+                            }
+                        }
+                    }
+                };
+                if (na > 0) issue(pa, j0, na);
+                if (nb > 0) issue(0, j0 + na, nb);
+                TT_PROF(t_mma += clock64() - tp; tp = clock64();)
+                umma::commit(&ring_free[idx % kRing]);
+                if (ri < 0 || ri >= n_out) mbar_arrive_n(&ring_free[idx % kRing], 4);     // no residual readers for halo rows
+#pragma unroll
+                for (int j = 0; j <= 2; ++j)
+                    if (j >= j0 && j <= j1) umma::commit(&acc1_full[slot_of(ri + (j - 1) * D)]);
+                if (ri >= 0 && ri < n_out) {
+                    // stand in for the contributing rows that do not exist (above / below the image or the strip's halo)
+                    const int missing = (ri - D < ri_first ? 1 : 0) + (ri + D > ri_last ? 1 : 0);
+                    if (missing) mbar_arrive_n(&acc1_full[slot_of(ri)], (uint32_t)missing);
+                }
+                TT_PROF(t_issue += clock64() - tp; tp = clock64();)
+            }
+            TT_PROF(if (par == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+                        const int nr = (ri_last - ri_first) / kRsIssuers1 + 1;
+                        printf("rs issuer1[0]: rows %d  cycles/row: ring wait %lld, slot wait %lld, mma %lld, commits %lld\n", nr, t_ring / nr,
+                               t_free / nr, t_mma / nr, t_issue / nr);
+                    })
+        }
+    } else if (warp == kRsEpiWarps + kRsIssuers1 + 1) {
+        // =================================== 1x1 MMA issuer ===================================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma::make_idesc_bf16(128, NC);
+            const uint32_t zero0 = umma::smem_u32(sZero), mid0 = umma::smem_u32(sMid), w2_0 = umma::smem_u32(sW2);
+            const uint32_t b_lo0 = desc_lo(w2_0, NC * 16u);
+            constexpr uint32_t b_step = (2u * NC * 16u) >> 4;
+            TT_PROF(long long t_mid = 0, t_iss = 0, tp = clock64();)
+            for (int it = 0; it < n_out; ++it) {
+                const int u = it / A2, a = it % A2;
+                umma::mbar_wait(&mid_full[a], (uint32_t)(u & 1));
+                umma::fence_after_sync();
+                TT_PROF(t_mid += clock64() - tp; tp = clock64();)
+                const uint32_t acc = tmem + (uint32_t)(acc2_col0 + a * NC);
+                const uint32_t mid = mid0 + (uint32_t)a * S_::kMidSlot;
+                if constexpr (CG == 1) {
+                    umma::mma_bf16(acc, desc64(desc_lo(mid, zero0 - mid)), desc64(b_lo0), idesc, true);
+                } else {
+                    const uint32_t a_lo = desc_lo(mid, 2048u);
+#pragma unroll
+                    for (int q = 0; q < CG / 2; ++q)
+                        umma::mma_bf16(acc, desc64(a_lo + (uint32_t)(2 * q) * (2048u >> 4)), desc64(b_lo0 + (uint32_t)q * b_step), idesc, true);
+                }
+                umma::commit(&acc2_full[a]);
+                TT_PROF(t_iss += clock64() - tp; tp = clock64();)
+            }
+            TT_PROF(if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+                        printf("rs issuer2: cycles/row: mid wait %lld, issue %lld\n", t_mid / n_out, t_iss / n_out);)
+        }
+    } else if (warp < kRsEpiWarps) {
+        // =================================== epilogue groups ===================================
+        const int quad = warp & 3, g = warp >> 2;
+        const int j = quad * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+        const bool t_ok = t0 + j < p.T;
+        uint4* const y_thread = reinterpret_cast<uint4*>(p.y) + ((size_t)b * CG * p.H + h_start) * p.T + t0 + j;
+        const size_t y_plane = (size_t)p.H * p.T;
+        TT_PROF(long long t_w1 = 0, t_e1 = 0, t_w2 = 0, t_e2 = 0, tp = clock64();)
+        // ---- 3x3 accumulator -> ELU -> bf16 intermediate (A operand of the 1x1 conv); slot <- bias ----
+        auto epi1 = [&](int it) {
+            const int sl = slot_of(it), a = it % A2;
+            TT_PROF(tp = clock64();)
+            umma::mbar_wait(&acc1_full[sl], (uint32_t)(((it / D) / SR) & 1));
+            umma::fence_after_sync();
+            TT_PROF(t_w1 += clock64() - tp; tp = clock64();)
+            uint8_t* mid = sMid + (size_t)a * S_::kMidSlot + (size_t)j * 16u;
+#pragma unroll
+            for (int c0 = 0; c0 < NREAL; c0 += NV) {
+                float v[NV];
+                tmem_load<NV>(lane_addr + (uint32_t)(sl * NC + c0), v);
+                tmem_store<NV>(lane_addr + (uint32_t)(sl * NC + c0), sBias + c0);
+#pragma unroll
+                for (int k = 0; k < NV; ++k) v[k] = elu_f(v[k]);
+#pragma unroll
+                for (int k = 0; k < NV; k += 8) {
+                    uint4 o;
+                    o.x = pack2(v[k], v[k + 1]);
+                    o.y = pack2(v[k + 2], v[k + 3]);
+                    if constexpr (NV >= 8) { o.z = pack2(v[k + 4], v[k + 5]); o.w = pack2(v[k + 6], v[k + 7]); }
+                    else { o.z = 0u; o.w = 0u; }
+                    *reinterpret_cast<uint4*>(mid + (size_t)((c0 + k) >> 3) * 2048u) = o;
+                    if constexpr (NV < 8) break;
+                }
+            }
+            tmem_store_wait();
+            umma::fence_before_sync();
+            umma::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&acc1_free[sl]);
+                mbar_arrive(&mid_full[a]);
+            }
+            TT_PROF(t_e1 += clock64() - tp;)
+        };
+        // ---- 1x1 accumulator -> ELU -> + x -> bf16 -> global; slot <- bias ----
+        auto epi2 = [&](int it) {
+            const int u = it / A2, a = it % A2;
+            TT_PROF(tp = clock64();)
+            umma::mbar_wait(&acc2_full[a], (uint32_t)(u & 1));
+            umma::fence_after_sync();
+            TT_PROF(t_w2 += clock64() - tp; tp = clock64();)
+            const int ridx = it - ri_first;                            // ring index of row h
+            const uint8_t* res = sRing + (size_t)(ridx % kRing) * slot_bytes + (size_t)(j + halo) * 16u;
+#pragma unroll
+            for (int c0 = 0; c0 < NREAL; c0 += NV) {
+                float v[NV];
+                tmem_load<NV>(lane_addr + (uint32_t)(acc2_col0 + a * NC + c0), v);
+                tmem_store<NV>(lane_addr + (uint32_t)(acc2_col0 + a * NC + c0), sBias + NC + c0);
+#pragma unroll
+                for (int k = 0; k < NV; k += 8) {
+                    const int cg = (c0 + k) >> 3;
+                    const uint4 rx = *reinterpret_cast<const uint4*>(res + (size_t)cg * TW * 16u);
+                    const __nv_bfloat162* rh = reinterpret_cast<const __nv_bfloat162*>(&rx);
+                    float r[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(rh[e]);
+                        r[2 * e] = f.x;
+                        r[2 * e + 1] = f.y;
+                    }
+                    constexpr int NE = NV >= 8 ? 8 : NV;
+#pragma unroll
+                    for (int e = 0; e < NE; ++e) r[e] += elu_f(v[k + e]);
+                    uint4 o;
+                    o.x = pack2(r[0], r[1]);
+                    o.y = pack2(r[2], r[3]);
+                    if constexpr (NE >= 8) { o.z = pack2(r[4], r[5]); o.w = pack2(r[6], r[7]); }
+                    else { o.z = 0u; o.w = 0u; }
+                    if (t_ok) y_thread[(size_t)cg * y_plane + (size_t)it * p.T] = o;
+                    if constexpr (NV < 8) break;
+                }
+            }
+            tmem_store_wait();
+            umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring_free[ridx % kRing]);
+            TT_PROF(t_e2 += clock64() - tp;)
+        };
+        if constexpr (A2 >= 2 * kRsGroups) {
+            // two slot sets per group: the 1x1 round trip of a row overlaps the first epilogue of the group's next row
+            int prev = -1;
+            for (int it = g; it < n_out; it += kRsGroups) {
+                epi1(it);
+                if (prev >= 0) epi2(prev);
+                prev = it;
+            }
+            if (prev >= 0) epi2(prev);
+        } else {
+            for (int it = g; it < n_out; it += kRsGroups) {
+                epi1(it);
+                epi2(it);
+            }
+        }
+        TT_PROF(if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+                    const int nr = (n_out + kRsGroups - 1) / kRsGroups;
+                    printf("rs epilogue group 0: rows %d  cycles/row: acc1 wait %lld, epi1 %lld, acc2 wait %lld, epi2 %lld\n", nr, t_w1 / nr,
+                           t_e1 / nr, t_w2 / nr, t_e2 / nr);
+                })
+    }
+
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+template <int CG, int NREAL, int D, bool P4>
+static int launch_rs(const void* x, ResRsParams p, cudaStream_t stream) {
+    using S_ = RsPlan<CG, D, P4>;
+    static bool configured = false;
+    if (!configured) {
+        TT_CUDA_CHECK(cudaFuncSetAttribute(res_rs_kernel<CG, NREAL, D, P4>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::kTotal));
+        configured = true;
+    }
+    CUtensorMap map;
+    const int rc = make_row_map(&map, x, p.B, CG, p.H, p.T, S_::TW);
+    if (rc) return rc;
+    dim3 grid((p.T + kStripTileT - 1) / kStripTileT, (p.H + p.rows_per_strip - 1) / p.rows_per_strip, p.B);
+    res_rs_kernel<CG, NREAL, D, P4><<<grid, rs_threads<CG>(), S_::kTotal, stream>>>(map, p);
+    TT_CUDA_CHECK(cudaGetLastError());
+    tt_count_launches(1);
+    return TT_OK;
+}
+
+template <int CG, int NREAL, bool P4>
+static int launch_rs_d(const void* x, const ResRsParams& p, int dilation, cudaStream_t stream) {
+    if (dilation == 1) return launch_rs<CG, NREAL, 1, P4>(x, p, stream);
+    if (dilation == 2) return launch_rs<CG, NREAL, 2, P4>(x, p, stream);
+    return launch_rs<CG, NREAL, 3, P4>(x, p, stream);
+}
+
+}  // namespace tt
+
+using namespace tt;
+
+extern "C" int tt_res_block_rs(const void* x, void* y, const void* w1, const void* w2, const float* bias, int B, int C, int c_real,
+                               int H, int T, int dilation, int packed4, void* stream) {
+    TT_REQUIRE(x && y && w1 && w2 && bias, "null argument");
+    TT_REQUIRE(C == 8 || C == 16 || C == 32, "res block: padded channel count must be 8, 16 or 32 (got %d)", C);
+    TT_REQUIRE(!packed4 || (C == 8 && c_real <= 4 && T % 2 == 0), "packed layout: at most 4 channels and an even frame count");
+    TT_REQUIRE(dilation >= 1 && dilation <= 3, "dilation must be in [1,3]");
+    TT_REQUIRE(c_real >= 1 && c_real <= C, "bad real channel count");
+    if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
+    ResRsParams p;
+    p.y = (__nv_bfloat16*)y; p.w1 = (const __nv_bfloat16*)w1; p.w2 = (const __nv_bfloat16*)w2; p.bias = bias;
+    // packed4: memory is (B, H, T, 4) bf16; a 16-byte unit is a PAIR of frames (e, 4 channels), so the kernel sees an 8-channel
+    // tensor with T/2 "frames" whose taps are the pair offsets -halo..halo (Toeplitz-expanded weights, packing.pack_res_rs_pairs)
+    if (packed4) T /= 2;
+    p.B = B; p.H = H; p.T = T;
+    // whole-height strips when the batch alone gives >= 6 waves of CTAs (2 CTAs/SM), shorter otherwise (each extra split re-reads
+    // 2d halo rows but evens out the last wave)
+    const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
+    int rows = H;
+    const long long target = 6 * 2 * 148;
+    if (tiles < target) {
+        const int splits = (int)std::min<long long>((target + tiles - 1) / tiles, std::max(1, H / 32));
+        rows = (H + splits - 1) / splits;
+    }
+    const char* env = getenv("TT_STRIP_ROWS");
+    if (env) rows = std::max(1, atoi(env));
+    p.rows_per_strip = std::min(rows, H);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (packed4) return launch_rs_d<1, 8, true>(x, p, dilation, s);
+    if (C == 8) return c_real <= 4 ? launch_rs_d<1, 4, false>(x, p, dilation, s) : launch_rs_d<1, 8, false>(x, p, dilation, s);
+    if (C == 16) return launch_rs_d<2, 16, false>(x, p, dilation, s);
+    return launch_rs_d<4, 32, false>(x, p, dilation, s);
+}

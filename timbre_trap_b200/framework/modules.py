@@ -11,6 +11,7 @@ Activations between layers live in the C8 planar bf16 layout (B, ceil(C/8), H, T
 """
 
 import ctypes
+import os
 
 import torch
 import torch.nn as nn
@@ -45,6 +46,10 @@ def _n16(c):
     return max(16, P.pad8(c))
 
 
+# residual-block kernel: 'rs' = row-stationary (csrc/res_rs.cu), 'strip' = one MMA per tap (csrc/res_strip.cu)
+_RES_KERNEL = os.environ.get('TT_RES_KERNEL', 'strip')
+
+
 class ResidualConv2dBlock(nn.Module):
     """modules.py:721-777: y = x + ELU(conv1x1(ELU(conv3x3_dilated(x)))), one fused kernel."""
 
@@ -62,13 +67,19 @@ class ResidualConv2dBlock(nn.Module):
 
     def _packed(self):
         c1, c2 = self.conv1[0], self.conv2[0]
+        key = (c1.weight, c1.bias, c2.weight, c2.bias)
+        if _RES_KERNEL == 'rs':
+            if self.packed4:
+                return self._cache.get(key, lambda: P.pack_res_rs_pairs(c1.weight, c1.bias, c2.weight, c2.bias, self.dilation))
+            return self._cache.get(key, lambda: P.pack_res_rs(c1.weight, c1.bias, c2.weight, c2.bias))
         if self.packed4:
-            return self._cache.get((c1.weight, c1.bias, c2.weight, c2.bias),
-                                   lambda: P.pack_res_strip_pairs(c1.weight, c1.bias, c2.weight, c2.bias, self.dilation))
-        return self._cache.get((c1.weight, c1.bias, c2.weight, c2.bias),
-                               lambda: P.pack_res_strip(c1.weight, c1.bias, c2.weight, c2.bias))
+            return self._cache.get(key, lambda: P.pack_res_strip_pairs(c1.weight, c1.bias, c2.weight, c2.bias, self.dilation))
+        return self._cache.get(key, lambda: P.pack_res_strip(c1.weight, c1.bias, c2.weight, c2.bias))
 
     def forward_c8(self, x, out=None):
+        if _RES_KERNEL == 'rs':
+            w1, w2, bias = self._packed()
+            return ops.res_block_rs(x, w1, w2, bias, self.channels, self.dilation, out=out)
         w1, w2 = self._packed()
         if self.packed4:
             return ops.res_block_strip_p4(x, w1, w2, self.dilation, out=out)

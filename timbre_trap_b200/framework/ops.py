@@ -121,6 +121,25 @@ def res_block_strip_p4(x, w1, w2, dilation, out=None):
     return y
 
 
+def res_block_rs(x, w1, w2, bias, c_real, dilation, out=None):
+    """Row-stationary fused residual block (csrc/res_rs.cu); weights from packing.pack_res_rs (C8 planar x) or
+    packing.pack_res_rs_pairs (packed 4-channel x of shape (B, H, T, 4))."""
+    packed4 = x.dim() == 4
+    if packed4:
+        _check_p4(x)
+        B, H, T, _ = x.shape
+        C, c_real = 8, 4
+    else:
+        _check_c8(x)
+        B, CG, H, T, _ = x.shape
+        C = CG * 8
+    _lib.require_cuda(bias, 'bias')
+    y = torch.empty_like(x) if out is None else out
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_res_block_rs(_p(x), _p(y), _p(w1), _p(w2), _p(bias), B, C, c_real, H, T, dilation, int(packed4), _s(x)))
+    return y
+
+
 def conv_down_strip(x, w, cout_pad):
     """C8 planar input, or the packed 4-channel layout (B, H, T, 4) with weights from packing.pack_down_pairs (4 -> 8 channels)."""
     packed4 = x.dim() == 4

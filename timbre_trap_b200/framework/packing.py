@@ -273,6 +273,76 @@ def pack_res_strip_pairs(w1, b1, w2, b2, dilation):
     return w1p, w2p
 
 
+def pack_res_rs(w1, b1, w2, b2):
+    """
+    Weights of one ResidualConv2dBlock for csrc/res_rs.cu (row-stationary: an input row meets all three vertical taps at once).
+    W1 -> (KG1, 3 NC, 8): B rows n = j * NC + co with j = 0, 1, 2 <-> output rows r-d, r, r+d, i.e. vertical taps ky = 2, 1, 0;
+      C <= 8 : K groups kx = 0, 1, 2 (8 input channels each), then a zero group so that groups pair up into K = 16 MMAs;
+      C >= 16: K groups (kx, channel group), kx-major.
+    W2 -> (KG2, NC, 8): channel groups (C <= 8: plus a zero group).  bias -> (2, NC) fp32: the accumulators' initial values.
+    NC = 16 for C <= 16, 32 for C = 32.
+    """
+    Co, Ci = w1.shape[:2]
+    Cp = pad8(Ci)
+    CG = Cp // 8
+    NC = 32 if Cp >= 32 else 16
+    dev = w1.device
+    w = w1.detach().float()
+    taps = torch.zeros((3, 3, NC, Cp), dtype=torch.float32, device=dev)           # [j][kx][co][ci]
+    for j in range(3):
+        taps[j, :, :Co, :Ci] = w[:, :, 2 - j, :].permute(2, 0, 1)
+    groups = [taps[:, kx, :, 8 * g: 8 * g + 8].reshape(3 * NC, 8) for kx in range(3) for g in range(CG)]
+    if CG == 1:
+        groups.append(torch.zeros((3 * NC, 8), dtype=torch.float32, device=dev))
+    w1p = torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)
+    k2 = torch.zeros((NC, Cp), dtype=torch.float32, device=dev)
+    k2[:Co, :Ci] = w2.detach().float().reshape(Co, Ci)
+    groups2 = [k2[:, 8 * g: 8 * g + 8] for g in range(CG)]
+    if CG == 1:
+        groups2.append(torch.zeros((NC, 8), dtype=torch.float32, device=dev))
+    w2p = torch.stack(groups2, dim=0).contiguous().to(torch.bfloat16)
+    bias = torch.zeros((2, NC), dtype=torch.float32, device=dev)
+    bias[0, :Co] = b1.detach().float()
+    bias[1, :Co] = b2.detach().float()
+    return w1p, w2p, bias
+
+
+def pack_res_rs_pairs(w1, b1, w2, b2, dilation):
+    """
+    pack_res_rs for the packed 4-channel layout (C <= 4): a GEMM row is a PAIR of frames, a K group is (frame parity e_in, 4
+    channels) of the input pair at offset o in [-hp, hp], hp = ceil((d+1)/2) // see pack_res_strip_pairs; accumulator column
+    = (e_out, co).  K groups: o = -hp..hp, then a zero group.
+    """
+    Co, Ci = w1.shape[:2]
+    assert Co <= 4 and Ci <= 4
+    d = int(dilation)
+    hp = (d + 1) // 2
+    NC = 16
+    dev = w1.device
+    w = w1.detach().float()
+    groups = []
+    for o in range(-hp, hp + 1):
+        g = torch.zeros((3, NC, 8), dtype=torch.float32, device=dev)
+        for j in range(3):
+            for e_out in range(2):
+                for e_in in range(2):
+                    s_ = 2 * o + e_in - e_out
+                    for kx in range(3):
+                        if (kx - 1) * d == s_:
+                            g[j, 4 * e_out: 4 * e_out + Co, 4 * e_in: 4 * e_in + Ci] = w[:, :, 2 - j, kx]
+        groups.append(g.reshape(3 * NC, 8))
+    groups.append(torch.zeros((3 * NC, 8), dtype=torch.float32, device=dev))
+    w1p = torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)
+    g2 = torch.zeros((NC, 8), dtype=torch.float32, device=dev)
+    bias = torch.zeros((2, NC), dtype=torch.float32, device=dev)
+    for e in range(2):
+        g2[4 * e: 4 * e + Co, 4 * e: 4 * e + Ci] = w2.detach().float().reshape(Co, Ci)
+        bias[0, 4 * e: 4 * e + Co] = b1.detach().float()
+        bias[1, 4 * e: 4 * e + Co] = b2.detach().float()
+    w2p = torch.stack([g2, torch.zeros_like(g2)], dim=0).contiguous().to(torch.bfloat16)
+    return w1p, w2p, bias
+
+
 def pack_down_pairs(w, b):
     """
     sconv.0.weight (Cout <= 8, Cin <= 4, 4, 1) for a packed 4-channel INPUT: GEMM row = frame pair, K group of tap row kh =
