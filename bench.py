@@ -222,7 +222,7 @@ def run_ours(args, rank, world, local_rank):
     line = None
     if rank == 0:
         pk = peaks()
-        # ---- roofline of the dominant kernel: the fused residual-block kernel (res_strip_kernel, ~60 % of the step).  Every
+        # ---- roofline of the dominant kernel: the fused residual-block kernel (res_rs_kernel, ~60 % of the step).  Every
         # instance is HBM-bound (arithmetic intensity 17..136 FLOP/B against a ridge of ~210); the line reports the first-stage
         # instance (C = 4, packed layout, the largest tensors) against the measured copy bandwidth, and the C = 32 instance
         # against the measured bf16 peak as `roofline_tensor` (the north star's tensor-pipe view).
@@ -233,11 +233,11 @@ def run_ours(args, rank, world, local_rank):
         ms_4 = time_kernel(lambda: blk4.forward_c8(x4, out=y4), iters=10)
         bytes_4 = 2.0 * x4.numel() * 2                      # read x + write y, un-padded 4 channels, bf16
         traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_res_strip_c4_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'r01_res_rs_c4_traffic.json')
         if os.path.exists(tpath):
             t = json.load(open(tpath))
             traffic = t['dram_bytes_per_launch'] * (n_chunks / t['chunks'])
-        roofline = dict(kernel='res_strip_kernel<1,8> (fused ResidualConv2dBlock, C=4 packed layout, dilation 1, H=540)', bound='hbm',
+        roofline = dict(kernel='res_rs_kernel<2,16,1,4> (fused ResidualConv2dBlock, C=4 packed layout folded to 4 frames per GEMM row, dilation 1, H=540)', bound='hbm',
                         achieved=bytes_4 / (ms_4 * 1e-3) / 1e9, peak=pk['hbm'], unit='GB/s', frac=bytes_4 / (ms_4 * 1e-3) / 1e9 / pk['hbm'],
                         traffic=traffic, peak_source=f"{pk['source']} HBM copy bandwidth", us_per_launch=ms_4 * 1e3,
                         bytes_per_launch=bytes_4, chunks_per_launch=n_chunks)
@@ -248,7 +248,7 @@ def run_ours(args, rank, world, local_rank):
         ms_k = time_kernel(lambda: blk.forward_c8(x32, out=y32), iters=10)
         flops = 2.0 * (9 * 32 * 32 + 32 * 32) * 65 * M * n_chunks
         achieved = flops / (ms_k * 1e-3) / 1e12
-        roofline_tensor = dict(kernel='res_strip_kernel<4,32> (fused ResidualConv2dBlock, C=32, dilation 2, H=65)', bound='tensor',
+        roofline_tensor = dict(kernel='res_rs_kernel<4,32,2,0> (fused ResidualConv2dBlock, C=32, dilation 2, H=65)', bound='tensor',
                                achieved=achieved, peak=pk['bf16_burst'], unit='TFLOP/s', frac=achieved / pk['bf16_burst'],
                                peak_source=f"{pk['source']} bf16 burst (kernel timed alone)", us_per_launch=ms_k * 1e3,
                                flops_per_launch=flops, hbm_gbs=2.0 * x32.numel() * 2 / (ms_k * 1e-3) / 1e9)

@@ -111,19 +111,18 @@ int tt_chunk_crossfade(const float* chunks, const float* window, int batch, int 
 /* ResidualConv2dBlock.forward (modules.py:743-777), fused: y = x + ELU(W2 * ELU(W1 (*)_dilation x + b1) + b2) */
 int tt_res_block(const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
                  int B, int C, int H, int T, int dilation, void* stream);
-/* The same block as a warp-specialised, row-pipelined kernel (TMA row ring -> tcgen05 -> TMEM -> epilogue warps);
- * weights from packing.pack_res_strip (biases folded in as a K group); c_real = un-padded channel count. */
-int tt_res_block_strip(const void* x, void* y, const void* w1, const void* w2, int B, int C, int c_real, int H, int T,
-                       int dilation, int packed4, void* stream);
-/* packed4 = 1: x / y are the packed 4-channel layout (B, H, T, 4) bf16 used by the first encoder / last decoder stage
- * (8 bytes per frame instead of 16: the channel padding of C8 planar would double that stage's HBM traffic); pass C = 8 and
- * weights from packing.pack_res_strip_pairs. */
-/* The same block, row-stationary: every input row meets the weights of all three vertical taps in one N = 3C MMA per
- * horizontal tap (a third of the shared-memory operand reads of tt_res_block_strip); accumulators of the output rows are TMEM
- * rings that start out holding the fp32 bias.  Weights from packing.pack_res_rs / pack_res_rs_pairs: w1 (KG1, 3 NC, 8),
- * w2 (KG2, NC, 8) bf16 and bias (2, NC) fp32 with NC = accumulator columns per row (16 for C <= 16, 32 for C = 32). */
+/* The same block as a warp-specialised, row-pipelined kernel (TMA row ring -> tcgen05 -> TMEM -> epilogue warps), in
+ * row-stationary form: every input row meets the weights of all three vertical taps in one N = 3C MMA per horizontal tap (a third
+ * of the shared-memory operand reads of one-MMA-per-tap); accumulators of the output rows are TMEM rings that start out holding
+ * the fp32 bias.  c_real = un-padded channel count.  layout selects how memory maps to GEMM rows:
+ *   0  C8 planar (B, C/8, H, T, 8), one frame per row                         weights packing.pack_res_rs
+ *   1  packed (B, H, T, 4), a row = 2 frames x 4 channels (pass C = 8)        weights packing.pack_res_rs_pairs
+ *   2  C8 planar with C = 8, folded: a row = 2 frames x 8 channels            weights packing.pack_res_rs_fold(..., fold=2)
+ *   4  packed (B, H, T, 4), folded: a row = 4 frames x 4 channels (C = 8)     weights packing.pack_res_rs_fold(..., fold=4)
+ * (folding makes every row 16 values wide, so the per-row hand-offs cover 2-4x more frames: the fast path for C <= 8).
+ * w1 (KG1, 3 NC, 8), w2 (KG2, NC, 8) bf16 and bias (2, NC) fp32 with NC = accumulator columns per row (16, or 32 for C = 32). */
 int tt_res_block_rs(const void* x, void* y, const void* w1, const void* w2, const float* bias, int B, int C, int c_real,
-                    int H, int T, int dilation, int packed4, void* stream);
+                    int H, int T, int dilation, int layout, void* stream);
 /* One 3x3 dilated 'same' conv (k = 3, weights packing.pack_res3x3) or 1x1 conv (k = 1, packing.pack_res1x1), optional ELU, on C8
  * planar tensors: building block of the backward pass (recompute + data gradients as convs with transformed weights) */
 int tt_conv_same(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,

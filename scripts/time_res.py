@@ -1,4 +1,4 @@
-"""Device timing of one residual block (either kernel) at a bench shape: python scripts/time_res.py C H d [B] [kernel] [iters]."""
+"""Device timing of one residual block at a bench shape: python scripts/time_res.py C H d [B] [kernel: rs|fold] [iters]."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,12 +15,12 @@ w2, b2 = torch.randn(C, C, 1, 1, device='cuda') * 0.3, torch.randn(C, device='cu
 packed = C <= 4
 x = (torch.randn((B, H, T, 4), device='cuda') if packed else torch.randn((B, (C + 7) // 8, H, T, 8), device='cuda')).to(torch.bfloat16)
 y = torch.empty_like(x)
-if kernel == 'rs':
+if kernel == 'fold':
+    w1p, w2p, bias = P.pack_res_rs_fold(w1, b1, w2, b2, d, 4 if packed else 2)
+    fn = lambda: ops.res_block_rs(x, w1p, w2p, bias, C, d, out=y, fold=True)
+else:
     w1p, w2p, bias = P.pack_res_rs_pairs(w1, b1, w2, b2, d) if packed else P.pack_res_rs(w1, b1, w2, b2)
     fn = lambda: ops.res_block_rs(x, w1p, w2p, bias, C, d, out=y)
-else:
-    w1p, w2p = P.pack_res_strip_pairs(w1, b1, w2, b2, d) if packed else P.pack_res_strip(w1, b1, w2, b2)
-    fn = (lambda: ops.res_block_strip_p4(x, w1p, w2p, d, out=y)) if packed else (lambda: ops.res_block_strip(x, w1p, w2p, C, d, out=y))
 for _ in range(2): fn()
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -44,27 +44,6 @@ def test_res_block(C, H, T, d, B):
         assert float(y.float().permute(0, 1, 4, 2, 3).reshape(B, -1, H, T)[:, C:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize('C,H,T,d,B', [(4, 37, 256, 1, 2), (8, 30, 128, 2, 1), (8, 19, 384, 3, 2), (16, 33, 256, 1, 2),
-                                         (16, 21, 128, 3, 1), (32, 65, 256, 2, 1), (32, 17, 128, 3, 2), (2, 20, 200, 1, 1),
-                                         (4, 540, 128, 3, 1), (32, 5, 128, 3, 1), (16, 2, 100, 2, 3)])
-@pytest.mark.parametrize('strip_rows', [None, 7])
-def test_res_block_strip(C, H, T, d, B, strip_rows, monkeypatch):
-    from timbre_trap_b200.framework import ops, packing as P
-    if strip_rows:
-        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
-    x = _bf(_rand((B, C, H, T), 1))
-    w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
-    w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
-    mid = _bf(F.elu(F.conv2d(x, w1, b1, padding=d, dilation=d)))
-    want = x + F.elu(F.conv2d(mid, w2, b2))
-    w1p, w2p = P.pack_res_strip(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda())
-    y = ops.res_block_strip(P.to_c8(x.cuda()), w1p, w2p, C, d)
-    torch.cuda.synchronize()
-    _assert_close(P.from_c8(y, C).cpu(), want)
-    if P.pad8(C) != C:
-        assert float(y.float().permute(0, 1, 4, 2, 3).reshape(B, -1, H, T)[:, C:].abs().max()) == 0.0
-
-
 @pytest.mark.parametrize('Cin,Cout,H,T,B', [(4, 8, 40, 256, 2), (8, 16, 27, 128, 1), (16, 32, 33, 256, 2), (32, 64, 65, 128, 1),
                                               (2, 4, 20, 100, 1)])
 def test_conv_down(Cin, Cout, H, T, B):
@@ -76,26 +55,6 @@ def test_conv_down(Cin, Cout, H, T, B):
     y = ops.conv_down(P.to_c8(x.cuda()), P.pack_down(w.cuda()), P.pad_vec(b.cuda(), n), P.pad8(Cout))
     assert y.shape[2] == want.shape[2]
     _assert_close(P.from_c8(y, Cout).cpu(), want)
-
-
-@pytest.mark.parametrize('C,H,T,d,B', [(4, 37, 256, 1, 2), (4, 30, 512, 2, 1), (4, 540, 256, 3, 1), (2, 20, 200, 1, 1), (3, 9, 260, 3, 2),
-                                         (4, 3, 1024, 2, 1)])
-@pytest.mark.parametrize('strip_rows', [None, 7])
-def test_res_block_strip_packed4(C, H, T, d, B, strip_rows, monkeypatch):
-    from timbre_trap_b200.framework import ops, packing as P
-    if strip_rows:
-        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
-    x = _bf(_rand((B, C, H, T), 1))
-    w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
-    w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
-    mid = _bf(F.elu(F.conv2d(x, w1, b1, padding=d, dilation=d)))
-    want = x + F.elu(F.conv2d(mid, w2, b2))
-    w1p, w2p = P.pack_res_strip_pairs(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), d)
-    y = ops.res_block_strip_p4(P.to_p4(x.cuda()), w1p, w2p, d)
-    torch.cuda.synchronize()
-    _assert_close(P.from_p4(y, C).cpu(), want)
-    if C < 4:
-        assert float(y[..., C:].float().abs().max()) == 0.0
 
 
 @pytest.mark.parametrize('Cin,Cout,H,T,B', [(4, 8, 540, 128, 1), (8, 16, 269, 256, 2), (16, 32, 133, 128, 1), (32, 64, 65, 256, 2),
@@ -277,3 +236,28 @@ def test_res_block_rs_packed4(C, H, T, d, B, strip_rows, monkeypatch):
     _assert_close(P.from_p4(y, C).cpu(), want)
     if C < 4:
         assert float(y[..., C:].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('C,H,T,d,B,fold', [(4, 37, 512, 1, 2, 4), (4, 30, 1024, 2, 1, 4), (4, 540, 512, 3, 1, 4), (2, 20, 200, 1, 1, 4),
+                                              (3, 9, 260, 3, 2, 4), (8, 30, 256, 1, 2, 2), (8, 269, 512, 2, 1, 2), (8, 19, 384, 3, 2, 2),
+                                              (5, 12, 130, 3, 1, 2), (8, 3, 1024, 1, 1, 2)])
+@pytest.mark.parametrize('strip_rows', [None, 7])
+def test_res_block_rs_folded(C, H, T, d, B, fold, strip_rows, monkeypatch):
+    """Folded rows: 4 frames x 4 channels of the packed layout, or 2 frames x 8 channels of C8 planar, per GEMM row."""
+    from timbre_trap_b200.framework import ops, packing as P
+    if strip_rows:
+        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+    x = _bf(_rand((B, C, H, T), 1))
+    w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
+    w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
+    mid = _bf(F.elu(F.conv2d(x, w1, b1, padding=d, dilation=d)))
+    want = x + F.elu(F.conv2d(mid, w2, b2))
+    w1p, w2p, bias = P.pack_res_rs_fold(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), d, fold)
+    xin = P.to_p4(x.cuda()) if fold == 4 else P.to_c8(x.cuda())
+    y = ops.res_block_rs(xin, w1p, w2p, bias, C, d, fold=True)
+    torch.cuda.synchronize()
+    got = P.from_p4(y, C) if fold == 4 else P.from_c8(y, C)
+    _assert_close(got.cpu(), want)
+    pad = y[..., C:] if fold == 4 else y.float().permute(0, 1, 4, 2, 3).reshape(B, -1, H, T)[:, C:]
+    if pad.numel():
+        assert float(pad.float().abs().max()) == 0.0

@@ -89,11 +89,75 @@ def test_chunk_slicing_matches_reference_loop():
             assert torch.equal(chunks[b * n_chunks + i, 0], padded[b, 0, i * (L // 2): i * (L // 2) + L])
 
 
+def _emulate_rs(x_rows, w1p, bias, d, shifts, step, halo, NC):
+    """The GEMMs csrc/res_rs.cu issues for the 3x3 stage, in torch: x_rows (H, Tr, K) GEMM rows, w1p (KG, 3 NC, 8) packed weights with
+    K groups ordered (shift, 8-wide chunk); input row r, shift s reads rows t + s * step - halo and feeds output rows r-d, r, r+d."""
+    H, Tr, K = x_rows.shape
+    kc = K // 8
+    w = w1p.float().reshape(shifts, -1, 3, NC, 8)[:, :kc]                         # [shift][chunk][j][n][k]
+    xp = torch.nn.functional.pad(x_rows, (0, 0, halo, halo))
+    acc = bias[0].float().view(1, 1, NC).repeat(H, Tr, 1)
+    for r in range(H):
+        for s_ in range(shifts):
+            a = xp[r, s_ * step: s_ * step + Tr].reshape(Tr, kc, 8)
+            for j in range(3):
+                o = r + (j - 1) * d
+                if 0 <= o < H:
+                    acc[o] += torch.einsum('tck,cnk->tn', a, w[s_, :, j])
+    return acc
+
+
+def test_weight_packing_row_stationary():
+    """packing.pack_res_rs / _pairs / _fold against F.conv2d through a torch emulation of the kernel's GEMM schedule."""
+    import torch.nn.functional as F
+    from timbre_trap_b200.framework import packing as P
+    torch.manual_seed(0)
+    H, T = 7, 24
+    for C, d, mode in ((16, 2, 'planar'), (32, 1, 'planar'), (4, 1, 'fold4'), (3, 3, 'fold4'), (8, 2, 'fold2'), (5, 3, 'fold2'),
+                       (4, 3, 'pairs'), (8, 1, 'planar8')):
+        x = torch.randn(1, C, H, T).to(torch.bfloat16).float()
+        w1, b1 = torch.randn(C, C, 3, 3).to(torch.bfloat16).float(), torch.randn(C)
+        w2, b2 = torch.randn(C, C, 1, 1).to(torch.bfloat16).float(), torch.randn(C)
+        want = F.conv2d(x, w1, b1, padding=d, dilation=d)[0]                   # (C, H, T)
+        if mode.startswith('fold'):
+            fold = int(mode[-1]); Cw = 16 // fold
+            w1p, w2p, bias = P.pack_res_rs_fold(w1, b1, w2, b2, d, fold)
+            hp = (d + 1) // 2 if fold == 2 else 1
+            assert tuple(w1p.shape) == (2 * (2 * hp + 1), 48, 8) and tuple(w2p.shape) == (2, 16, 8) and tuple(bias.shape) == (2, 16)
+            rows = torch.zeros(H, T // fold, fold, Cw)
+            rows[..., :C] = x[0].permute(1, 2, 0).reshape(H, T // fold, fold, C)
+            acc = _emulate_rs(rows.reshape(H, T // fold, 16), w1p, bias, d, 2 * hp + 1, 1, hp, 16)
+            got = acc.reshape(H, T // fold, fold, Cw)[..., :C].reshape(H, T, C).permute(2, 0, 1)
+        elif mode == 'pairs':
+            w1p, w2p, bias = P.pack_res_rs_pairs(w1, b1, w2, b2, d)
+            hp = (d + 1) // 2
+            assert tuple(w1p.shape) == (2 * hp + 2, 48, 8)
+            rows = torch.zeros(H, T // 2, 2, 4)
+            rows[..., :C] = x[0].permute(1, 2, 0).reshape(H, T // 2, 2, C)
+            # K groups are single 8-wide chunks per shift here (the kernel pairs neighbouring shifts into one K = 16 MMA)
+            acc = _emulate_rs(rows.reshape(H, T // 2, 8), w1p[:2 * hp + 1], bias, d, 2 * hp + 1, 1, hp, 16)
+            got = acc.reshape(H, T // 2, 16)[..., :8].reshape(H, T // 2, 2, 4)[..., :C].reshape(H, T, C).permute(2, 0, 1)
+        else:
+            w1p, w2p, bias = P.pack_res_rs(w1, b1, w2, b2)
+            Cp, NC = P.pad8(C), (32 if C >= 32 else 16)
+            assert tuple(w1p.shape) == (3 * (Cp // 8) + (1 if Cp == 8 else 0), 3 * NC, 8) and w1p.dtype == torch.bfloat16
+            rows = torch.zeros(H, T, Cp)
+            rows[..., :C] = x[0].permute(1, 2, 0)
+            acc = _emulate_rs(rows, w1p[:3 * (Cp // 8)], bias, d, 3, d, d, NC)
+            got = acc[..., :C].permute(2, 0, 1)
+        assert float((got - want).abs().max()) <= 2e-2 * float(want.abs().max()), (C, d, mode)
+        # 1x1 stage: block-diagonal over the frames of a folded row, biases in the accumulator-column order
+        n2 = w2p.float().permute(1, 0, 2).reshape(w2p.shape[1], -1)              # [n][k over the row]
+        Cw = {'fold4': 4, 'fold2': 8, 'pairs': 4}.get(mode, None)
+        if Cw:
+            assert torch.allclose(n2[:C, :C], w2.reshape(C, C)) and torch.allclose(n2[Cw:Cw + C, Cw:Cw + C], w2.reshape(C, C))
+            assert float(n2[:Cw, Cw:2 * Cw].abs().max()) == 0.0 and torch.allclose(bias[1, Cw:Cw + C], b2)
+        else:
+            assert torch.allclose(n2[:C, :C], w2.reshape(C, C)) and torch.allclose(bias[1, :C], b2)
+
+
 def test_weight_packing_shapes():
     from timbre_trap_b200.framework import packing as P
-    for C, kg1, kg2, n in ((4, 12, 2, 16), (8, 12, 2, 16), (16, 20, 4, 16), (32, 38, 6, 32)):
-        w1, w2 = P.pack_res_strip(torch.randn(C, C, 3, 3), torch.randn(C), torch.randn(C, C, 1, 1), torch.randn(C))
-        assert tuple(w1.shape) == (kg1, n, 8) and tuple(w2.shape) == (kg2, n, 8) and w1.dtype == torch.bfloat16
     w, b = torch.randn(129, 64, 31, 1), torch.randn(64)
     packed, tables = P.pack_deconv_in(w, b, 128)
     assert tuple(packed.shape) == (31, 16, 64, 8) and tuple(tables.shape) == (2, 31, 64)

@@ -37,11 +37,8 @@ namespace tt {
 
 constexpr int kRsGroups = 4;
 constexpr int kRsEpiWarps = 16;
-// warps issuing the 3x3 MMAs (input row -> issuer row % n; one thread each).  A row costs its issuer ~1000 cycles of waits, MMA
-// hand-offs and a commit although the tensor pipe needs only ~50 cycles per MMA, so the rows are spread over several issuers;
-// three where two CTAs share an SM (register file: 2 x 21 warps x 48 registers), four for the one-CTA C = 32 plan
-template <int CG> constexpr int rs_issuers1() { return 4; }
-template <int CG> constexpr int rs_threads() { return (kRsEpiWarps + 2 + rs_issuers1<CG>()) * 32; }
+// warps: 16 epilogue + TMA producer + scout + 3x3 issuer + 1x1 issuer (the last four use one thread each)
+constexpr int kRsThreads = (kRsEpiWarps + 4) * 32;
 constexpr int kRsSlots = 16;       // TMEM accumulator slots (3x3 rings + 1x1 slots)
 
 struct ResRsParams {
@@ -53,16 +50,28 @@ struct ResRsParams {
     int rows_per_strip;
 };
 
-// compile-time plan of one instantiation: CG channel groups, dilation D, P4 = packed 4-channel layout (a 16-byte unit is a frame pair)
-template <int CG, int D, bool P4>
+// Layout modes.  A GEMM row is normally one frame of a C8 planar tensor.  Small channel counts are FOLDED so that a GEMM row is
+// 16 values wide whatever C is (every barrier hand-off, MMA and epilogue pass then covers 2-4x more frames, and those per-row
+// costs are what bounds the kernel): the 3x3 kernel is Toeplitz-expanded over the frames of a row on the host.
+constexpr int kRsPlanar = 0;   // C8 planar (B, CG, H, T, 8); taps are frame shifts of d
+constexpr int kRsPairs8 = 1;   // packed (B, H, T, 4) seen as T/2 rows of 8 values (CG = 1); shifts of one pair
+constexpr int kRsFold2 = 2;    // C <= 8: C8 planar with one channel group seen as T/2 rows of 16 values (2 frames x 8 channels)
+constexpr int kRsFold4 = 4;    // C <= 4: packed (B, H, T, 4) seen as T/4 rows of 16 values (4 frames x 4 channels)
+
+// compile-time plan of one instantiation: CG channel groups (of the GEMM row), dilation D, layout mode
+template <int CG, int D, int MODE>
 struct RsPlan {
-    static constexpr int kHalo = P4 ? (D + 1) / 2 : D;               // column halo in 16-byte units
-    static constexpr int kColStep = P4 ? 1 : D;                      // distance between the K groups of a row (CG = 1), 16-byte units
+    static constexpr bool P4 = MODE == kRsPairs8;
+    static constexpr bool kFolded = MODE >= kRsFold2;
+    static_assert(!kFolded || CG == 2, "folded rows are 16 values wide");
+    static constexpr int kHalo = (P4 || MODE == kRsFold2) ? (D + 1) / 2 : (MODE == kRsFold4 ? 1 : D);   // column halo in GEMM rows (16-byte units)
+    static constexpr int kColStep = (P4 || kFolded) ? 1 : D;         // distance between the horizontal taps / K groups of a row, 16-byte units
     static constexpr int kG = P4 ? 2 * kHalo + 1 : 3;                // K groups per row (CG = 1)
+    static constexpr int kShifts = kFolded ? 2 * kHalo + 1 : 3;      // horizontal taps (CG >= 2)
     static constexpr int kRing = CG == 1 ? 32 : (CG == 2 ? 14 : 16);
     static constexpr int NC = CG >= 4 ? 32 : 16;                     // accumulator columns per output row (padded)
     static constexpr int N3 = 3 * NC;
-    static constexpr int KG1 = CG == 1 ? kG + 1 : 3 * CG;
+    static constexpr int KG1 = CG == 1 ? kG + 1 : kShifts * CG;
     static constexpr int KG2 = CG == 1 ? 2 : CG;
     // accumulator slots: the 1x1 stage gets 8 (two per epilogue group, hiding its round trip) where the 3x3 rings still fit
     static constexpr int A2 = (CG == 4 || D == 3) ? 4 : 8;
@@ -98,22 +107,22 @@ __device__ __forceinline__ void tmem_store(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_store_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int CG, int NREAL, int D, bool P4>
-__global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResRsParams p) {
-    using S_ = RsPlan<CG, D, P4>;
+template <int CG, int NREAL, int D, int MODE>
+__global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResRsParams p) {
+    using S_ = RsPlan<CG, D, MODE>;
     constexpr int NC = S_::NC, N3 = S_::N3, SR = S_::SR, A2 = S_::A2;
     constexpr int kRing = S_::kRing, TW = S_::TW, halo = S_::kHalo;
     constexpr int slot_bytes = S_::kSlotBytes;
-    constexpr int kRsIssuers1 = rs_issuers1<CG>(), kRsThreads = rs_threads<CG>();
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S_::kBars);
     uint64_t* ring_full = bars;                 // [kRing]  TMA landed
-    uint64_t* ring_free = bars + kRing;         // [kRing]  5 arrivals: the commit of the row's 3x3 MMAs + the 4 warps reading it as the residual
-    uint64_t* acc1_full = bars + 2 * kRing;     // [12]     3 arrivals: one commit per contributing input row (stand-ins at the edges)
+    uint64_t* ring_free = bars + kRing;         // [kRing]  8 arrivals: the 4 warps that saw the row's 3x3 MMAs complete + the 4 warps reading it as the residual
+    uint64_t* acc1_full = bars + 2 * kRing;     // [12]     commit after the last contributing input row
     uint64_t* acc1_free = acc1_full + 12;       // [12]     4 arrivals (slot drained and re-initialised with the bias)
     uint64_t* mid_full = acc1_free + 12;        // [8]      4 arrivals
     uint64_t* acc2_full = mid_full + 8;         // [8]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + S_::kTmemSlot);
+    uint32_t* rows_ready = tmem_slot + 1;       // number of input rows the scout has cleared for the 3x3 issuer
     float* sBias = reinterpret_cast<float*>(smem + S_::kBias);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -141,16 +150,17 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
     if (tid == 32) {
         for (int i = 0; i < kRing; ++i) {
             umma::mbar_init(&ring_full[i], 1);
-            umma::mbar_init(&ring_free[i], 5);
+            umma::mbar_init(&ring_free[i], 8);
         }
         for (int i = 0; i < 12; ++i) {
-            umma::mbar_init(&acc1_full[i], 3);
+            umma::mbar_init(&acc1_full[i], 1);
             umma::mbar_init(&acc1_free[i], 4);
         }
         for (int i = 0; i < 8; ++i) {
             umma::mbar_init(&mid_full[i], 4);
             umma::mbar_init(&acc2_full[i], 1);
         }
+        *rows_ready = 0;
         umma::mbar_fence_init();
     }
     for (int i = tid; i < S_::KG1 * N3; i += kRsThreads) reinterpret_cast<uint4*>(sW1)[i] = __ldg(reinterpret_cast<const uint4*>(p.w1) + i);
@@ -188,38 +198,46 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
                 tma_load_5d(sRing + (size_t)slot * slot_bytes, &tmap_x, &ring_full[slot], 0, t0 - halo, h_start + ri, 0, b);
             }
         }
-    } else if (warp > kRsEpiWarps && warp <= kRsEpiWarps + kRsIssuers1) {
-        // =================================== 3x3 MMA issuers (input rows par, par + 2, ...; one thread each) ===================================
-        // Accumulations into one TMEM slot from different issuing threads are interlocked by the tensor pipe (checked with
-        // scripts/microbench/mma_shared_acc.cu: exact sums, no lost updates), and every MMA accumulates, so the issuers need no
-        // ordering among themselves; an output row is complete when the commits of its (up to) three contributing rows have arrived.
+    } else if (warp == kRsEpiWarps + 1) {
+        // =================================== scout ===================================
+        // Does the 3x3 issuer's waiting for it: row landed (TMA), accumulator slot of the row's newest target drained and re-initialised
+        // (the other two targets were acquired with earlier rows).  A barrier probe costs ~100 cycles even when it succeeds; the issuer
+        // only reads one counter.
         if (lane == 0) {
-            const int par = warp - (kRsEpiWarps + 1);
+            for (int ri = ri_first; ri <= ri_last; ++ri) {
+                const int idx = ri - ri_first;
+                umma::mbar_wait(&ring_full[idx % kRing], (uint32_t)((idx / kRing) & 1));
+                const int it_new = ri + D;
+                if (it_new < n_out) {
+                    const int u = (it_new / D) / SR;
+                    if (u > 0) umma::mbar_wait(&acc1_free[slot_of(it_new)], (uint32_t)((u - 1) & 1));
+                }
+                asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(umma::smem_u32(rows_ready)), "r"((uint32_t)idx + 1u) : "memory");
+            }
+        }
+    } else if (warp == kRsEpiWarps + 2) {
+        // =================================== 3x3 MMA issuer: one thread, input rows in order ===================================
+        // (a single in-order issuer keeps the accumulation order of every output row fixed - results are bit-reproducible - and needs
+        // one commit per row: it covers everything issued before, i.e. all three contributions of output row ri - D)
+        // (measured: running the loop warp-uniformly with one elected lane issuing is not faster - the cost is the tcgen05 hand-off)
+        if (lane == 0) {
+            constexpr bool issuer = true;
             constexpr uint32_t idesc1 = umma::make_idesc_bf16(128, NC), idesc2 = umma::make_idesc_bf16(128, 2 * NC), idesc3 = umma::make_idesc_bf16(128, N3);
             const uint32_t ring0 = umma::smem_u32(sRing), zero0 = umma::smem_u32(sZero), w1_0 = umma::smem_u32(sW1);
             constexpr uint32_t plane = (uint32_t)TW * 16u;
             constexpr uint32_t b_step = (2u * N3 * 16u) >> 4;             // two K groups per MMA
             const uint32_t b_base = desc_lo(w1_0, N3 * 16u);
-            TT_PROF(long long t_ring = 0, t_free = 0, t_issue = 0, t_mma = 0, tp = clock64();)
-            for (int ri = ri_first + par; ri <= ri_last; ri += kRsIssuers1) {
+            uint32_t ready = 0;
+            TT_PROF(long long t_wait = 0, t_mma = 0, t_commit = 0, tp = clock64();)
+            for (int ri = ri_first; ri <= ri_last; ++ri) {
                 const int idx = ri - ri_first;
-                umma::mbar_wait(&ring_full[idx % kRing], (uint32_t)((idx / kRing) & 1));
-                TT_PROF(t_ring += clock64() - tp; tp = clock64();)
+                while (ready <= (uint32_t)idx)
+                    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(ready) : "r"(umma::smem_u32(rows_ready)) : "memory");
+                umma::fence_after_sync();
+                TT_PROF(t_wait += clock64() - tp; tp = clock64();)
                 // target blocks j = 0, 1, 2 <-> output rows ri - D, ri, ri + D (vertical taps ky = 2, 1, 0)
                 const int j0 = ri >= D ? 0 : (ri >= 0 ? 1 : 2);
                 const int j1 = ri + D < n_out ? 2 : (ri < n_out ? 1 : 0);
-                // a slot must have been drained (and re-initialised with the bias) from its previous use before any MMA into it; the
-                // issuers are not ordered among themselves, so each checks all of its targets
-#pragma unroll
-                for (int j = 0; j <= 2; ++j) {
-                    const int it = ri + (j - 1) * D;
-                    if (j >= j0 && j <= j1) {
-                        const int u = (it / D) / SR;
-                        if (u > 0) umma::mbar_wait(&acc1_free[slot_of(it)], (uint32_t)((u - 1) & 1));
-                    }
-                }
-                umma::fence_after_sync();
-                TT_PROF(t_free += clock64() - tp; tp = clock64();)
                 const int res = (ri + D) % D;                            // residue class of the three targets
                 const int q1 = (ri + D) / D - 1;                         // ring sequence number of output row ri
                 const int pa = (q1 - 1 + j0) % SR;
@@ -237,16 +255,16 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
                         for (int g = 0; g < S_::kG; g += 2) {
                             const uint32_t a = row + (uint32_t)g * cs;
                             const uint32_t lbo = g + 1 < S_::kG ? cs : zero0 - a;
-                            umma::mma_bf16(acc, desc64(desc_lo(a, lbo)), desc64(b_lo), idesc, true);
+                            if (issuer) umma::mma_bf16(acc, desc64(desc_lo(a, lbo)), desc64(b_lo), idesc, true);
                             b_lo += b_step;
                         }
                     } else {
                         const uint32_t row_lo = ((row >> 4) & 0x3FFFu) | (((plane >> 4) & 0x3FFFu) << 16);
 #pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) {
+                        for (int kx = 0; kx < S_::kShifts; ++kx) {
 #pragma unroll
                             for (int q = 0; q < CG / 2; ++q) {
-                                umma::mma_bf16(acc, desc64(row_lo + (uint32_t)(kx * D) + (uint32_t)(2 * q) * (plane >> 4)), desc64(b_lo), idesc, true);
+                                if (issuer) umma::mma_bf16(acc, desc64(row_lo + (uint32_t)(kx * S_::kColStep) + (uint32_t)(2 * q) * (plane >> 4)), desc64(b_lo), idesc, true);
                                 b_lo += b_step;
                             }
                         }
@@ -255,27 +273,20 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
                 if (na > 0) issue(pa, j0, na);
                 if (nb > 0) issue(0, j0 + na, nb);
                 TT_PROF(t_mma += clock64() - tp; tp = clock64();)
-                umma::commit(&ring_free[idx % kRing]);
-                if (ri < 0 || ri >= n_out) mbar_arrive_n(&ring_free[idx % kRing], 4);     // no residual readers for halo rows
-#pragma unroll
-                for (int j = 0; j <= 2; ++j)
-                    if (j >= j0 && j <= j1) umma::commit(&acc1_full[slot_of(ri + (j - 1) * D)]);
-                if (ri >= 0 && ri < n_out) {
-                    // stand in for the contributing rows that do not exist (above / below the image or the strip's halo)
-                    const int missing = (ri - D < ri_first ? 1 : 0) + (ri + D > ri_last ? 1 : 0);
-                    if (missing) mbar_arrive_n(&acc1_full[slot_of(ri)], (uint32_t)missing);
-                }
-                TT_PROF(t_issue += clock64() - tp; tp = clock64();)
+                if (ri - D >= 0) umma::commit(&acc1_full[slot_of(ri - D)]);
+                if (ri == ri_last)
+                    for (int it = max(0, ri_last - D + 1); it < n_out; ++it) umma::commit(&acc1_full[slot_of(it)]);
+                TT_PROF(t_commit += clock64() - tp; tp = clock64();)
             }
-            TT_PROF(if (par == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-                        const int nr = (ri_last - ri_first) / kRsIssuers1 + 1;
-                        printf("rs issuer1[0]: rows %d  cycles/row: ring wait %lld, slot wait %lld, mma %lld, commits %lld\n", nr, t_ring / nr,
-                               t_free / nr, t_mma / nr, t_issue / nr);
+            TT_PROF(if (issuer && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+                        const int nr = ri_last - ri_first + 1;
+                        printf("rs issuer1: rows %d  cycles/row: wait %lld, mma %lld, commit %lld\n", nr, t_wait / nr, t_mma / nr, t_commit / nr);
                     })
         }
-    } else if (warp == kRsEpiWarps + kRsIssuers1 + 1) {
+    } else if (warp == kRsEpiWarps + 3) {
         // =================================== 1x1 MMA issuer ===================================
         if (lane == 0) {
+            constexpr bool issuer = true;
             constexpr uint32_t idesc = umma::make_idesc_bf16(128, NC);
             const uint32_t zero0 = umma::smem_u32(sZero), mid0 = umma::smem_u32(sMid), w2_0 = umma::smem_u32(sW2);
             const uint32_t b_lo0 = desc_lo(w2_0, NC * 16u);
@@ -289,17 +300,17 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
                 const uint32_t acc = tmem + (uint32_t)(acc2_col0 + a * NC);
                 const uint32_t mid = mid0 + (uint32_t)a * S_::kMidSlot;
                 if constexpr (CG == 1) {
-                    umma::mma_bf16(acc, desc64(desc_lo(mid, zero0 - mid)), desc64(b_lo0), idesc, true);
+                    if (issuer) umma::mma_bf16(acc, desc64(desc_lo(mid, zero0 - mid)), desc64(b_lo0), idesc, true);
                 } else {
                     const uint32_t a_lo = desc_lo(mid, 2048u);
 #pragma unroll
                     for (int q = 0; q < CG / 2; ++q)
-                        umma::mma_bf16(acc, desc64(a_lo + (uint32_t)(2 * q) * (2048u >> 4)), desc64(b_lo0 + (uint32_t)q * b_step), idesc, true);
+                        if (issuer) umma::mma_bf16(acc, desc64(a_lo + (uint32_t)(2 * q) * (2048u >> 4)), desc64(b_lo0 + (uint32_t)q * b_step), idesc, true);
                 }
                 umma::commit(&acc2_full[a]);
                 TT_PROF(t_iss += clock64() - tp; tp = clock64();)
             }
-            TT_PROF(if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+            TT_PROF(if (issuer && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
                         printf("rs issuer2: cycles/row: mid wait %lld, issue %lld\n", t_mid / n_out, t_iss / n_out);)
         }
     } else if (warp < kRsEpiWarps) {
@@ -308,8 +319,10 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
         const int j = quad * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         const bool t_ok = t0 + j < p.T;
-        uint4* const y_thread = reinterpret_cast<uint4*>(p.y) + ((size_t)b * CG * p.H + h_start) * p.T + t0 + j;
-        const size_t y_plane = (size_t)p.H * p.T;
+        // planar: y[b][cg][h][t]; folded: the two 16-byte halves of a GEMM row are adjacent in memory, y[b][h][t][cg]
+        uint4* const y_thread = S_::kFolded ? reinterpret_cast<uint4*>(p.y) + (((size_t)b * p.H + h_start) * p.T + t0 + j) * 2
+                                            : reinterpret_cast<uint4*>(p.y) + ((size_t)b * CG * p.H + h_start) * p.T + t0 + j;
+
         TT_PROF(long long t_w1 = 0, t_e1 = 0, t_w2 = 0, t_e2 = 0, tp = clock64();)
         // ---- 3x3 accumulator -> ELU -> bf16 intermediate (A operand of the 1x1 conv); slot <- bias ----
         auto epi1 = [&](int it) {
@@ -344,6 +357,14 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
             if (lane == 0) {
                 mbar_arrive(&acc1_free[sl]);
                 mbar_arrive(&mid_full[a]);
+                // acc1_full[it] was committed after the MMAs of row it + D, in row order: the 3x3 stage is done with every row up to
+                // it + D.  Release the ring slot of it + D - and of the rows that are no output row's "it + D" (the first D rows of the
+                // strip); halo rows have no residual readers, so their release stands in for both halves of the count.
+                if (it + D <= ri_last) mbar_arrive_n(&ring_free[(it + D - ri_first) % kRing], it + D >= n_out ? 2u : 1u);
+                if (it < D) {
+                    mbar_arrive(&ring_free[(it - ri_first) % kRing]);
+                    if (it - D >= ri_first) mbar_arrive_n(&ring_free[(it - D - ri_first) % kRing], 2u);
+                }
             }
             TT_PROF(t_e1 += clock64() - tp;)
         };
@@ -356,6 +377,7 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
             TT_PROF(t_w2 += clock64() - tp; tp = clock64();)
             const int ridx = it - ri_first;                            // ring index of row h
             const uint8_t* res = sRing + (size_t)(ridx % kRing) * slot_bytes + (size_t)(j + halo) * 16u;
+            uint4 folded_out[2];                                       // folded rows: both halves of the thread's 32 contiguous bytes
 #pragma unroll
             for (int c0 = 0; c0 < NREAL; c0 += NV) {
                 float v[NV];
@@ -381,9 +403,17 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
                     o.y = pack2(r[2], r[3]);
                     if constexpr (NE >= 8) { o.z = pack2(r[4], r[5]); o.w = pack2(r[6], r[7]); }
                     else { o.z = 0u; o.w = 0u; }
-                    if (t_ok) y_thread[(size_t)cg * y_plane + (size_t)it * p.T] = o;
+                    if constexpr (S_::kFolded) folded_out[cg] = o;
+                    else if (t_ok) y_thread[(size_t)cg * p.H * p.T + (size_t)it * p.T] = o;
                     if constexpr (NV < 8) break;
                 }
+            }
+            if constexpr (S_::kFolded) {
+                // one 32-byte store per thread: a warp writes 1 KB contiguous
+                if (t_ok)
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(y_thread + (size_t)it * (2 * p.T)), "r"(folded_out[0].x),
+                                 "r"(folded_out[0].y), "r"(folded_out[0].z), "r"(folded_out[0].w), "r"(folded_out[1].x), "r"(folded_out[1].y),
+                                 "r"(folded_out[1].z), "r"(folded_out[1].w) : "memory");
             }
             tmem_store_wait();
             umma::fence_before_sync();
@@ -418,29 +448,45 @@ __global__ void __launch_bounds__(rs_threads<CG>(), CG <= 2 ? 2 : 1) res_rs_kern
     if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
-template <int CG, int NREAL, int D, bool P4>
+// folded view of a tensor whose GEMM rows are 32 contiguous bytes: 5-D tensor (8, Tf, H, 2, B) whose "channel group" dimension is
+// the 16-byte half of the row, so that one TMA box (8, TW, 1, 2, 1) lands as two planes [half][row][8] - the planar operand layout
+static inline int make_folded_row_map(CUtensorMap* map, const void* x, int B, int H, int Tf, int TW) {
+    EncodeTiledFn fn = encode_fn();
+    TT_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[5] = {8, (cuuint64_t)Tf, (cuuint64_t)H, 2, (cuuint64_t)B};
+    const cuuint64_t strides[4] = {32, (cuuint64_t)Tf * 32, 16, (cuuint64_t)H * Tf * 32};
+    const cuuint32_t box[5] = {8, (cuuint32_t)TW, 1, 2, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(x), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    TT_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (folded rows) failed with code %d", (int)r);
+    return TT_OK;
+}
+
+template <int CG, int NREAL, int D, int MODE>
 static int launch_rs(const void* x, ResRsParams p, cudaStream_t stream) {
-    using S_ = RsPlan<CG, D, P4>;
+    using S_ = RsPlan<CG, D, MODE>;
     static bool configured = false;
     if (!configured) {
-        TT_CUDA_CHECK(cudaFuncSetAttribute(res_rs_kernel<CG, NREAL, D, P4>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::kTotal));
+        TT_CUDA_CHECK(cudaFuncSetAttribute(res_rs_kernel<CG, NREAL, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::kTotal));
         configured = true;
     }
     CUtensorMap map;
-    const int rc = make_row_map(&map, x, p.B, CG, p.H, p.T, S_::TW);
+    const int rc = S_::kFolded ? make_folded_row_map(&map, x, p.B, p.H, p.T, S_::TW) : make_row_map(&map, x, p.B, CG, p.H, p.T, S_::TW);
     if (rc) return rc;
     dim3 grid((p.T + kStripTileT - 1) / kStripTileT, (p.H + p.rows_per_strip - 1) / p.rows_per_strip, p.B);
-    res_rs_kernel<CG, NREAL, D, P4><<<grid, rs_threads<CG>(), S_::kTotal, stream>>>(map, p);
+    res_rs_kernel<CG, NREAL, D, MODE><<<grid, kRsThreads, S_::kTotal, stream>>>(map, p);
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;
 }
 
-template <int CG, int NREAL, bool P4>
+template <int CG, int NREAL, int MODE>
 static int launch_rs_d(const void* x, const ResRsParams& p, int dilation, cudaStream_t stream) {
-    if (dilation == 1) return launch_rs<CG, NREAL, 1, P4>(x, p, stream);
-    if (dilation == 2) return launch_rs<CG, NREAL, 2, P4>(x, p, stream);
-    return launch_rs<CG, NREAL, 3, P4>(x, p, stream);
+    if (dilation == 1) return launch_rs<CG, NREAL, 1, MODE>(x, p, stream);
+    if (dilation == 2) return launch_rs<CG, NREAL, 2, MODE>(x, p, stream);
+    return launch_rs<CG, NREAL, 3, MODE>(x, p, stream);
 }
 
 }  // namespace tt
@@ -448,18 +494,22 @@ static int launch_rs_d(const void* x, const ResRsParams& p, int dilation, cudaSt
 using namespace tt;
 
 extern "C" int tt_res_block_rs(const void* x, void* y, const void* w1, const void* w2, const float* bias, int B, int C, int c_real,
-                               int H, int T, int dilation, int packed4, void* stream) {
+                               int H, int T, int dilation, int layout, void* stream) {
     TT_REQUIRE(x && y && w1 && w2 && bias, "null argument");
     TT_REQUIRE(C == 8 || C == 16 || C == 32, "res block: padded channel count must be 8, 16 or 32 (got %d)", C);
-    TT_REQUIRE(!packed4 || (C == 8 && c_real <= 4 && T % 2 == 0), "packed layout: at most 4 channels and an even frame count");
+    TT_REQUIRE(layout == kRsPlanar || layout == kRsPairs8 || layout == kRsFold2 || layout == kRsFold4, "unknown layout mode %d", layout);
+    TT_REQUIRE(layout == kRsPlanar || C == 8, "packed / folded layouts are for C <= 8");
+    TT_REQUIRE((layout != kRsPairs8 && layout != kRsFold4) || c_real <= 4, "packed 4-channel layouts: at most 4 channels");
+    TT_REQUIRE((layout != kRsPairs8 && layout != kRsFold2) || T % 2 == 0, "frame pairs need an even frame count");
+    TT_REQUIRE(layout != kRsFold4 || T % 4 == 0, "frame quads need a frame count divisible by 4");
     TT_REQUIRE(dilation >= 1 && dilation <= 3, "dilation must be in [1,3]");
     TT_REQUIRE(c_real >= 1 && c_real <= C, "bad real channel count");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
     ResRsParams p;
     p.y = (__nv_bfloat16*)y; p.w1 = (const __nv_bfloat16*)w1; p.w2 = (const __nv_bfloat16*)w2; p.bias = bias;
-    // packed4: memory is (B, H, T, 4) bf16; a 16-byte unit is a PAIR of frames (e, 4 channels), so the kernel sees an 8-channel
-    // tensor with T/2 "frames" whose taps are the pair offsets -halo..halo (Toeplitz-expanded weights, packing.pack_res_rs_pairs)
-    if (packed4) T /= 2;
+    // the kernel's T counts GEMM rows: frames, frame pairs or frame quads
+    if (layout == kRsPairs8 || layout == kRsFold2) T /= 2;
+    if (layout == kRsFold4) T /= 4;
     p.B = B; p.H = H; p.T = T;
     // whole-height strips when the batch alone gives >= 6 waves of CTAs (2 CTAs/SM), shorter otherwise (each extra split re-reads
     // 2d halo rows but evens out the last wave)
@@ -474,8 +524,10 @@ extern "C" int tt_res_block_rs(const void* x, void* y, const void* w1, const voi
     if (env) rows = std::max(1, atoi(env));
     p.rows_per_strip = std::min(rows, H);
     cudaStream_t s = (cudaStream_t)stream;
-    if (packed4) return launch_rs_d<1, 8, true>(x, p, dilation, s);
-    if (C == 8) return c_real <= 4 ? launch_rs_d<1, 4, false>(x, p, dilation, s) : launch_rs_d<1, 8, false>(x, p, dilation, s);
-    if (C == 16) return launch_rs_d<2, 16, false>(x, p, dilation, s);
-    return launch_rs_d<4, 32, false>(x, p, dilation, s);
+    if (layout == kRsFold4) return launch_rs_d<2, 16, kRsFold4>(x, p, dilation, s);
+    if (layout == kRsFold2) return launch_rs_d<2, 16, kRsFold2>(x, p, dilation, s);
+    if (layout == kRsPairs8) return launch_rs_d<1, 8, kRsPairs8>(x, p, dilation, s);
+    if (C == 8) return c_real <= 4 ? launch_rs_d<1, 4, kRsPlanar>(x, p, dilation, s) : launch_rs_d<1, 8, kRsPlanar>(x, p, dilation, s);
+    if (C == 16) return launch_rs_d<2, 16, kRsPlanar>(x, p, dilation, s);
+    return launch_rs_d<4, 32, kRsPlanar>(x, p, dilation, s);
 }

@@ -11,7 +11,6 @@ Activations between layers live in the C8 planar bf16 layout (B, ceil(C/8), H, T
 """
 
 import ctypes
-import os
 
 import torch
 import torch.nn as nn
@@ -46,10 +45,6 @@ def _n16(c):
     return max(16, P.pad8(c))
 
 
-# residual-block kernel: 'rs' = row-stationary (csrc/res_rs.cu), 'strip' = one MMA per tap (csrc/res_strip.cu)
-_RES_KERNEL = os.environ.get('TT_RES_KERNEL', 'strip')
-
-
 class ResidualConv2dBlock(nn.Module):
     """modules.py:721-777: y = x + ELU(conv1x1(ELU(conv3x3_dilated(x)))), one fused kernel."""
 
@@ -63,27 +58,27 @@ class ResidualConv2dBlock(nn.Module):
         self.dilation = dilation
         self.channels = in_channels
         self.packed4 = False        # set by Encoder / Decoder for the first / last stage: (B, H, T, 4) activations
-        self._cache = _PackedCache()
+        self._caches = {}
 
-    def _packed(self):
+    def _packed(self, mode):
+        """mode: 'fold4' / 'fold2' / 'pairs' / 'planar' (csrc/res_rs.cu layouts 4 / 2 / 1 / 0)."""
         c1, c2 = self.conv1[0], self.conv2[0]
-        key = (c1.weight, c1.bias, c2.weight, c2.bias)
-        if _RES_KERNEL == 'rs':
-            if self.packed4:
-                return self._cache.get(key, lambda: P.pack_res_rs_pairs(c1.weight, c1.bias, c2.weight, c2.bias, self.dilation))
-            return self._cache.get(key, lambda: P.pack_res_rs(c1.weight, c1.bias, c2.weight, c2.bias))
-        if self.packed4:
-            return self._cache.get(key, lambda: P.pack_res_strip_pairs(c1.weight, c1.bias, c2.weight, c2.bias, self.dilation))
-        return self._cache.get(key, lambda: P.pack_res_strip(c1.weight, c1.bias, c2.weight, c2.bias))
+        args = (c1.weight, c1.bias, c2.weight, c2.bias)
+        build = {'fold4': lambda: P.pack_res_rs_fold(*args, self.dilation, 4),
+                 'fold2': lambda: P.pack_res_rs_fold(*args, self.dilation, 2),
+                 'pairs': lambda: P.pack_res_rs_pairs(*args, self.dilation),
+                 'planar': lambda: P.pack_res_rs(*args)}[mode]
+        return self._caches.setdefault(mode, _PackedCache()).get(args, build)
 
     def forward_c8(self, x, out=None):
-        if _RES_KERNEL == 'rs':
-            w1, w2, bias = self._packed()
-            return ops.res_block_rs(x, w1, w2, bias, self.channels, self.dilation, out=out)
-        w1, w2 = self._packed()
+        # rows of C <= 8 tensors are folded to 16 values (4 or 2 frames per GEMM row) when T allows
+        T = x.size(-2)
         if self.packed4:
-            return ops.res_block_strip_p4(x, w1, w2, self.dilation, out=out)
-        return ops.res_block_strip(x, w1, w2, self.channels, self.dilation, out=out)
+            mode = 'fold4' if T % 4 == 0 else 'pairs'
+        else:
+            mode = 'fold2' if (self.channels <= 8 and T % 2 == 0) else 'planar'
+        w1, w2, bias = self._packed(mode)
+        return ops.res_block_rs(x, w1, w2, bias, self.channels, self.dilation, out=out, fold=mode.startswith('fold'))
 
     def forward(self, x):
         """(B, C, H, W) -> (B, C, H, W) fp32 (API parity; the fast paths stay in the internal layouts)."""

@@ -95,48 +95,31 @@ def conv_out(x, w, b, c):
     return y
 
 
-def res_block_strip(x, w1, w2, c_real, dilation, out=None):
-    """Row-pipelined fused residual block (csrc/res_strip.cu); weights from packing.pack_res_strip."""
-    _check_c8(x)
-    B, CG, H, T, _ = x.shape
-    y = torch.empty_like(x) if out is None else out
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_res_block_strip(_p(x), _p(y), _p(w1), _p(w2), B, CG * 8, c_real, H, T, dilation, 0, _s(x)))
-    return y
-
-
 def _check_p4(x, name='x'):
     _lib.require_cuda(x, name)
     if x.dtype != torch.bfloat16 or x.dim() != 4 or x.size(-1) != 4 or x.size(-2) % 2 or not x.is_contiguous():
         raise ValueError(f'{name} must be a contiguous packed 4-channel bf16 tensor (B, H, T, 4) with even T, got {tuple(x.shape)} {x.dtype}')
 
 
-def res_block_strip_p4(x, w1, w2, dilation, out=None):
-    """The residual block on the packed 4-channel layout (B, H, T, 4); weights from packing.pack_res_strip_pairs."""
-    _check_p4(x)
-    B, H, T, _ = x.shape
-    y = torch.empty_like(x) if out is None else out
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_res_block_strip(_p(x), _p(y), _p(w1), _p(w2), B, 8, 4, H, T, dilation, 1, _s(x)))
-    return y
-
-
-def res_block_rs(x, w1, w2, bias, c_real, dilation, out=None):
-    """Row-stationary fused residual block (csrc/res_rs.cu); weights from packing.pack_res_rs (C8 planar x) or
-    packing.pack_res_rs_pairs (packed 4-channel x of shape (B, H, T, 4))."""
+def res_block_rs(x, w1, w2, bias, c_real, dilation, out=None, fold=False):
+    """Row-stationary fused residual block (csrc/res_rs.cu).  x C8 planar: weights from packing.pack_res_rs, or with fold=True
+    (C <= 8, even T) packing.pack_res_rs_fold(..., fold=2); x packed 4-channel (B, H, T, 4): packing.pack_res_rs_pairs, or with
+    fold=True (T % 4 == 0) packing.pack_res_rs_fold(..., fold=4)."""
     packed4 = x.dim() == 4
     if packed4:
         _check_p4(x)
         B, H, T, _ = x.shape
-        C, c_real = 8, 4
+        C, c_real = 8, min(c_real, 4)
+        layout = 4 if fold else 1
     else:
         _check_c8(x)
         B, CG, H, T, _ = x.shape
         C = CG * 8
+        layout = 2 if fold else 0
     _lib.require_cuda(bias, 'bias')
     y = torch.empty_like(x) if out is None else out
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_res_block_rs(_p(x), _p(y), _p(w1), _p(w2), _p(bias), B, C, c_real, H, T, dilation, int(packed4), _s(x)))
+        _lib.check(_lib.lib().tt_res_block_rs(_p(x), _p(y), _p(w1), _p(w2), _p(bias), B, C, c_real, H, T, dilation, layout, _s(x)))
     return y
 
 

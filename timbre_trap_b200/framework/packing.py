@@ -12,7 +12,7 @@ The C8 planar activation layout is (B, ceil(C/8), H, T, 8) bf16.
 
 import torch
 
-__all__ = ['pack_down_pairs', 'pack_res_strip_pairs', 'to_p4', 'from_p4', 'pack_down_strip', 'pack_up_strip', 'pack_res_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
+__all__ = ['pack_down_pairs', 'pack_res_rs', 'pack_res_rs_pairs', 'pack_res_rs_fold', 'to_p4', 'from_p4', 'pack_down_strip', 'pack_up_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
            'pad_vec']
 
 
@@ -142,36 +142,6 @@ def _bias_group(b, N):
     return g
 
 
-def pack_res_strip(w1, b1, w2, b2):
-    """
-    Weights of one ResidualConv2dBlock for csrc/res_strip.cu (biases ride along as an extra K group):
-      C <= 8 : W1 K groups per tap row ky: tap(ky,0), tap(ky,1), tap(ky,2), X_ky with X_0 = bias, X_1 = X_2 = 0  (12 groups);
-               W2 K groups: the 8 input channels, bias                                                          (2 groups)
-      C >= 16: W1 K groups: (tap, channel group) tap-major, then bias, then zeros  (9 C/8 + 2);  W2: channel groups, bias, zeros
-    Returns (w1_packed, w2_packed) in the B-operand layout [K/8][N][8] bf16, N = max(16, C padded to 8).
-    """
-    Co, Ci = w1.shape[:2]
-    Cp = pad8(Ci)
-    N = max(16, Cp)
-    CG = Cp // 8
-    taps = torch.zeros((N, 9, Cp), dtype=torch.float32, device=w1.device)
-    taps[:Co, :, :Ci] = w1.detach().float().permute(0, 2, 3, 1).reshape(Co, 9, Ci)
-    zero = torch.zeros((N, 8), dtype=torch.float32, device=w1.device)
-    if CG == 1:
-        groups = []
-        for ky in range(3):
-            groups += [taps[:, 3 * ky + kx, :] for kx in range(3)]
-            groups.append(_bias_group(b1, N) if ky == 0 else zero)
-    else:
-        groups = [taps[:, t, 8 * g: 8 * g + 8] for t in range(9) for g in range(CG)] + [_bias_group(b1, N), zero]
-    w1p = torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)          # (KG, N, 8)
-    k2 = torch.zeros((N, Cp), dtype=torch.float32, device=w2.device)
-    k2[:Co, :Ci] = w2.detach().float().reshape(Co, Ci)
-    groups2 = [k2[:, 8 * g: 8 * g + 8] for g in range(CG)] + [_bias_group(b2, N)] + ([] if CG == 1 else [zero])
-    w2p = torch.stack(groups2, dim=0).contiguous().to(torch.bfloat16)
-    return w1p, w2p
-
-
 def _rows_to_groups(rows_nc, bias_group, N):
     """rows_nc: list over input rows of (N, Cin_pad) weight slabs -> packed (KG, N, 8) for csrc/updown_strip.cu."""
     Cp = rows_nc[0].shape[1]
@@ -232,47 +202,6 @@ def from_p4(y, C):
     return y.permute(0, 3, 1, 2)[:, :C].float()
 
 
-def pack_res_strip_pairs(w1, b1, w2, b2, dilation):
-    """
-    Weights of one ResidualConv2dBlock with C <= 4 for the packed layout.  A GEMM row is a PAIR of frames (2j, 2j+1), a K group
-    is (frame parity e_in, 4 channels) of one input pair, N = (e_out, co).  The tap (ky, kx) with column shift s = (kx-1)*d feeds
-    output parity e_out from the input pair at offset o and parity e_in where 2*o + e_in - e_out = s, o in [-hp, hp],
-    hp = ceil((d+1)/2) ... i.e. the 3x3 kernel is Toeplitz-expanded over the pair.  K groups per tap row: o = -hp..hp, then one
-    filler group (the bias for ky = 0, zeros otherwise) so that groups pair up into K = 16 MMAs.  W2: block-diagonal in e, + bias.
-    """
-    Co, Ci = w1.shape[:2]
-    assert Co <= 4 and Ci <= 4
-    d = int(dilation)
-    hp = (d + 1) // 2
-    N = 16
-    dev = w1.device
-    w = w1.detach().float()
-    zero = torch.zeros((N, 8), dtype=torch.float32, device=dev)
-    bias1 = torch.zeros(N, dtype=torch.float32, device=dev)
-    bias2 = torch.zeros(N, dtype=torch.float32, device=dev)
-    for e in range(2):
-        bias1[4 * e: 4 * e + Co] = b1.detach().float()
-        bias2[4 * e: 4 * e + Co] = b2.detach().float()
-    groups = []
-    for ky in range(3):
-        for o in range(-hp, hp + 1):
-            g = torch.zeros((N, 8), dtype=torch.float32, device=dev)
-            for e_out in range(2):
-                for e_in in range(2):
-                    s_ = 2 * o + e_in - e_out
-                    for kx in range(3):
-                        if (kx - 1) * d == s_:
-                            g[4 * e_out: 4 * e_out + Co, 4 * e_in: 4 * e_in + Ci] = w[:, :, ky, kx]
-            groups.append(g)
-        groups.append(_bias_group(bias1, N) if ky == 0 else zero)
-    w1p = torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)
-    g2 = torch.zeros((N, 8), dtype=torch.float32, device=dev)
-    for e in range(2):
-        g2[4 * e: 4 * e + Co, 4 * e: 4 * e + Ci] = w2.detach().float().reshape(Co, Ci)
-    w2p = torch.stack([g2, _bias_group(bias2, N)], dim=0).contiguous().to(torch.bfloat16)
-    return w1p, w2p
-
-
 def pack_res_rs(w1, b1, w2, b2):
     """
     Weights of one ResidualConv2dBlock for csrc/res_rs.cu (row-stationary: an input row meets all three vertical taps at once).
@@ -310,7 +239,7 @@ def pack_res_rs(w1, b1, w2, b2):
 def pack_res_rs_pairs(w1, b1, w2, b2, dilation):
     """
     pack_res_rs for the packed 4-channel layout (C <= 4): a GEMM row is a PAIR of frames, a K group is (frame parity e_in, 4
-    channels) of the input pair at offset o in [-hp, hp], hp = ceil((d+1)/2) // see pack_res_strip_pairs; accumulator column
+    channels) of the input pair at offset o in [-hp, hp], hp = ceil((d+1)/2) (the 3x3 kernel is Toeplitz-expanded over the pair); accumulator column
     = (e_out, co).  K groups: o = -hp..hp, then a zero group.
     """
     Co, Ci = w1.shape[:2]
@@ -340,6 +269,47 @@ def pack_res_rs_pairs(w1, b1, w2, b2, dilation):
         bias[0, 4 * e: 4 * e + Co] = b1.detach().float()
         bias[1, 4 * e: 4 * e + Co] = b2.detach().float()
     w2p = torch.stack([g2, torch.zeros_like(g2)], dim=0).contiguous().to(torch.bfloat16)
+    return w1p, w2p, bias
+
+
+def pack_res_rs_fold(w1, b1, w2, b2, dilation, fold):
+    """
+    pack_res_rs for FOLDED rows (csrc/res_rs.cu layouts 2 and 4): a GEMM row is `fold` consecutive frames x Cw = 16 / fold
+    channels (fold = 2: C <= 8 in C8 planar; fold = 4: C <= 4 in the packed layout), i.e. always 16 values = two K groups
+    (halves).  The horizontal tap (kx - 1) * d becomes row offsets o in [-hp, hp] with fold * o + e_in - e_out = (kx - 1) * d
+    (Toeplitz expansion over the frames of a row); hp = ceil((d+1)/2) for fold = 2, 1 for fold = 4.
+    W1 -> (2 (2 hp + 1), 48, 8): K groups (o, half); rows n = j * 16 + e_out * Cw + co with j <-> vertical tap ky = 2 - j.
+    W2 -> (2, 16, 8) block-diagonal over the frames; bias -> (2, 16).
+    """
+    Co, Ci = w1.shape[:2]
+    Cw = 16 // fold
+    assert fold in (2, 4) and Co <= Cw and Ci <= Cw
+    d = int(dilation)
+    hp = (d + 1) // 2 if fold == 2 else 1
+    dev = w1.device
+    w = w1.detach().float()
+    per_half = fold // 2                                       # frames per 16-byte half
+    groups = []
+    for o in range(-hp, hp + 1):
+        g = torch.zeros((3, 16, 16), dtype=torch.float32, device=dev)          # [j][n][k over the whole row]
+        for e_out in range(fold):
+            for e_in in range(fold):
+                s_ = fold * o + e_in - e_out
+                for kx in range(3):
+                    if (kx - 1) * d == s_:
+                        for j in range(3):
+                            g[j, e_out * Cw: e_out * Cw + Co, e_in * Cw: e_in * Cw + Ci] = w[:, :, 2 - j, kx]
+        g = g.reshape(48, 16)
+        groups += [g[:, :8], g[:, 8:]]
+    w1p = torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)
+    g2 = torch.zeros((16, 16), dtype=torch.float32, device=dev)
+    bias = torch.zeros((2, 16), dtype=torch.float32, device=dev)
+    for e in range(fold):
+        g2[e * Cw: e * Cw + Co, e * Cw: e * Cw + Ci] = w2.detach().float().reshape(Co, Ci)
+        bias[0, e * Cw: e * Cw + Co] = b1.detach().float()
+        bias[1, e * Cw: e * Cw + Co] = b2.detach().float()
+    w2p = torch.stack([g2[:, :8], g2[:, 8:]], dim=0).contiguous().to(torch.bfloat16)
+    assert per_half * Cw == 8
     return w1p, w2p, bias
 
 
