@@ -7,8 +7,9 @@ The reference's loss step (reference: experiments/train.py:393-500) on the CUDA 
                                                     given), clip_grad_norm_(10), AdamW
 
 Forward kernels are the inference kernels (tcgen05 strips); every layer is a torch.autograd.Function whose backward calls
-the native gradient kernels of csrc/train_kernels.cu (generic direct-convolution dgrad / wgrad on fp32 NCHW - first version,
-CUDA cores).  PyTorch's autograd engine only walks the graph and accumulates `.grad`; there is no cuDNN / ATen compute on the
+the native gradient kernels of csrc/train_kernels.cu (direct-convolution dgrad / tiled wgrad on fp32 NCHW, CUDA cores); the
+residual blocks recompute their intermediate and take their data gradients on the tensor cores (tt_conv_same, the gradient
+operand split into bf16 hi + lo parts).  PyTorch's autograd engine only walks the graph and accumulates `.grad`; there is no cuDNN / ATen compute on the
 path except layout conversions (permute / dtype copies) between the inference layouts (C8 planar / packed4 bf16) and NCHW.
 Differences to the reference that do not change values: the CQT target is computed once (the reference computes it twice,
 train.py:404 and modules.py:366 -> :88); no `.item()` host syncs inside the step; activation gradients travel in bf16 between
