@@ -737,6 +737,178 @@ __global__ void __launch_bounds__(128) conv_out_kernel(const __nv_bfloat16* __re
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Row-walking variants for the packed 4-channel layout (the model's first / last layer: the largest tensors).
+// A thread owns 4 consecutive frames and walks down a strip of rows: every input row is loaded ONCE and its contributions to the
+// three output rows it touches are accumulated in registers (three rotating accumulator sets: when input row r has been added,
+// output row r-1 is complete and is stored).  Output-channel pairs are packed f32x2 accumulators (FFMA2: half the FMA instructions).
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 dup2(float v) { return make_float2(v, v); }
+
+// Decoder.convout, packed4 input (B, H, T, 4) bf16 -> fp32 interleaved (B, H, T, 2)
+__global__ void __launch_bounds__(128) conv_out_p4_kernel(const uint2* __restrict__ x, float2* __restrict__ y, const float* __restrict__ w /* [2][C][3][3] */,
+                                                          const float* __restrict__ bias, int C, int H, int T, int rows) {
+    __shared__ __align__(16) float2 sw[3][3][4];     // [ky][kx][c] -> (w for output 0, w for output 1)
+    __shared__ float2 sb;
+    for (int i = threadIdx.x; i < 36; i += 128) {
+        const int ky = i / 12, kx = (i / 4) % 3, c = i % 4;
+        sw[ky][kx][c] = c < C ? make_float2(w[(0 * C + c) * 9 + ky * 3 + kx], w[(1 * C + c) * 9 + ky * 3 + kx]) : make_float2(0.f, 0.f);
+    }
+    if (threadIdx.x == 0) sb = make_float2(bias[0], bias[1]);
+    __syncthreads();
+    const int t0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+    if (t0 >= T) return;
+    const int b = blockIdx.z, h0 = blockIdx.y * rows, h1 = min(H, h0 + rows);
+    const float2 bias2 = sb;
+    float2 P[4], Q[4], R[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) P[f] = Q[f] = R[f] = bias2;
+    const uint2* xb = x + (size_t)b * H * T + t0;
+    float2* yb = y + (size_t)b * H * T + t0;
+    // the six frames t0-1 .. t0+4 of input row hh (zeros outside the image); issued one row ahead of their use
+    auto load = [&](int hh, uint2 (&raw)[6]) {
+        if (hh >= 0 && hh < H) {
+            const uint2* xr = xb + (size_t)hh * T;
+            const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(xr)), m1 = __ldg(reinterpret_cast<const uint4*>(xr) + 1);
+            raw[0] = t0 > 0 ? __ldg(xr - 1) : make_uint2(0u, 0u);
+            raw[1] = make_uint2(m0.x, m0.y); raw[2] = make_uint2(m0.z, m0.w);
+            raw[3] = make_uint2(m1.x, m1.y); raw[4] = make_uint2(m1.z, m1.w);
+            raw[5] = t0 + 4 < T ? __ldg(xr + 4) : make_uint2(0u, 0u);
+        }
+    };
+    uint2 raw[6], nxt[6];
+    // input row hh: += into A (output row hh-1, ky = 2), Bq (row hh, ky = 1), Cq (row hh+1, ky = 0); then A is complete
+    auto step = [&](int hh, float2 (&A)[4], float2 (&Bq)[4], float2 (&Cq)[4]) {
+        if (hh < h1) load(hh + 1, nxt);
+        if (hh >= 0 && hh < H) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const float v[4] = {__uint_as_float(raw[i].x << 16), __uint_as_float(raw[i].x & 0xFFFF0000u),
+                                    __uint_as_float(raw[i].y << 16), __uint_as_float(raw[i].y & 0xFFFF0000u)};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float2 vv = dup2(v[c]);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int f = i - kx;
+                        if (f >= 0 && f < 4) {
+                            Cq[f] = __ffma2_rn(vv, sw[0][kx][c], Cq[f]);
+                            Bq[f] = __ffma2_rn(vv, sw[1][kx][c], Bq[f]);
+                            A[f] = __ffma2_rn(vv, sw[2][kx][c], A[f]);
+                        }
+                    }
+                }
+            }
+        }
+        const int ho = hh - 1;
+        if (ho >= h0 && ho < h1) {
+            float4* dst = reinterpret_cast<float4*>(yb + (size_t)ho * T);
+            dst[0] = make_float4(A[0].x, A[0].y, A[1].x, A[1].y);
+            dst[1] = make_float4(A[2].x, A[2].y, A[3].x, A[3].y);
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f) A[f] = bias2;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) raw[i] = nxt[i];
+    };
+    int hh = h0 - 1;
+    load(hh, raw);
+    while (true) {
+        step(hh, P, Q, R); if (++hh > h1) break;
+        step(hh, Q, R, P); if (++hh > h1) break;
+        step(hh, R, P, Q); if (++hh > h1) break;
+    }
+}
+
+// Encoder.convin, fp32 interleaved (B, H, T, 2) -> packed4 (B, H, T, 4) bf16, + ELU
+__global__ void __launch_bounds__(128) conv_in_p4_kernel(const float2* __restrict__ x, uint2* __restrict__ y, const float* __restrict__ w /* [C0][2][3][3] */,
+                                                         const float* __restrict__ bias, int C0, int H, int T, int rows) {
+    __shared__ __align__(16) float2 sw[3][3][2][2];  // [ky][kx][re/im][channel pair] -> (w for channel 2p, 2p+1)
+    __shared__ float2 sb[2];
+    for (int i = threadIdx.x; i < 36; i += 128) {
+        const int ky = i / 12, kx = (i / 4) % 3, comp = (i / 2) % 2, pr = i % 2;
+        const int c0 = 2 * pr, c1 = 2 * pr + 1;
+        sw[ky][kx][comp][pr] = make_float2(c0 < C0 ? w[(c0 * 2 + comp) * 9 + ky * 3 + kx] : 0.f, c1 < C0 ? w[(c1 * 2 + comp) * 9 + ky * 3 + kx] : 0.f);
+    }
+    if (threadIdx.x < 2) sb[threadIdx.x] = make_float2(2 * threadIdx.x < C0 ? bias[2 * threadIdx.x] : 0.f, 2 * threadIdx.x + 1 < C0 ? bias[2 * threadIdx.x + 1] : 0.f);
+    __syncthreads();
+    const int t0 = (blockIdx.x * 128 + threadIdx.x) * 4;
+    if (t0 >= T) return;
+    const int b = blockIdx.z, h0 = blockIdx.y * rows, h1 = min(H, h0 + rows);
+    const float2 b01 = sb[0], b23 = sb[1];
+    float2 P[4][2], Q[4][2], R[4][2];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) { P[f][0] = Q[f][0] = R[f][0] = b01; P[f][1] = Q[f][1] = R[f][1] = b23; }
+    const float2* xb = x + (size_t)b * H * T + t0;
+    uint2* yb = y + (size_t)b * H * T + t0;
+    auto load = [&](int hh, float2 (&v)[6]) {
+        if (hh >= 0 && hh < H) {
+            const float2* xr = xb + (size_t)hh * T;
+            const float4 m0 = __ldg(reinterpret_cast<const float4*>(xr)), m1 = __ldg(reinterpret_cast<const float4*>(xr) + 1);
+            v[0] = t0 > 0 ? __ldg(xr - 1) : make_float2(0.f, 0.f);
+            v[1] = make_float2(m0.x, m0.y); v[2] = make_float2(m0.z, m0.w);
+            v[3] = make_float2(m1.x, m1.y); v[4] = make_float2(m1.z, m1.w);
+            v[5] = t0 + 4 < T ? __ldg(xr + 4) : make_float2(0.f, 0.f);
+        }
+    };
+    float2 v[6], nxt[6];
+    auto step = [&](int hh, float2 (&A)[4][2], float2 (&Bq)[4][2], float2 (&Cq)[4][2]) {
+        if (hh < h1) load(hh + 1, nxt);
+        if (hh >= 0 && hh < H) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int comp = 0; comp < 2; ++comp) {
+                    const float2 vv = dup2(comp ? v[i].y : v[i].x);
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int f = i - kx;
+                        if (f >= 0 && f < 4) {
+#pragma unroll
+                            for (int pr = 0; pr < 2; ++pr) {
+                                Cq[f][pr] = __ffma2_rn(vv, sw[0][kx][comp][pr], Cq[f][pr]);
+                                Bq[f][pr] = __ffma2_rn(vv, sw[1][kx][comp][pr], Bq[f][pr]);
+                                A[f][pr] = __ffma2_rn(vv, sw[2][kx][comp][pr], A[f][pr]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const int ho = hh - 1;
+        if (ho >= h0 && ho < h1) {
+            float r[16];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                r[4 * f] = elu(A[f][0].x); r[4 * f + 1] = elu(A[f][0].y); r[4 * f + 2] = elu(A[f][1].x); r[4 * f + 3] = elu(A[f][1].y);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(yb + (size_t)ho * T);
+            dst[0] = pack8(r);
+            dst[1] = pack8(r + 8);
+        }
+#pragma unroll
+        for (int f = 0; f < 4; ++f) { A[f][0] = b01; A[f][1] = b23; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = nxt[i];
+    };
+    int hh = h0 - 1;
+    load(hh, v);
+    while (true) {
+        step(hh, P, Q, R); if (++hh > h1) break;
+        step(hh, Q, R, P); if (++hh > h1) break;
+        step(hh, R, P, Q); if (++hh > h1) break;
+    }
+}
+
+// rows per CTA of the row-walking kernels: long strips amortise the two halo rows, short ones keep small batches parallel
+static inline int walk_rows(int B, int H, int T) {
+    const long long ctas_per_row_strip = (long long)B * ((T / 4 + 127) / 128);
+    int rows = 36;
+    while (rows > 6 && ctas_per_row_strip * ((H + rows - 1) / rows) < 4 * 148) rows /= 2;
+    return rows;
+}
+
 }  // namespace tt
 
 extern "C" int tt_conv_lat(const void* x, void* lat, const void* w, const float* bias, int B, int C4, int H4, int NL, int T,
@@ -771,7 +943,11 @@ extern "C" int tt_conv_in(const float* coeffs, void* y, const float* w, const fl
     TT_REQUIRE(T % 4 == 0, "conv_in: the frame count must be a multiple of 4 (got %d)", T);
     dim3 grid((T / 4 + 127) / 128, H, B);
     TT_REQUIRE(!packed4 || C0 <= 4, "conv_in: the packed layout holds at most 4 channels");
-    if (C0 <= 4) conv_in_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T, packed4);
+    if (packed4) {
+        const int rows = walk_rows(B, H, T);
+        conv_in_p4_kernel<<<dim3((T / 4 + 127) / 128, (H + rows - 1) / rows, B), 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (uint2*)y, w, bias, C0,
+                                                                                                            H, T, rows);
+    } else if (C0 <= 4) conv_in_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T, packed4);
     else conv_in_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T, 0);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
@@ -786,7 +962,11 @@ extern "C" int tt_conv_out(const void* x, float* coeffs, const float* w, const f
     TT_REQUIRE(T % 4 == 0, "conv_out: the frame count must be a multiple of 4 (got %d)", T);
     dim3 grid((T / 4 + 127) / 128, H, B);
     TT_REQUIRE(!packed4 || C <= 4, "conv_out: the packed layout holds at most 4 channels");
-    if (C <= 4) conv_out_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T, packed4);
+    if (packed4) {
+        const int rows = walk_rows(B, H, T);
+        conv_out_p4_kernel<<<dim3((T / 4 + 127) / 128, (H + rows - 1) / rows, B), 128, 0, (cudaStream_t)stream>>>((const uint2*)x, (float2*)coeffs, w, bias, C, H,
+                                                                                                             T, rows);
+    } else if (C <= 4) conv_out_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T, packed4);
     else conv_out_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T, 0);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
