@@ -102,6 +102,24 @@ int tt_chunk_crossfade(const float* chunks, const float* window, int batch, int 
                        float* coeffs_out, float* act_out, void* stream);
 
 /*
+ * ---- evaluation post-processing, the step after `transcribe` --------------------------------
+ * activations (B, F, T) fp32 row-major.  Bit-exact against oracle/postproc_ref.py.
+ */
+/* filter_non_peaks (timbre_trap/utils/processing.py:66-98): out = activations where strictly greater than both frequency
+ * neighbours (zeros beyond the edges), else 0 */
+int tt_filter_non_peaks(const float* activations, float* out, int B, int F, int T, void* stream);
+/* PitchDataset.activations_to_multi_pitch's binary map (datasets/PitchDataset.py:309-349): optional filter_non_peaks, then
+ * threshold (processing.py:101-124, `>= threshold`), restricted to bins [bin_lo, bin_hi) (the mask of experiments/evaluate.py:48);
+ * out (B, F, T) uint8 in {0, 1} */
+int tt_peak_threshold(const float* activations, unsigned char* out, int B, int F, int T, float threshold, int peaks_only,
+                      int bin_lo, int bin_hi, void* stream);
+/* Frame-wise multi-pitch matching in the manner of mir_eval.multipitch (utils/experiments.py:354-396): per frame the maximum
+ * matching between estimated and reference bins whose distance is <= tolerance_bins; counts (B, 3) int64 = true positives,
+ * estimated, reference (precision = tp / est, recall = tp / ref).  counts is zeroed by the call. */
+int tt_multipitch_counts(const unsigned char* est, const unsigned char* ref, int B, int F, int T, int tolerance_bins,
+                         int64_t* counts, void* stream);
+
+/*
  * ---- conv autoencoder (modules.py:396-777), bf16 tensor-core implicit GEMMs --------------------------------
  * Activations: "C8 planar" bf16  [B][ceil(C/8)][H][T][8]  (channel counts below are the PADDED counts, multiples of 8).
  * Weights: pre-packed bf16 in the tcgen05 B-operand layout [K/8][N][8]; K order and zero padding are documented at

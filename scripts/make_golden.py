@@ -182,10 +182,35 @@ def main():
                         transcription_sub=sub(trn, 9, 31), transcription_norm=float(trn.norm()),
                         transcribe_sub=sub(act, 9, 31), transcribe_norm=float(act.norm()), transcribe_max=float(act.max()),
                         reconstruct_sub=wav[..., ::41].numpy(), reconstruct_norm=float(wav.norm()))
+    make_postproc()
     print('golden vectors written to', GOLDEN)
     for fn in sorted(os.listdir(GOLDEN)):
         print(f'  {fn:28s} {os.path.getsize(os.path.join(GOLDEN, fn)) / 1024:8.1f} KiB')
 
 
+def make_postproc():
+    """tests/golden/postproc.npz: the reference's own filter_non_peaks / threshold (timbre_trap/utils/processing.py:66-124, numpy +
+    scipy, imported unmodified) on a seeded activation map with plateaus, ties, edge peaks and exact-threshold values."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('ref_processing', '/root/reference/timbre_trap/utils/processing.py')
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    rng = np.random.default_rng(5)
+    act = rng.random((2, 48, 37)).astype(np.float32)
+    act = np.round(act * 16) / 16                       # many ties and plateaus
+    act[0, 0, :5] = 1.0                                 # peaks at the lower edge
+    act[0, -1, 5:9] = 1.0                               # ... and the upper edge
+    act[1, 10:13, 3] = 0.75                             # a plateau: no strict peak
+    act[1, 20, :] = 0.5                                 # exactly at the threshold
+    peaks = mod.filter_non_peaks(act)
+    binary = mod.threshold(act, 0.5)
+    peaks_binary = mod.threshold(mod.filter_non_peaks(act), 0.5)
+    np.savez_compressed(os.path.join(GOLDEN, 'postproc.npz'), activations=act, filter_non_peaks=peaks.astype(np.float32),
+                        threshold=binary.astype(np.uint8), peaks_threshold=peaks_binary.astype(np.uint8))
+
+
 if __name__ == '__main__':
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == 'postproc':
+        make_postproc()
+    else:
+        main()

@@ -107,3 +107,38 @@ def test_objectives(golden_dir):
     np.testing.assert_allclose(float(R.transcription_loss_ref(est, tgt, True)), float(g['transcription_weighted']), rtol=1e-6)
     cs, cc = R.consistency_loss_ref(a, b, d)
     np.testing.assert_allclose([float(cs), float(cc)], [float(g['consistency_spectral']), float(g['consistency_score'])], rtol=1e-6)
+
+
+def test_postprocessing_oracle_vs_reference_functions(golden_dir):
+    """oracle/postproc_ref.py against tests/golden/postproc.npz = outputs of the reference's own filter_non_peaks / threshold
+    (timbre_trap/utils/processing.py:66-124); the matching counts against a brute-force maximum bipartite matching."""
+    import itertools
+    from oracle import postproc_ref as R
+    g = np.load(os.path.join(golden_dir, 'postproc.npz'))
+    a = g['activations']
+    assert np.array_equal(R.filter_non_peaks(a).astype(np.float32), g['filter_non_peaks'])
+    assert np.array_equal(R.threshold(a, 0.5).astype(np.uint8), g['threshold'])
+    assert np.array_equal(R.binary_map(a, 0.5, peaks_only=True), g['peaks_threshold'])
+    assert np.array_equal(R.binary_map(a, 0.5), g['threshold'])
+    masked = R.binary_map(a, 0.5, bin_lo=3, bin_hi=40)
+    assert masked[:, :3].sum() == 0 and masked[:, 40:].sum() == 0 and np.array_equal(masked[:, 3:40], g['threshold'][:, 3:40])
+
+    def brute(e, r, tol):                       # maximum matching by exhaustive search (tiny frames only)
+        ei, ri = np.flatnonzero(e), np.flatnonzero(r)
+        best = 0
+        for k in range(min(len(ei), len(ri)), 0, -1):
+            for es in itertools.combinations(ei, k):
+                for rs in itertools.permutations(ri, k):
+                    if all(abs(int(x) - int(y)) <= tol for x, y in zip(es, rs)):
+                        return k
+        return best
+    rng = np.random.default_rng(11)
+    for tol in (0, 1, 2):
+        est = (rng.random((9, 40)) < 0.3).astype(np.uint8)
+        ref = (rng.random((9, 40)) < 0.3).astype(np.uint8)
+        tp, ne, nr = R.multipitch_counts(est, ref, tol)
+        assert ne == est.sum() and nr == ref.sum()
+        assert tp == sum(brute(est[:, t], ref[:, t], tol) for t in range(est.shape[1]))
+    same = (rng.random((30, 50)) < 0.1).astype(np.uint8)
+    assert R.prf(*R.multipitch_counts(same, same, 0))[:2] == (1.0, 1.0)
+    assert R.prf(*R.multipitch_counts(same, np.zeros_like(same), 2)) == (0.0, 0.0, 0.0)

@@ -57,6 +57,9 @@ SIGNATURES = {
     'tt_adamw_step': (c_int, [c_void_p] * 4 + [c_int64, c_void_p] + [ctypes.c_float] * 6 + [c_int, c_void_p]),
     'tt_umma_probe': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'tt_to_decibels': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
+    'tt_filter_non_peaks': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'tt_peak_threshold': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_int, c_int, c_int, c_void_p]),
+    'tt_multipitch_counts': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
 }
 
 
