@@ -1,6 +1,7 @@
 // Backward half of the loss step (reference: experiments/train.py:470-496 = autograd through timbre_trap/framework/modules.py
-// and objectives.py, clip_grad_norm_, AdamW).  First native version: generic direct-convolution gradient kernels on CUDA cores,
-// fp32 NCHW tensors (B, C, H, T), correct for every layer shape of the model; the tensor-core versions are the next step.
+// and objectives.py, clip_grad_norm_, AdamW): direct-convolution gradient kernels on CUDA cores over fp32 NCHW tensors (B, C, H, T),
+// correct for every layer shape of the model, register-tiled where the problem is large; tensor-core versions are the next step
+// (the residual blocks already take their data gradients on the tensor cores, framework/train.py).
 //
 // All three conv kernels are written for a REGULAR convolution
 //     y[b,co,ho,t] = bias[co] + sum_{ci,kh,kw} W[co,ci,kh,kw] * x[b,ci, ho*sh + kh*dh - ph, t + kw*dw - pw]
@@ -79,6 +80,104 @@ __global__ void __launch_bounds__(256) conv_bwd_data_f32_kernel(const float* __r
     }
 }
 
+// Register-tiled versions of the two kernels above: a thread owns kTileC channels x kTileP consecutive frames of one row, so that
+// every loaded input / weight feeds kTileC (resp. kTileP) FMAs (2 FMAs per load instead of 0.5).
+constexpr int kTileC = 4, kTileP = 4;
+
+__global__ void __launch_bounds__(256) conv_fwd_f32_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, float* __restrict__ y, ConvGeom g, int act) {
+    const int tq = (g.T + kTileP - 1) / kTileP, cq = (g.Cout + kTileC - 1) / kTileC;
+    const long long n = (long long)g.B * cq * g.Hout * tq;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t0 = (int)(i % tq) * kTileP;
+        long long r = i / tq;
+        const int ho = (int)(r % g.Hout); r /= g.Hout;
+        const int co0 = (int)(r % cq) * kTileC;
+        const int b = (int)(r / cq);
+        float acc[kTileC][kTileP];
+#pragma unroll
+        for (int o = 0; o < kTileC; ++o)
+#pragma unroll
+            for (int q = 0; q < kTileP; ++q) acc[o][q] = (bias && co0 + o < g.Cout) ? bias[co0 + o] : 0.f;
+        for (int ci = 0; ci < g.Cin; ++ci) {
+            const float* xp = x + ((size_t)b * g.Cin + ci) * g.Hin * g.T;
+            for (int kh = 0; kh < g.KH; ++kh) {
+                const int hi = ho * g.sh + kh * g.dh - g.ph;
+                if (hi < 0 || hi >= g.Hin) continue;
+                for (int kw = 0; kw < g.KW; ++kw) {
+                    const int ti = t0 + kw * g.dw - g.pw;
+                    float v[kTileP], wv[kTileC];
+#pragma unroll
+                    for (int q = 0; q < kTileP; ++q) v[q] = (ti + q >= 0 && ti + q < g.T) ? __ldg(xp + (size_t)hi * g.T + ti + q) : 0.f;
+#pragma unroll
+                    for (int o = 0; o < kTileC; ++o)
+                        wv[o] = co0 + o < g.Cout ? __ldg(w + (((size_t)(co0 + o) * g.Cin + ci) * g.KH + kh) * g.KW + kw) : 0.f;
+#pragma unroll
+                    for (int o = 0; o < kTileC; ++o)
+#pragma unroll
+                        for (int q = 0; q < kTileP; ++q) acc[o][q] = fmaf(wv[o], v[q], acc[o][q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < kTileC; ++o) {
+            if (co0 + o >= g.Cout) break;
+            float* yp = y + (((size_t)b * g.Cout + co0 + o) * g.Hout + ho) * g.T + t0;
+#pragma unroll
+            for (int q = 0; q < kTileP; ++q)
+                if (t0 + q < g.T) yp[q] = act ? elu_act(acc[o][q]) : acc[o][q];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) conv_bwd_data_f32_tiled_kernel(const float* __restrict__ dz, const float* __restrict__ w,
+                                                                      float* __restrict__ dx, ConvGeom g) {
+    const int tq = (g.T + kTileP - 1) / kTileP, cq = (g.Cin + kTileC - 1) / kTileC;
+    const long long n = (long long)g.B * cq * g.Hin * tq;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int t0 = (int)(i % tq) * kTileP;
+        long long r = i / tq;
+        const int hi = (int)(r % g.Hin); r /= g.Hin;
+        const int ci0 = (int)(r % cq) * kTileC;
+        const int b = (int)(r / cq);
+        float acc[kTileC][kTileP];
+#pragma unroll
+        for (int c = 0; c < kTileC; ++c)
+#pragma unroll
+            for (int q = 0; q < kTileP; ++q) acc[c][q] = 0.f;
+        for (int kh = 0; kh < g.KH; ++kh) {
+            const int num = hi + g.ph - kh * g.dh;
+            if (num < 0 || num % g.sh) continue;
+            const int ho = num / g.sh;
+            if (ho >= g.Hout) continue;
+            for (int kw = 0; kw < g.KW; ++kw) {
+                const int to = t0 + g.pw - kw * g.dw;
+                for (int co = 0; co < g.Cout; ++co) {
+                    const float* zp = dz + (((size_t)b * g.Cout + co) * g.Hout + ho) * g.T;
+                    float v[kTileP], wv[kTileC];
+#pragma unroll
+                    for (int q = 0; q < kTileP; ++q) v[q] = (to + q >= 0 && to + q < g.T) ? __ldg(zp + to + q) : 0.f;
+#pragma unroll
+                    for (int c = 0; c < kTileC; ++c)
+                        wv[c] = ci0 + c < g.Cin ? __ldg(w + (((size_t)co * g.Cin + ci0 + c) * g.KH + kh) * g.KW + kw) : 0.f;
+#pragma unroll
+                    for (int c = 0; c < kTileC; ++c)
+#pragma unroll
+                        for (int q = 0; q < kTileP; ++q) acc[c][q] = fmaf(wv[c], v[q], acc[c][q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kTileC; ++c) {
+            if (ci0 + c >= g.Cin) break;
+            float* xp = dx + (((size_t)b * g.Cin + ci0 + c) * g.Hin + hi) * g.T + t0;
+#pragma unroll
+            for (int q = 0; q < kTileP; ++q)
+                if (t0 + q < g.T) xp[q] = acc[c][q];
+        }
+    }
+}
+
 // dW[co,ci,kh,kw] += sum_{b,ho,t} dz[b,co,ho,t] * x[b,ci,hi,ti];  db[co] += sum dz.
 // grid: (pixel chunks, Cout * Cin); each CTA owns one (co, ci) pair and all taps (KH*KW <= 32), reduces its pixel chunk and
 // adds the partial sums atomically (fp32 atomics: the summation order across chunks is not fixed).
@@ -134,28 +233,38 @@ __global__ void __launch_bounds__(256) conv_bwd_weight_f32_kernel(const float* _
 }
 
 // Same reduction, specialised: the tap loops are compile-time (accumulators stay in registers without predicated updates) and one
-// CTA covers CIT input channels of one output channel (dz is loaded once per CIT * KH * KW products).
-template <int KH, int KW, int CIT>
+// CTA covers a COT x CIT tile of (output, input) channels: per pixel COT gradient values and CIT * KH * KW inputs are loaded for
+// COT * CIT * KH * KW products (3.3 FMAs per load for the 3x3 case; the one-output-channel version did 1 and was bound by its loads).
+template <int KH, int KW, int CIT, int COT>
 __global__ void __launch_bounds__(256) conv_bwd_weight_tiled_kernel(const float* __restrict__ x, const float* __restrict__ dz,
                                                                     float* __restrict__ dw, float* __restrict__ db, ConvGeom g) {
     constexpr int TAPS = KH * KW;
-    __shared__ float red[8][CIT * TAPS + 1];
+    constexpr int NACC = COT * CIT * TAPS;
+    __shared__ float red[8][NACC + COT];
     const int n_cib = (g.Cin + CIT - 1) / CIT;
-    const int co = blockIdx.y / n_cib, ci0 = (blockIdx.y % n_cib) * CIT;
-    float acc[CIT][TAPS];
-    float accb = 0.f;
+    const int co0 = (blockIdx.y / n_cib) * COT, ci0 = (blockIdx.y % n_cib) * CIT;
+    float acc[COT][CIT][TAPS];
+    float accb[COT];
 #pragma unroll
-    for (int c = 0; c < CIT; ++c)
+    for (int o = 0; o < COT; ++o) {
+        accb[o] = 0.f;
 #pragma unroll
-        for (int k = 0; k < TAPS; ++k) acc[c][k] = 0.f;
+        for (int c = 0; c < CIT; ++c)
+#pragma unroll
+            for (int k = 0; k < TAPS; ++k) acc[o][c][k] = 0.f;
+    }
     const long long n = (long long)g.B * g.Hout * g.T;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i % g.T);
         long long r = i / g.T;
         const int ho = (int)(r % g.Hout);
         const int b = (int)(r / g.Hout);
-        const float z = __ldg(dz + (((size_t)b * g.Cout + co) * g.Hout + ho) * g.T + t);
-        accb += z;
+        float z[COT];
+#pragma unroll
+        for (int o = 0; o < COT; ++o) {
+            z[o] = co0 + o < g.Cout ? __ldg(dz + (((size_t)b * g.Cout + co0 + o) * g.Hout + ho) * g.T + t) : 0.f;
+            accb[o] += z[o];
+        }
 #pragma unroll
         for (int c = 0; c < CIT; ++c) {
             if (ci0 + c >= g.Cin) break;
@@ -168,33 +277,38 @@ __global__ void __launch_bounds__(256) conv_bwd_weight_tiled_kernel(const float*
                 for (int kw = 0; kw < KW; ++kw) {
                     const int ti = t + kw * g.dw - g.pw;
                     const float v = (h_ok && ti >= 0 && ti < g.T) ? __ldg(xp + (size_t)hi * g.T + ti) : 0.f;
-                    acc[c][kh * KW + kw] = fmaf(z, v, acc[c][kh * KW + kw]);
+#pragma unroll
+                    for (int o = 0; o < COT; ++o) acc[o][c][kh * KW + kw] = fmaf(z[o], v, acc[o][c][kh * KW + kw]);
                 }
             }
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int c = 0; c < CIT; ++c)
+    for (int o = 0; o < COT; ++o) {
 #pragma unroll
-        for (int k = 0; k < TAPS; ++k) {
-            float v = acc[c][k];
+        for (int c = 0; c < CIT; ++c)
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-            if (lane == 0) red[warp][c * TAPS + k] = v;
-        }
+            for (int k = 0; k < TAPS; ++k) {
+                float v = acc[o][c][k];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) accb += __shfl_xor_sync(0xffffffffu, accb, o);
-    if (lane == 0) red[warp][CIT * TAPS] = accb;
+                for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                if (lane == 0) red[warp][(o * CIT + c) * TAPS + k] = v;
+            }
+        float vb = accb[o];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) vb += __shfl_xor_sync(0xffffffffu, vb, s);
+        if (lane == 0) red[warp][NACC + o] = vb;
+    }
     __syncthreads();
-    for (int k = threadIdx.x; k <= CIT * TAPS; k += 256) {
+    for (int k = threadIdx.x; k < NACC + COT; k += 256) {
         float v = 0.f;
         for (int wv = 0; wv < 8; ++wv) v += red[wv][k];
-        if (k < CIT * TAPS) {
-            const int c = k / TAPS, tap = k % TAPS;
-            if (ci0 + c < g.Cin) atomicAdd(dw + ((size_t)co * g.Cin + ci0 + c) * TAPS + tap, v);
-        } else if (db && ci0 == 0) {
-            atomicAdd(db + co, v);
+        if (k < NACC) {
+            const int o = k / (CIT * TAPS), c = (k / TAPS) % CIT, tap = k % TAPS;
+            if (co0 + o < g.Cout && ci0 + c < g.Cin) atomicAdd(dw + ((size_t)(co0 + o) * g.Cin + ci0 + c) * TAPS + tap, v);
+        } else if (db && ci0 == 0 && co0 + (k - NACC) < g.Cout) {
+            atomicAdd(db + co0 + (k - NACC), v);
         }
     }
 }
@@ -329,7 +443,10 @@ extern "C" int tt_conv_fwd_f32(const float* x, const float* w, const float* bias
     if (int rc = fill_geom(&g, B, Cin, Hin, T, Cout, KH, KW, sh, dh, dw, ph, pw)) return rc;
     const long long n = (long long)B * Cout * g.Hout * T;
     if (n == 0) return TT_OK;
-    conv_fwd_f32_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, g, act_elu);
+    const long long n_tiles = (long long)B * ((Cout + kTileC - 1) / kTileC) * g.Hout * ((T + kTileP - 1) / kTileP);
+    // the tiled kernel wants enough threads to fill the GPU; tiny problems keep one thread per output
+    if (n_tiles >= 148 * 512) conv_fwd_f32_tiled_kernel<<<grid_for(n_tiles), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, g, act_elu);
+    else conv_fwd_f32_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, g, act_elu);
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;
@@ -345,7 +462,9 @@ extern "C" int tt_conv_bwd_data_f32(const float* dz, const float* w, float* dx, 
     if (hout_override > 0) g.Hout = hout_override;
     const long long n = (long long)B * Cin * Hin * T;
     if (n == 0) return TT_OK;
-    conv_bwd_data_f32_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dz, w, dx, g);
+    const long long n_tiles = (long long)B * ((Cin + kTileC - 1) / kTileC) * Hin * ((T + kTileP - 1) / kTileP);
+    if (n_tiles >= 148 * 512) conv_bwd_data_f32_tiled_kernel<<<grid_for(n_tiles), 256, 0, (cudaStream_t)stream>>>(dz, w, dx, g);
+    else conv_bwd_data_f32_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(dz, w, dx, g);
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;
@@ -362,12 +481,13 @@ extern "C" int tt_conv_bwd_weight_f32(const float* x, const float* dz, float* dw
     if (n == 0) return TT_OK;
     const unsigned gx = (unsigned)std::max<long long>(1, std::min<long long>((n + 256 * 16 - 1) / (256 * 16), 256));
     cudaStream_t s = (cudaStream_t)stream;
-#define TT_WGRAD(KH_, KW_, CIT_)                                                                               \
-    conv_bwd_weight_tiled_kernel<KH_, KW_, CIT_><<<dim3(gx, (unsigned)(Cout * ((Cin + CIT_ - 1) / CIT_))), 256, 0, s>>>(x, dz, dw, db, g)
-    if (KH == 3 && KW == 3) TT_WGRAD(3, 3, 4);
-    else if (KH == 1 && KW == 1) TT_WGRAD(1, 1, 8);
-    else if (KH == 4 && KW == 1) TT_WGRAD(4, 1, 4);
-    else if (KH == 31 && KW == 1) TT_WGRAD(31, 1, 1);
+#define TT_WGRAD(KH_, KW_, CIT_, COT_)                                                                                          \
+    conv_bwd_weight_tiled_kernel<KH_, KW_, CIT_, COT_>                                                                          \
+        <<<dim3(gx, (unsigned)(((Cout + COT_ - 1) / COT_) * ((Cin + CIT_ - 1) / CIT_))), 256, 0, s>>>(x, dz, dw, db, g)
+    if (KH == 3 && KW == 3) TT_WGRAD(3, 3, 2, 4);
+    else if (KH == 1 && KW == 1) TT_WGRAD(1, 1, 8, 4);
+    else if (KH == 4 && KW == 1) TT_WGRAD(4, 1, 4, 4);
+    else if (KH == 31 && KW == 1) TT_WGRAD(31, 1, 1, 2);
     else conv_bwd_weight_f32_kernel<<<dim3(gx, (unsigned)(Cout * Cin)), 256, 0, s>>>(x, dz, dw, db, g);
 #undef TT_WGRAD
     TT_CUDA_CHECK(cudaGetLastError());
