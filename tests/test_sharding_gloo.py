@@ -40,3 +40,38 @@ def test_sharded_peak_normalise_equals_global(tmp_path):
     errs = [np.load(os.path.join(tmp_path, f'err{r}.npy')) for r in range(2)]
     assert max(e[0] for e in errs) < 1e-6
     assert abs(max(e[1] for e in errs) - 1.0) < 1e-6               # exactly one shard holds the global peak
+
+
+def _grad_worker(rank, world, port, out_dir):
+    """Loss step sharding: each rank back-propagates the reference's losses (oracle, CPU fp32) on ITS half of the batch, then
+    framework.train.allreduce_mean_gradients averages the flat bucket - the result must be the gradient of the whole batch."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from timbre_trap_b200.framework.train import allreduce_mean_gradients
+    torch.manual_seed(0)
+    # a small stand-in with the same structure of the problem: per-item losses averaged over the batch
+    params = [torch.nn.Parameter(torch.randn(5, 3)), torch.nn.Parameter(torch.randn(7))]
+    data = torch.randn(4, 3)
+
+    def loss_of(batch):
+        h = torch.tanh(batch @ params[0].t())                        # (b, 5)
+        return ((h.sum(-1, keepdim=True) * params[1]) ** 2).sum(-1).mean()
+    for p in params:
+        p.grad = None
+    loss_of(data[rank * 2:(rank + 1) * 2]).backward()
+    allreduce_mean_gradients(params, dist.group.WORLD)
+    got = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    loss_of(data).backward()
+    err = max(float((g - p.grad).abs().max()) for g, p in zip(got, params))
+    np.save(os.path.join(out_dir, f'gerr{rank}.npy'), np.array([err]))
+    dist.destroy_process_group()
+
+
+def test_gradient_bucket_allreduce_equals_global_batch(tmp_path):
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    errs = [float(np.load(os.path.join(tmp_path, f'gerr{r}.npy'))[0]) for r in range(2)]
+    assert max(errs) < 1e-5

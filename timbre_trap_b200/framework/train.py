@@ -27,7 +27,7 @@ from .cqt import CQT
 from .modules import _PackedCache
 from .objectives import compute_consistency_loss, compute_reconstruction_loss, compute_transcription_loss
 
-__all__ = ['compute_step_losses', 'TrainStep']
+__all__ = ['compute_step_losses', 'TrainStep', 'allreduce_mean_gradients']
 
 
 def _p(t):
@@ -364,6 +364,20 @@ def _decoder(dec, lat, reconstruct):
     return _ConvFn.apply(x, co.weight, co.bias, lambda t: ops.conv_out(t, w_out, b_out, ch[4]), _geom(3, 3, ph=1, pw=1), ch[4], 2, False)
 
 
+def allreduce_mean_gradients(params, group):
+    """Replicas with equal per-rank batches: the mean over ranks of the per-rank gradients is the gradient of the reference's
+    global `.mean()` losses (objectives.py:31,72).  One flat bucket (base model: 614,490 fp32 = 2.46 MB), one all-reduce (NCCL on
+    the GPU path; any backend works - tests/test_sharding_gloo.py runs it over gloo), copied back into the `.grad` tensors."""
+    import torch.distributed as dist
+    flat = torch.cat([p.grad.reshape(-1) for p in params])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for p in params:
+        p.grad.copy_(flat[off:off + p.numel()].view_as(p))
+        off += p.numel()
+
+
 class TrainStep:
     """
     One optimisation step of experiments/train.py:393-500 for the base TimbreTrap (no skip connections):
@@ -415,14 +429,7 @@ class TrainStep:
             p.grad = None
         total.backward()
         if self.group is not None:
-            import torch.distributed as dist
-            flat = torch.cat([p.grad.reshape(-1) for p in self.params])          # one 2.46 MB bucket (614,490 fp32)
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-            flat /= dist.get_world_size(self.group)
-            off = 0
-            for p in self.params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                off += p.numel()
+            allreduce_mean_gradients(self.params, self.group)
 
     def optimizer_step(self):
         self.t += 1
