@@ -83,6 +83,10 @@ __global__ void __launch_bounds__(256) conv_bwd_data_f32_kernel(const float* __r
 // Register-tiled versions of the two kernels above: a thread owns kTileC channels x kTileP consecutive frames of one row, so that
 // every loaded input / weight feeds kTileC (resp. kTileP) FMAs (2 FMAs per load instead of 0.5).
 constexpr int kTileC = 4, kTileP = 4;
+#ifndef TT_WG33_CIT
+#define TT_WG33_CIT 1   // (input, output) channel tile of the 3x3 weight-gradient kernel (measured best of (2,4) (4,4) (2,8) (4,2) (1,8))
+#define TT_WG33_COT 8
+#endif
 
 __global__ void __launch_bounds__(256) conv_fwd_f32_tiled_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                                  const float* __restrict__ bias, float* __restrict__ y, ConvGeom g, int act) {
@@ -484,7 +488,7 @@ extern "C" int tt_conv_bwd_weight_f32(const float* x, const float* dz, float* dw
 #define TT_WGRAD(KH_, KW_, CIT_, COT_)                                                                                          \
     conv_bwd_weight_tiled_kernel<KH_, KW_, CIT_, COT_>                                                                          \
         <<<dim3(gx, (unsigned)(((Cout + COT_ - 1) / COT_) * ((Cin + CIT_ - 1) / CIT_))), 256, 0, s>>>(x, dz, dw, db, g)
-    if (KH == 3 && KW == 3) TT_WGRAD(3, 3, 2, 4);
+    if (KH == 3 && KW == 3) TT_WGRAD(3, 3, TT_WG33_CIT, TT_WG33_COT);
     else if (KH == 1 && KW == 1) TT_WGRAD(1, 1, 8, 4);
     else if (KH == 4 && KW == 1) TT_WGRAD(4, 1, 4, 4);
     else if (KH == 31 && KW == 1) TT_WGRAD(31, 1, 1, 2);
