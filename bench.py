@@ -107,6 +107,10 @@ def cpu_state():
     return R.init_state_dict(F, LATENT, COMPLEXITY, seed=0), R.CQTRef(N_OCT, BPO, SR, SECS, dtype=np.complex64)
 
 
+WORKLOAD = ('BASELINE.json configs[2]: transcribe+reconstruct, 256 x 3 s blocks per GPU, base model '
+            '(9 oct x 60 bpo, 22.05 kHz, latent 128, complexity 2), random init')
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -120,7 +124,8 @@ def run_reference(args, rank):
     cores = torch.get_num_threads()
     line = dict(metric=METRIC, value=value, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=per_step * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload='transcribe+reconstruct, base model, CPU', sample=f'{n_blocks} x 3 s block per step (sequential chunk loop)'),
+                config=dict(workload=WORKLOAD, sample=f'bounded sample of that workload: {n_blocks} x 3 s block per step on the host CPU '
+                                                      '(the reference\'s sequential chunk loop)'),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='port',
                                   sample=f'{args.steps} steps x {n_blocks} block(s) of 3 s; oracle/model_ref.py + oracle/nsgt_ref.py (the reference is '
                                          'pure Python with an un-vendored CQT dependency; /root/reference is absent on the GPU box)'),
@@ -284,8 +289,7 @@ def run_ours(args, rank, world, local_rank):
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
                     higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16 convs (fp32 accumulate), fp32 CQT',
                     data='synthetic', impl='ours',
-                    config=dict(workload='BASELINE.json configs[2]: transcribe+reconstruct, 256 x 3 s blocks per GPU, base model '
-                                         '(9 oct x 60 bpo, 22.05 kHz, latent 128, complexity 2), random init',
+                    config=dict(workload=WORKLOAD,
                                 blocks_per_gpu=n_blocks, chunks_per_gpu=3 * n_blocks, parallelism=f'dp{world} (block sharding)',
                                 l2='working set per step ~40 GB >> 126 MB L2; no explicit flush'),
                     e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_tensor=roofline_tensor, cqt=cq, cpu_baseline=cpu, clocks=clocks)
