@@ -1,22 +1,29 @@
 // Fused ResidualConv2dBlock (reference: timbre_trap/framework/modules.py:721-777), row-stationary form:
 //     y = x + ELU(W2 * ELU(W1 (*)_d x + b1) + b2)      (3x3 dilated 'same' conv, 1x1 conv, residual)
 //
-// The implicit GEMM of res_strip.cu (N = C per MMA, one MMA per tap) re-reads every activation row nine times from shared
-// memory, and the shared-memory operand pipe (128 B/clk/SM) is what bounds it.  Here every INPUT row is multiplied once per
-// horizontal tap against the weights of all three vertical taps at once:
+// An implicit GEMM with one MMA per tap (N = C; the first design of this kernel) re-reads every activation row nine times from
+// shared memory, and below N ~ 100 an MMA costs the tensor pipe its A-operand fetch, not its math (profiles/r01_tcgen05_microbench.md).
+// Here every INPUT row is multiplied once per horizontal tap against the weights of all three vertical taps at once:
 //
-//     D[128 frames][ (out row r-d | out row r | out row r+d) x C ]  +=  A[row r, shifted by kx*d][K = C] * B[kx][3C][K]
+//     D[128 rows][ (out row r-d | out row r | out row r+d) x C ]  +=  A[row r, shifted by kx*d][K = C] * B[kx][3C][K]
 //
 // i.e. N = 3C and a third of the operand reads.  The accumulators of the output rows live in TMEM as d rings of S slots
 // (rows of equal residue mod d are neighbours in their ring, so the three targets of one input row are adjacent columns; at the
 // ring's wrap-around the MMA is split in two).  Every MMA accumulates: a slot starts out holding the bias, written with
 // tcgen05.st by the epilogue that drained it (so the biases are fp32 and cost no operand traffic).
 //
-//   warp 16 (producer)  one TMA box per input row (all channel groups, 128 + 2 halo frames, zero-filled outside the image)
-//   warp 17 (3x3)       per input row: waits for the row and for the slot of the newest output row, issues the N = 3C MMAs
-//                       in row order (single issuer: accumulation order and the commits are then trivially ordered)
-//   warp 18 (1x1)       the 1x1 conv of output row h from the bf16 intermediate in shared memory
-//   warps 0-15          four epilogue groups (row -> group row % 4; warp quadrant = TMEM lane quadrant), as in res_strip.cu
+//   warp 16 (producer)  one TMA box per input row (all channel groups, 128 + 2 halo GEMM rows, zero-filled outside the image) into
+//                       a shared-memory ring; every input row is fetched once per strip
+//   warp 17 (scout)     does the 3x3 issuer's barrier waiting (row landed, slot of the newest output row drained) and publishes one
+//                       counter of cleared rows
+//   warp 18 (3x3)       one thread: per input row the N = 3C MMAs, in row order (fixed accumulation order = bit-reproducible
+//                       results; one commit per row covers all three contributions of output row r - d)
+//   warp 19 (1x1)       one thread: the 1x1 conv of each output row from the bf16 intermediate in shared memory
+//   warps 0-15          four epilogue groups (row -> group row % 4; warp quadrant = TMEM lane quadrant): accumulator -> ELU -> bf16
+//                       intermediate;  accumulator -> ELU -> + x (from the ring) -> bf16 -> coalesced stores; both re-initialise
+//                       their slot with the bias and release ring slots / accumulators with one arrival per warp
+// All hand-offs are mbarriers; nothing in the row loop is a CTA-wide barrier.  For C <= 8 the rows are FOLDED (see the layout modes
+// below) so that a GEMM row is always 16 values wide.
 #include <stdlib.h>
 #include <string.h>
 

@@ -1,5 +1,5 @@
 // EncoderBlock.sconv and DecoderBlock.tconv (reference: timbre_trap/framework/modules.py:626-629, 685-688) as row-pipelined
-// tcgen05 kernels, same machinery as res_strip.cu (TMA row ring -> MMA issuer warps -> TMEM -> epilogue warp groups), one
+// tcgen05 kernels, same machinery as the first design of the residual-block kernel (TMA row ring -> MMA issuer warps -> TMEM -> epilogue warp groups), one
 // GEMM stage, bias folded into the GEMM, ELU in the epilogue:
 //
 //   DOWN  Conv2d(Cin, Cout, (4,1), stride (2,1)):       out[q] = ELU(b + sum_kh W[kh] x[2q + kh])          K = (kh, ci)
