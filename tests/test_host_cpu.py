@@ -164,3 +164,91 @@ def test_weight_packing_shapes():
     assert torch.allclose(tables[1] - tables[0], w[128, :, :, 0].t(), atol=1e-6)
     x = torch.randn(2, 5, 7, 16)
     assert torch.equal(P.from_c8(P.to_c8(x), 5), x.to(torch.bfloat16).float())
+
+
+def _unpack_b(packed):
+    """(KG, N, 8) bf16 B operand -> (N, K) fp32."""
+    return packed.float().permute(1, 0, 2).reshape(packed.shape[1], -1)
+
+
+def _ones_k(n_rows):
+    """The kernels' constant "ones" K group: (1, 1, 0, ..., 0) per GEMM row - meets the bias group (bf16 hi + lo)."""
+    o = torch.zeros(n_rows, 8)
+    o[:, :2] = 1.0
+    return o
+
+
+def test_weight_packing_strided_transposed_latent():
+    """pack_down / pack_up (+ _strip, _pairs variants with their bias groups), pack_lat, pack_deconv_in against torch's convs,
+    through the GEMMs the kernels issue (K order, polyphase rows, bias-as-K-group, indicator-as-bias-table)."""
+    import torch.nn.functional as F
+    from timbre_trap_b200.framework import packing as P
+    torch.manual_seed(1)
+    bf = lambda t: t.to(torch.bfloat16).float()
+    T = 6
+    for Ci, Co, H in ((4, 8, 11), (8, 16, 10), (16, 32, 9), (3, 5, 8)):
+        x = bf(torch.randn(1, Ci, H, T))
+        Cip, Cop = P.pad8(Ci), P.pad8(Co)
+        xp = torch.zeros(H, T, Cip)
+        xp[..., :Ci] = x[0].permute(1, 2, 0)
+        # ---- strided conv (4,1)/(2,1): K = (kh, ci) over input rows 2q .. 2q+3
+        w, b = bf(torch.randn(Co, Ci, 4, 1)), torch.randn(Co)
+        want = F.conv2d(x, w, b, stride=(2, 1))[0]                                   # (Co, Hq, T)
+        Hq = want.shape[1]
+        a = torch.stack([xp[2 * q: 2 * q + 4].permute(1, 0, 2).reshape(T, 4 * Cip) for q in range(Hq)])      # (Hq, T, K)
+        got = (a @ _unpack_b(P.pack_down(w)).t())[..., :Co].permute(2, 0, 1) + b.view(-1, 1, 1)
+        assert torch.allclose(got, want, atol=1e-4)
+        ws = _unpack_b(P.pack_down_strip(w, b))                                      # K groups: rows (+ per-row filler / bias groups)
+        if Cip == 8:
+            a_s = torch.stack([torch.cat([torch.cat([xp[2 * q + kh], _ones_k(T) if kh == 0 else torch.zeros(T, 8)], -1) for kh in range(4)], -1)
+                               for q in range(Hq)])
+        else:
+            a_s = torch.cat([a, _ones_k(T).expand(Hq, T, 8), torch.zeros(Hq, T, 8)], -1)
+        got = (a_s @ ws.t())[..., :Co].permute(2, 0, 1)
+        assert torch.allclose(got, want, atol=2e-3)                                  # bias as bf16 hi + lo
+        if Ci <= 4 and Co <= 8:                                                      # packed 4-channel input: a GEMM row is a frame pair
+            wp = _unpack_b(P.pack_down_pairs(w, b))
+            x4 = torch.zeros(H, T // 2, 2, 4)
+            x4[..., :Ci] = x[0].permute(1, 2, 0).reshape(H, T // 2, 2, Ci)
+            x4 = x4.reshape(H, T // 2, 8)
+            a_p = torch.stack([torch.cat([torch.cat([x4[2 * q + kh], _ones_k(T // 2) if kh == 0 else torch.zeros(T // 2, 8)], -1) for kh in range(4)], -1)
+                               for q in range(Hq)])
+            got = (a_p @ wp.t()).reshape(Hq, T // 2, 2, 8)[..., :Co].reshape(Hq, T, Co).permute(2, 0, 1)
+            assert torch.allclose(got, want, atol=2e-3)
+        # ---- transposed conv (4,1)/(2,1) as a polyphase GEMM: rows q-1, q -> output rows 2q, 2q+1
+        wt, bt = bf(torch.randn(Ci, Co, 4, 1)), torch.randn(Co)
+        for op in (0, 1):
+            want = F.conv_transpose2d(x, wt, bt, stride=(2, 1), output_padding=(op, 0))[0]                   # (Co, 2H + 2 + op, T)
+            Ho = want.shape[1]
+            xz = torch.cat([torch.zeros(1, T, Cip), xp, torch.zeros(2, T, Cip)])    # rows -1 .. H+1
+            rows = []
+            for q in range((Ho + 1) // 2):
+                a_q = torch.cat([xz[q], xz[q + 1]], -1)                              # input rows q-1, q
+                y = a_q @ _unpack_b(P.pack_up(wt)).t() + P.pack_up_bias(bt, Co)
+                if Cip > 8:
+                    a_s = torch.cat([a_q, _ones_k(T), torch.zeros(T, 8)], -1)
+                else:
+                    a_s = torch.cat([xz[q], _ones_k(T), xz[q + 1], torch.zeros(T, 8)], -1)
+                ys = a_s @ _unpack_b(P.pack_up_strip(wt, bt)).t()
+                assert torch.allclose(y, ys, atol=2e-3)
+                rows += [y[:, :Co], y[:, Cop:Cop + Co]]
+            got = torch.stack(rows[:Ho]).permute(2, 0, 1)
+            assert torch.allclose(got, want, atol=1e-4), (Ci, Co, op)
+    # ---- Encoder.convlat: one GEMM over the full height, K = (kh, ci)
+    C4, H4, D = 16, 5, 24
+    x = bf(torch.randn(1, C4, H4, T))
+    w = bf(torch.randn(D, C4, H4, 1))
+    want = F.conv2d(x, w)[0, :, 0]                                                   # (D, T)
+    a = x[0].permute(2, 1, 0).reshape(T, H4 * C4)
+    assert torch.allclose((a @ _unpack_b(P.pack_lat(w, 32)).t())[:, :D].t(), want, atol=1e-4)
+    # ---- Decoder.convin: per output row its own (C0 x D) operand; the indicator channel is a bias table
+    C0 = 16
+    wd, bd = bf(torch.randn(D + 1, C0, H4, 1)), torch.randn(C0)
+    lat = bf(torch.randn(1, D, 1, T))
+    packed, tables = P.pack_deconv_in(wd, bd, 32)
+    for ind in (0, 1):
+        want = F.conv_transpose2d(torch.cat([lat, torch.full((1, 1, 1, T), float(ind))], 1), wd, bd)[0]      # (C0, H4, T)
+        latp = torch.zeros(T, 32)
+        latp[:, :D] = lat[0, :, 0].t()
+        got = torch.stack([latp @ packed[h].float().permute(1, 0, 2).reshape(packed.shape[2], -1).t()[:, :C0] + tables[ind, h, :C0] for h in range(H4)])
+        assert torch.allclose(got.permute(2, 0, 1), want, atol=1e-4)
