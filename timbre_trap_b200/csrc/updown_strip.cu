@@ -48,7 +48,7 @@ struct UdSmem {
 // P4 (packed 4-channel layout on one side): DOWN reads it - a GEMM row is a frame PAIR, the 16 output columns are (frame parity, 8
 // channels) and go to two consecutive frames of the C8 planar output; UP writes it - only the first 4 channels of each output row.
 template <int CGIN, int N, int NCOL, bool UP, bool P4>
-__global__ void __launch_bounds__(kUdThreads, 1) updown_strip_kernel(const __grid_constant__ CUtensorMap tmap_x, const UpDownParams p) {
+__global__ void __launch_bounds__(kUdThreads, (N <= 32 && !UP) ? 2 : 1) updown_strip_kernel(const __grid_constant__ CUtensorMap tmap_x, const UpDownParams p) {
     using S = UdSmem<CGIN, N>;
     constexpr int kRing = S::kRing;
     constexpr int R = UP ? 2 : 4;                 // input rows per output row group
@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(kUdThreads, 1) updown_strip_kernel(const __gri
         const int j = quad * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
         const bool t_ok = t0 + j < p.T;
-        constexpr int NV = NCOL >= 16 ? 16 : 8;
+        // The strided convs with N <= 32 run two CTAs per SM (TMEM: 8 slots x N columns each; 40 registers per thread, hence 8-column
+        // TMEM loads): measured 0.69 -> 0.53 ms (4 -> 8 channels) and 0.68 -> 0.49 ms (8 -> 16); the transposed convs did not gain.
+        constexpr int NV = (NCOL >= 16 && (N > 32 || UP)) ? 16 : 8;
         for (int it = g; it < n_out; it += kUdGroups) {
             const int u = it / kUdSlots, a = it % kUdSlots;
             const int grp = g_start + it;
