@@ -13,7 +13,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_library_exports_every_header_symbol():
-    from timbre_trap_b200 import _lib
+    from timbre_trap_b200 import _lib, build
+    if not os.path.exists(_lib.LIB_PATH):
+        build.build()                                   # a fresh checkout: the .so is not in the history (nvcc cross-compiles without a GPU)
     header = open(os.path.join(ROOT, 'include', 'timbre_trap_b200.h')).read()
     declared = set(re.findall(r'\b(tt_[a-z0-9_]+)\s*\(', header))
     assert declared, 'no declarations found'
