@@ -250,12 +250,14 @@ def inference_ref(audio, sd, cqt, transcribe=False):
     return decode_ref(latents, sd, cqt.n_bins, transcribe, _skips(sd, emb))
 
 
-def chunked_inference_ref(audio, sd, cqt, transcribe=False):
-    """TimbreTrap.chunked_inference (modules.py:204-269): 50 % overlapped blocks, Hann cross-fade of coefficients, trim."""
+def chunked_inference_ref(audio, sd, cqt, transcribe=False, prepadded=False):
+    """TimbreTrap.chunked_inference (modules.py:204-269): 50 % overlapped blocks, Hann cross-fade of coefficients, trim.
+    prepadded: `audio` already is whole blocks plus half a block on either side (a shard with its neighbourhood)."""
     B, nb = audio.size(0), cqt.n_bins
-    audio = cqt.pad_to_block_length(audio)
     hop = cqt.block_length // 2
-    audio = F.pad(audio, [hop, hop])
+    if not prepadded:
+        audio = cqt.pad_to_block_length(audio)
+        audio = F.pad(audio, [hop, hop])
     n_chunks = (audio.size(-1) - hop) // hop
     M = cqt.max_window_length
     window = hann_sym(M)

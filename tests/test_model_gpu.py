@@ -112,3 +112,23 @@ def test_chunk_batching_is_invisible():
     model.MAX_CHUNKS_PER_BATCH = 3
     b = model.transcribe(audio)
     assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(os.environ.get('TT_TEST_SHARDED') != '1',
+                    reason='sharded long-clip methods: host logic is covered on CPU (tests/test_sharding_gloo.py); the GPU run of this '
+                           'test is opt-in (TT_TEST_SHARDED=1) until it has been executed once on a B200')
+def test_sharded_long_clip_equals_unsharded():
+    """transcribe_sharded / reconstruct_sharded with the ranks emulated one after the other on one GPU."""
+    model, sd, c = _build(SMALL, 16, 1, False, seed=0)
+    L = model.sliCQ.block_length
+    audio = tonal_clip(5 * L - 77, SMALL[2], seed=4).cuda()
+    act = model.transcribe(audio)
+    world = 3
+    parts = [model.transcribe_sharded(audio, rank=r, world=world, gather=False) for r in range(world)]
+    assert torch.equal(torch.cat(parts, dim=-1), act)
+    rec = model._chunked(audio, False, True)[1]
+    raws = []
+    for r in range(world):
+        sub, b0, b1 = model.shard_audio(audio, r, world)
+        raws.append(model._chunked(sub, False, True, prepadded=True)[1])
+    assert torch.equal(torch.cat(raws, dim=2), rec)

@@ -75,3 +75,35 @@ def test_gradient_bucket_allreduce_equals_global_batch(tmp_path):
     mp.spawn(_grad_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     errs = [float(np.load(os.path.join(tmp_path, f'gerr{r}.npy'))[0]) for r in range(2)]
     assert max(errs) < 1e-5
+
+
+def _clip_worker(rank, world, port, out_dir):
+    """One long clip over several ranks (BASELINE.json configs[4]): every rank runs the reference's chunk loop (oracle) on ITS
+    blocks plus the half-block halos cut by framework.modules.shard_audio, the product's all_gather helper reassembles the
+    frames - the result must equal the unsharded loop on the whole clip."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from oracle import model_ref as R
+    from tests.helpers import tonal_clip
+    from timbre_trap_b200.framework.modules import _gather_frames, shard_audio
+    cqt = R.CQTRef(6, 12, 8000, 0.5)
+    sd = R.init_state_dict(cqt.n_bins, 16, 1, seed=0)
+    L, M = cqt.block_length, cqt.max_window_length
+    audio = tonal_clip(5 * L - 123, 8000, seed=9)                       # 5 blocks after padding: ranks own 2 and 3 blocks
+    sub, b0, b1 = shard_audio(cqt.pad_to_block_length(audio), L, rank, world)
+    local = R.chunked_inference_ref(sub, sd, cqt, True, prepadded=True)             # (1, 2, F, (b1 - b0) * M)
+    whole = R.chunked_inference_ref(audio, sd, cqt, True)
+    err_local = float((local - whole[..., b0 * M: b1 * M]).abs().max())
+    gathered = _gather_frames(local.contiguous(), -1, M, audio, L, dist.group.WORLD, world)
+    err_gather = float((gathered - whole).abs().max()) if gathered.shape == whole.shape else 1e9
+    np.save(os.path.join(out_dir, f'cerr{rank}.npy'), np.array([err_local, err_gather, b1 - b0]))
+    dist.destroy_process_group()
+
+
+def test_long_clip_sharded_by_blocks_equals_unsharded(tmp_path):
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_clip_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    res = [np.load(os.path.join(tmp_path, f'cerr{r}.npy')) for r in range(2)]
+    assert sorted(int(r[2]) for r in res) == [2, 3]
+    assert max(r[0] for r in res) < 1e-5 and max(r[1] for r in res) < 1e-5

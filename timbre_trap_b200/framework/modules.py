@@ -20,7 +20,7 @@ from . import ops
 from . import packing as P
 from .cqt import CQT
 
-__all__ = ['TimbreTrap', 'Encoder', 'Decoder', 'EncoderBlock', 'DecoderBlock', 'ResidualConv2dBlock']
+__all__ = ['TimbreTrap', 'Encoder', 'Decoder', 'EncoderBlock', 'DecoderBlock', 'ResidualConv2dBlock', 'shard_block_range', 'shard_audio']
 
 
 class _PackedCache:
@@ -305,6 +305,44 @@ def _latents_to_c8(latents, latent_pad):
     return x.reshape(B, latent_pad // 8, 8, 1, T).permute(0, 1, 3, 4, 2).contiguous().to(torch.bfloat16)
 
 
+def shard_block_range(n_blocks, rank, world):
+    """Contiguous, balanced ranges of blocks: rank r owns [r * n // world, (r + 1) * n // world)."""
+    return rank * n_blocks // world, (rank + 1) * n_blocks // world
+
+
+def shard_audio(padded, block_length, rank, world):
+    """padded (B, 1, n * L): the samples rank `rank` needs for its output blocks [b0, b1) - those blocks plus half a block on
+    either side (zeros beyond the ends of the clip, exactly the padding of the unsharded loop, modules.py:226-234)."""
+    L, hop = block_length, block_length // 2
+    b0, b1 = shard_block_range(padded.size(-1) // L, rank, world)
+    haloed = torch.nn.functional.pad(padded, [hop, hop])
+    return haloed[..., b0 * L: b1 * L + 2 * hop], b0, b1
+
+
+def _rank_world(group, rank, world):
+    if rank is None or world is None:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    return rank, world
+
+
+def _gather_frames(local, dim, per_block, audio, block_length, group, world):
+    """all_gather of per-rank results whose extent along `dim` is (blocks of the rank) * per_block (ranks may differ by one block)."""
+    if group is None or world == 1:
+        return local
+    import torch.distributed as dist
+    n_blocks = -(-audio.size(-1) // block_length)
+    counts = [shard_block_range(n_blocks, r, world) for r in range(world)]
+    most = max(b1 - b0 for b0, b1 in counts) * per_block
+    shape = list(local.shape)
+    shape[dim] = most
+    mine = torch.zeros(shape, dtype=local.dtype, device=local.device)
+    mine.narrow(dim, 0, local.size(dim)).copy_(local)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    return torch.cat([p.narrow(dim, 0, (b1 - b0) * per_block) for p, (b0, b1) in zip(parts, counts)], dim=dim)
+
+
 class TimbreTrap(nn.Module):
     """modules.py:23-393.  Same public surface; `sliCQ` is the CQT module (every reference script uses that name)."""
 
@@ -367,17 +405,22 @@ class TimbreTrap(nn.Module):
             self._windows[key] = torch.signal.windows.hann(self.sliCQ.max_window_length, device=device)
         return self._windows[key]
 
-    def _chunks(self, audio):
-        """Pad and slice audio into 50 %-overlapped blocks (modules.py:226-234, 247-253): (B*n_chunks, 1, L), n_chunks."""
-        audio = self.sliCQ.pad_to_block_length(audio)
+    def _chunks(self, audio, prepadded=False):
+        """Pad and slice audio into 50 %-overlapped blocks (modules.py:226-234, 247-253): (B*n_chunks, 1, L), n_chunks.
+        prepadded: `audio` already is a whole number of blocks plus the half-block on either side (a shard of a longer clip
+        with its true neighbourhood, see shard_audio)."""
         L = self.sliCQ.block_length
         hop = L // 2
-        audio = torch.nn.functional.pad(audio, [hop] * 2)
+        if not prepadded:
+            audio = self.sliCQ.pad_to_block_length(audio)
+            audio = torch.nn.functional.pad(audio, [hop] * 2)
+        elif (audio.size(-1) - 2 * hop) % L:
+            raise ValueError(f'a pre-padded shard must hold n * {L} + {2 * hop} samples, got {audio.size(-1)}')
         n_chunks = (audio.size(-1) - hop) // hop
         chunks = audio.unfold(-1, L, hop)[:, :, :n_chunks]                 # (B, 1, n_chunks, L) view
         return chunks.reshape(audio.size(0) * n_chunks, 1, L), n_chunks
 
-    def _chunked(self, audio, want_transcription, want_reconstruction, activations=True):
+    def _chunked(self, audio, want_transcription, want_reconstruction, activations=True, prepadded=False):
         """
         Batched form of chunked_inference (modules.py:204-269) for one or both switch settings with a shared
         encoder pass.  Returns (transcription, reconstruction) coefficient tensors (B, F, T, 2) interleaved - or the
@@ -386,7 +429,7 @@ class TimbreTrap(nn.Module):
         _lib.require_cuda(audio, 'audio')
         with torch.no_grad():
             B, F, M = audio.size(0), self.sliCQ.n_bins, self.sliCQ.max_window_length
-            chunks, n_chunks = self._chunks(audio.detach().float())
+            chunks, n_chunks = self._chunks(audio.detach().float(), prepadded)
             n_out = (n_chunks - 1) * (M // 2)
             window = self._window(audio.device)
             outs = []
@@ -452,6 +495,42 @@ class TimbreTrap(nn.Module):
         """Both outputs of transcribe() and reconstruct() from ONE encoder pass (not in the reference, which runs two)."""
         act, rec = self._chunked(audio, True, True)
         return act, self._decode_shared_peak(rec.permute(0, 3, 1, 2), group)
+
+    # ---- one long clip over several GPUs (BASELINE.json configs[4]) ---------------------------------------------------
+    # Blocks are independent except for the 50 % cross-fade with the two neighbouring chunks (modules.py:259-263): a rank that
+    # owns output blocks [b0, b1) needs the audio of those blocks plus half a block on either side and nothing else - no
+    # collective on the compute path; the results are all-gathered (and `reconstruct` shares one scalar MAX for the peak).
+    def shard_audio(self, audio, rank, world):
+        """(B, 1, N) -> (the rank's slice with its half-block halos, b0, b1): contiguous ranges of output blocks."""
+        return shard_audio(self.sliCQ.pad_to_block_length(audio), self.sliCQ.block_length, rank, world)
+
+    def transcribe_sharded(self, audio, group=None, rank=None, world=None, gather=True):
+        """transcribe() of a clip every rank holds, each rank computing a contiguous range of blocks.  Returns the whole
+        (B, F, T) activations on every rank (gather=True, via all_gather over `group`) or the rank's own frames."""
+        rank, world = _rank_world(group, rank, world)
+        sub, b0, b1 = self.shard_audio(audio, rank, world)
+        M, F = self.sliCQ.max_window_length, self.sliCQ.n_bins
+        if b1 > b0:
+            local = self._chunked(sub, True, False, prepadded=True)[0]
+        else:
+            local = torch.empty((audio.size(0), F, 0), dtype=torch.float32, device=audio.device)
+        return _gather_frames(local, -1, M, audio, self.sliCQ.block_length, group, world) if gather else local
+
+    def reconstruct_sharded(self, audio, group=None, rank=None, world=None, gather=True):
+        """reconstruct() of a clip every rank holds, sharded like transcribe_sharded; the reference's global peak normalise
+        (cqtwrapper.py:209-211) is one scalar MAX all-reduce over `group`."""
+        rank, world = _rank_world(group, rank, world)
+        sub, b0, b1 = self.shard_audio(audio, rank, world)
+        L = self.sliCQ.block_length
+        if b1 > b0:
+            rec = self._chunked(sub, False, True, prepadded=True)[1].permute(0, 3, 1, 2)
+            local = self._decode_shared_peak(rec, group)
+        else:
+            local = torch.empty((audio.size(0), 1, 0), dtype=torch.float32, device=audio.device)
+            if group is not None:                      # still take part in the peak exchange
+                import torch.distributed as dist
+                dist.all_reduce(torch.zeros(1, device=audio.device), op=dist.ReduceOp.MAX, group=group)
+        return _gather_frames(local, -1, L, audio, L, group, world) if gather else local
 
     def forward(self, audio, consistency=False):
         """modules.py:338-393 (inference semantics; the training step with gradients is framework.train_step)."""
