@@ -126,10 +126,8 @@ int tt_multipitch_counts(const unsigned char* est, const unsigned char* ref, int
  * timbre_trap_b200/framework/packing.py (one function per entry point).  Biases: fp32, padded to N.
  */
 
-/* ResidualConv2dBlock.forward (modules.py:743-777), fused: y = x + ELU(W2 * ELU(W1 (*)_dilation x + b1) + b2) */
-int tt_res_block(const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
-                 int B, int C, int H, int T, int dilation, void* stream);
-/* The same block as a warp-specialised, row-pipelined kernel (TMA row ring -> tcgen05 -> TMEM -> epilogue warps), in
+/* ResidualConv2dBlock.forward (modules.py:743-777), fused: y = x + ELU(W2 * ELU(W1 (*)_dilation x + b1) + b2),
+ * as a warp-specialised, row-pipelined kernel (TMA row ring -> tcgen05 -> TMEM -> epilogue warps), in
  * row-stationary form: every input row meets the weights of all three vertical taps in one N = 3C MMA per horizontal tap (a third
  * of the shared-memory operand reads of one-MMA-per-tap); accumulators of the output rows are TMEM rings that start out holding
  * the fp32 bias.  c_real = un-padded channel count.  layout selects how memory maps to GEMM rows:
@@ -145,14 +143,15 @@ int tt_res_block_rs(const void* x, void* y, const void* w1, const void* w2, cons
  * planar tensors: building block of the backward pass (recompute + data gradients as convs with transformed weights) */
 int tt_conv_same(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,
                  int act_elu, void* stream);
-/* EncoderBlock.sconv + ELU (modules.py:626-629): Conv2d(Cin, Cout, (4,1), stride (2,1)); Hout = (Hin-4)/2 + 1 */
-int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int T, void* stream);
-/* DecoderBlock.tconv + ELU (modules.py:685-688): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding); Hout = 2 Hin + 2 + out_pad */
-int tt_conv_up(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int out_pad, int T, void* stream);
-/* The same two layers as row-pipelined kernels (csrc/updown_strip.cu); weights from packing.pack_down_strip / pack_up_strip
+/* EncoderBlock.sconv + ELU (modules.py:626-629): Conv2d(Cin, Cout, (4,1), stride (2,1)); Hout = (Hin-4)/2 + 1, and
+ * DecoderBlock.tconv + ELU (modules.py:685-688): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding);
+ * Hout = 2 Hin + 2 + out_pad - row-pipelined kernels (csrc/updown_strip.cu); weights from packing.pack_down_strip / pack_up_strip
  * (bias folded in).  Supported padded channel pairs: down 8->8, 8->16, 16->32, 32->64; up 64->32, 32->16, 16->8, 8->8. */
 /* packed4_in / packed4_out = 1: the input (down, 4 -> 8 channels, weights from packing.pack_down_pairs) / the output (up, 8 -> 4
  * channels) is the packed 4-channel layout (B, H, T, 4) bf16; pass the padded channel counts 8 -> 8. */
+/* Testing / tuning knob of the row-pipelined kernels (residual blocks, strided and transposed convs): force the number of image
+ * rows (row groups) one CTA walks; 0 restores the automatic split.  Results do not depend on it (tests/test_conv_ops_gpu.py). */
+int tt_set_strip_rows(int rows);
 int tt_conv_down_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int T, int packed4_in, void* stream);
 int tt_conv_up_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int out_pad, int T, int packed4_out,
                      void* stream);
@@ -207,13 +206,6 @@ int tt_activations_bwd(const float* coeffs, const float* dact, float* dcoeffs, i
 int tt_grad_sumsq(const float* g, int64_t n, double* acc, void* stream);
 int tt_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, const double* sumsq, float max_norm, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
-
-/*
- * Self-test of the tcgen05 / TMEM plumbing the conv kernels are built on (no reference counterpart):
- * D (128 x n, fp32) = A (128 x k, bf16, row-major) * B (n x k, bf16, row-major)^T on one CTA.
- * swap_lbo_sbo = 1 encodes the shared-memory descriptors with the two stride fields exchanged (must FAIL).
- */
-int tt_umma_probe(const void* a_bf16, const void* b_bf16, float* d, int n, int k, int swap_lbo_sbo, void* stream);
 
 #ifdef __cplusplus
 }

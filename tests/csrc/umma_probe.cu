@@ -1,9 +1,23 @@
 // Self-test of the tcgen05 plumbing in umma.cuh: D (128 x N, fp32) = A (128 x K, bf16) * B (N x K, bf16)^T on one
 // CTA, operands staged by plain loads into the SWIZZLE_NONE K-major canonical layout.  The GPU test suite runs it
 // before any conv kernel so that a descriptor-encoding mistake shows up as a GEMM mismatch, not as a wrong model.
-#include "../../include/timbre_trap_b200.h"
-#include "tt_common.cuh"
-#include "umma.cuh"
+// TEST-ONLY: built into tests/csrc/libtt_selftest.so by timbre_trap_b200.build.build_selftest(); not part of the product ABI.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../timbre_trap_b200/csrc/tt_common.cuh"
+#include "../../timbre_trap_b200/csrc/umma.cuh"
+
+// the product library's error / launch bookkeeping hooks, private to this test library
+static thread_local char g_selftest_err[512] = "";
+void tt_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_selftest_err, sizeof(g_selftest_err), fmt, ap);
+    va_end(ap);
+}
+void tt_count_launches(int) {}
+extern "C" const char* tt_selftest_last_error(void) { return g_selftest_err; }
 
 namespace tt {
 

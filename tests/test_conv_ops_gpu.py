@@ -20,50 +20,27 @@ def _bf(x):
     return x.to(torch.bfloat16).float()
 
 
+@pytest.fixture
+def force_strip_rows():
+    """tt_set_strip_rows(rows) for the duration of one test (automatic split restored afterwards)."""
+    from timbre_trap_b200 import _lib
+    yield lambda rows: _lib.check(_lib.lib().tt_set_strip_rows(rows))
+    _lib.lib().tt_set_strip_rows(0)
+
+
 def _assert_close(got, want, tol=1.2e-2):
     err = float((got - want).abs().max())
     ref = float(want.abs().max())
     assert err <= tol * ref, (err, ref)
 
 
-@pytest.mark.parametrize('C,H,T,d,B', [(4, 37, 256, 1, 2), (8, 30, 128, 2, 1), (8, 19, 384, 3, 2), (16, 33, 256, 1, 2),
-                                         (16, 21, 128, 3, 1), (32, 65, 256, 2, 1), (32, 17, 128, 3, 2), (2, 20, 200, 1, 1)])
-def test_res_block(C, H, T, d, B):
-    from timbre_trap_b200.framework import ops, packing as P
-    x = _bf(_rand((B, C, H, T), 1))
-    w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
-    w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
-    mid = _bf(F.elu(F.conv2d(x, w1, b1, padding=d, dilation=d)))
-    want = x + F.elu(F.conv2d(mid, w2, b2))
-    n = max(16, P.pad8(C))
-    y = ops.res_block(P.to_c8(x.cuda()), P.pack_res3x3(w1.cuda()), P.pad_vec(b1.cuda(), n), P.pack_res1x1(w2.cuda()),
-                      P.pad_vec(b2.cuda(), n), d)
-    got = P.from_c8(y, C).cpu()
-    _assert_close(got, want)
-    if P.pad8(C) != C:   # padded channels stay exactly zero
-        assert float(y.float().permute(0, 1, 4, 2, 3).reshape(B, -1, H, T)[:, C:].abs().max()) == 0.0
-
-
-@pytest.mark.parametrize('Cin,Cout,H,T,B', [(4, 8, 40, 256, 2), (8, 16, 27, 128, 1), (16, 32, 33, 256, 2), (32, 64, 65, 128, 1),
-                                              (2, 4, 20, 100, 1)])
-def test_conv_down(Cin, Cout, H, T, B):
-    from timbre_trap_b200.framework import ops, packing as P
-    x = _bf(_rand((B, Cin, H, T), 11))
-    w, b = _bf(_rand((Cout, Cin, 4, 1), 12, 0.3)), _rand((Cout,), 13, 0.3)
-    want = F.elu(F.conv2d(x, w, b, stride=(2, 1)))
-    n = max(16, P.pad8(Cout))
-    y = ops.conv_down(P.to_c8(x.cuda()), P.pack_down(w.cuda()), P.pad_vec(b.cuda(), n), P.pad8(Cout))
-    assert y.shape[2] == want.shape[2]
-    _assert_close(P.from_c8(y, Cout).cpu(), want)
-
-
 @pytest.mark.parametrize('Cin,Cout,H,T,B', [(4, 8, 540, 128, 1), (8, 16, 269, 256, 2), (16, 32, 133, 128, 1), (32, 64, 65, 256, 2),
                                               (2, 4, 20, 100, 1), (8, 16, 7, 128, 1)])
 @pytest.mark.parametrize('strip_rows', [None, 5])
-def test_conv_down_strip(Cin, Cout, H, T, B, strip_rows, monkeypatch):
+def test_conv_down_strip(Cin, Cout, H, T, B, strip_rows, force_strip_rows):
     from timbre_trap_b200.framework import ops, packing as P
     if strip_rows:
-        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+        force_strip_rows(strip_rows)
     x = _bf(_rand((B, Cin, H, T), 11))
     w, b = _bf(_rand((Cout, Cin, 4, 1), 12, 0.3)), _rand((Cout,), 13, 0.3)
     want = F.elu(F.conv2d(x, w, b, stride=(2, 1)))
@@ -114,26 +91,14 @@ def test_conv_in_out_packed4():
 @pytest.mark.parametrize('Cin,Cout,H,T,op,B', [(64, 32, 31, 128, 1, 2), (32, 16, 65, 256, 1, 1), (16, 8, 133, 128, 1, 2),
                                                  (8, 4, 269, 256, 0, 1), (4, 2, 9, 100, 1, 1), (16, 8, 5, 128, 0, 1)])
 @pytest.mark.parametrize('strip_rows', [None, 3])
-def test_conv_up_strip(Cin, Cout, H, T, op, B, strip_rows, monkeypatch):
+def test_conv_up_strip(Cin, Cout, H, T, op, B, strip_rows, force_strip_rows):
     from timbre_trap_b200.framework import ops, packing as P
     if strip_rows:
-        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+        force_strip_rows(strip_rows)
     x = _bf(_rand((B, Cin, H, T), 21))
     w, b = _bf(_rand((Cin, Cout, 4, 1), 22, 0.3)), _rand((Cout,), 23, 0.3)
     want = F.elu(F.conv_transpose2d(x, w, b, stride=(2, 1), output_padding=(op, 0)))
     y = ops.conv_up_strip(P.to_c8(x.cuda()), P.pack_up_strip(w.cuda(), b.cuda()), P.pad8(Cout), op)
-    assert y.shape[2] == want.shape[2]
-    _assert_close(P.from_c8(y, Cout).cpu(), want)
-
-
-@pytest.mark.parametrize('Cin,Cout,H,T,op,B', [(64, 32, 31, 128, 1, 2), (32, 16, 65, 256, 1, 1), (16, 8, 33, 128, 1, 2),
-                                                 (8, 4, 29, 256, 0, 1), (4, 2, 9, 100, 1, 1), (16, 8, 5, 128, 0, 1)])
-def test_conv_up(Cin, Cout, H, T, op, B):
-    from timbre_trap_b200.framework import ops, packing as P
-    x = _bf(_rand((B, Cin, H, T), 21))
-    w, b = _bf(_rand((Cin, Cout, 4, 1), 22, 0.3)), _rand((Cout,), 23, 0.3)
-    want = F.elu(F.conv_transpose2d(x, w, b, stride=(2, 1), output_padding=(op, 0)))
-    y = ops.conv_up(P.to_c8(x.cuda()), P.pack_up(w.cuda()), P.pack_up_bias(b.cuda(), Cout), P.pad8(Cout), op)
     assert y.shape[2] == want.shape[2]
     _assert_close(P.from_c8(y, Cout).cpu(), want)
 
@@ -199,12 +164,12 @@ def test_conv_same(C, H, T, k, d, act):
                                          (4, 540, 128, 3, 1), (32, 5, 128, 3, 1), (16, 2, 100, 2, 3), (16, 67, 128, 2, 1),
                                          (32, 70, 128, 1, 1)])
 @pytest.mark.parametrize('strip_rows', [None, 7, 2])
-def test_res_block_rs(C, H, T, d, B, strip_rows, monkeypatch):
+def test_res_block_rs(C, H, T, d, B, strip_rows, force_strip_rows):
     """Row-stationary residual block (csrc/res_rs.cu): image edges, strip seams (rows per strip below the dilation included),
     TMEM ring wrap-around (H well above the slot count)."""
     from timbre_trap_b200.framework import ops, packing as P
     if strip_rows:
-        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+        force_strip_rows(strip_rows)
     x = _bf(_rand((B, C, H, T), 1))
     w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
     w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
@@ -221,10 +186,10 @@ def test_res_block_rs(C, H, T, d, B, strip_rows, monkeypatch):
 @pytest.mark.parametrize('C,H,T,d,B', [(4, 37, 256, 1, 2), (4, 30, 512, 2, 1), (4, 540, 256, 3, 1), (2, 20, 200, 1, 1), (3, 9, 260, 3, 2),
                                          (4, 3, 1024, 2, 1)])
 @pytest.mark.parametrize('strip_rows', [None, 7, 1])
-def test_res_block_rs_packed4(C, H, T, d, B, strip_rows, monkeypatch):
+def test_res_block_rs_packed4(C, H, T, d, B, strip_rows, force_strip_rows):
     from timbre_trap_b200.framework import ops, packing as P
     if strip_rows:
-        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+        force_strip_rows(strip_rows)
     x = _bf(_rand((B, C, H, T), 1))
     w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
     w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)
@@ -242,11 +207,11 @@ def test_res_block_rs_packed4(C, H, T, d, B, strip_rows, monkeypatch):
                                               (3, 9, 260, 3, 2, 4), (8, 30, 256, 1, 2, 2), (8, 269, 512, 2, 1, 2), (8, 19, 384, 3, 2, 2),
                                               (5, 12, 130, 3, 1, 2), (8, 3, 1024, 1, 1, 2)])
 @pytest.mark.parametrize('strip_rows', [None, 7])
-def test_res_block_rs_folded(C, H, T, d, B, fold, strip_rows, monkeypatch):
+def test_res_block_rs_folded(C, H, T, d, B, fold, strip_rows, force_strip_rows):
     """Folded rows: 4 frames x 4 channels of the packed layout, or 2 frames x 8 channels of C8 planar, per GEMM row."""
     from timbre_trap_b200.framework import ops, packing as P
     if strip_rows:
-        monkeypatch.setenv('TT_STRIP_ROWS', str(strip_rows))
+        force_strip_rows(strip_rows)
     x = _bf(_rand((B, C, H, T), 1))
     w1, b1 = _bf(_rand((C, C, 3, 3), 2, 0.3)), _rand((C,), 3, 0.3)
     w2, b2 = _bf(_rand((C, C, 1, 1), 4, 0.5)), _rand((C,), 5, 0.3)

@@ -104,14 +104,93 @@ def test_magnitude_and_decibels():
     c = ref(x)
     mag = cqt.to_magnitude(c.cuda())
     assert rel_err(mag.cpu().numpy(), ref.to_magnitude(c).numpy())[0] < 1e-6
-    db = cqt.to_decibels(mag)
     want = to_decibels_ref(ref.to_magnitude(c))
-    # typical deviation 1e-7; ONE of ~15 full-suite runs of round 1 showed 1.4e-4 (0.011 dB) here and could not be reproduced
-    # (6 repeats of this file + 2 full runs right after were clean) - see DESIGN.md "Known issues"; the bound keeps the gate
-    # meaningful (0.04 dB) without failing a round on that one-off
-    assert float((db.cpu() - want).abs().max()) < 5e-4
+    want_raw = to_decibels_ref(ref.to_magnitude(c), rescale=False)
+    # Round 1 saw ONE 1.4e-4 deviation here in ~15 suite runs.  The path is memset + max-reduction (atomicMax on float bits) +
+    # element-wise map on one stream: any timing dependence would show as run-to-run differences, so the call is repeated and
+    # must be BIT-IDENTICAL every time, and the oracle bound is the tight one (expected deviation ~1e-7).  compute-sanitizer
+    # racecheck / initcheck logs of this test are under profiles/ (r02_sanitizer_*.txt).
+    first = cqt.to_decibels(mag)
+    for i in range(25):
+        again = cqt.to_decibels(mag)
+        assert torch.equal(again, first), f'run {i}: to_decibels is not reproducible'
+    err = (first.cpu() - want).abs()
+    if float(err.max()) >= 1e-5:
+        k = int(err.argmax())
+        b_, rest = divmod(k, want[0].numel())
+        raise AssertionError(f'to_decibels deviates by {float(err.max()):.3e} at item {b_}, flat index {rest}: got {float(first.flatten()[k])}, '
+                             f'want {float(want.flatten()[k])}, magnitude {float(mag.flatten()[k])}, item max {float(mag[b_].max())} '
+                             f'(oracle item max {float(ref.to_magnitude(c)[b_].max())})')
     db_raw = cqt.to_decibels(mag, rescale=False)
-    assert float((db_raw.cpu() - to_decibels_ref(ref.to_magnitude(c), rescale=False)).abs().max()) < 1e-3
+    assert float((db_raw.cpu() - want_raw).abs().max()) < 1e-3
+    # degenerate items: all-zero (clamped to 1e-10 on both sides) and a single spike
+    z = torch.zeros(2, 5, 7)
+    z[1, 2, 3] = 3.0
+    assert float((cqt.to_decibels(z.cuda()).cpu() - to_decibels_ref(z)).abs().max()) < 1e-5
+
+
+def test_tables_from_checkpoint_buffers_drive_the_kernels():
+    """A reference checkpoint's sliCQ.* buffers replace the restated tables: the kernels then reproduce THAT transform.  Emulated
+    with a variant of the oracle (symmetric instead of periodic Hann, one of the open choices U1-U8) emitted in upstream's dense
+    buffer shapes - the default-constructed CQT must NOT match it, the loaded one must, to 1e-4."""
+    import oracle.nsgt_ref as N
+    from oracle.model_ref import CQTRef
+    from timbre_trap_b200.framework import CQT
+    old = N.U4_HANN_PERIODIC
+    N.U4_HANN_PERIODIC = False
+    try:
+        ref = CQTRef(*SMALL)
+    finally:
+        N.U4_HANN_PERIODIC = old
+    t = ref.nsgt.tables
+    x = tonal_clip(2 * ref.block_length, SMALL[2], seed=5, n_batch=2)
+    want = ref(x)
+    cqt = CQT(*SMALL)
+    assert rel_err(cqt(x.cuda()).cpu().numpy(), want.numpy())[1] > 1e-3          # the open choice matters at the 1e-3 level
+    cqt.load_state_dict({'windows': torch.from_numpy(t.win).float(), 'windows_range_indices': torch.from_numpy(t.idx),
+                         'windows_inverse': torch.from_numpy(t.win_inv).float()})
+    got = cqt(x.cuda())
+    emax, el2 = rel_err(got.cpu().numpy(), want.numpy())
+    assert emax < TOL and el2 < TOL, (emax, el2)
+    emax, el2 = rel_err(cqt.decode(got).cpu().numpy(), ref.decode(want).numpy())
+    assert emax < TOL and el2 < TOL, (emax, el2)
+
+
+@pytest.mark.parametrize('cfg', [BASE, SMALL])
+def test_frame_properties_independent_of_the_oracle(cfg):
+    """
+    Properties of a painless non-stationary Gabor frame that hold whatever the restated table details are - checked with
+    torch.fft on the GPU and the product's own tables, NOT with the oracle's transform:
+      (a) energy identity: sum |c|^2 = (1/M) sum_j |X_j|^2 D_j over the one-sided spectrum, D = frame-operator diagonal
+          (sum of squared windows); hence the frame bounds  A ||x_band||^2 <= sum |c|^2 <= B ||x||^2;
+      (b) frame-operator identity: the un-normalised synthesis of the analysis is x/2 on the covered band (the transform keeps
+          the positive-frequency half only), i.e. decode_raw(encode(x)) == irfft(rfft(x) * [D > 0]) / 2.
+    """
+    from timbre_trap_b200.framework import CQT
+    cqt = CQT(*cfg)
+    b, L, M = cqt._bank, cqt.block_length, cqt.max_window_length
+    diag = np.zeros(L // 2 + 1)
+    for k in range(b.n_bins):
+        diag[b.start[k]: b.start[k] + b.length[k]] += b.win[b.offset[k]: b.offset[k + 1]].astype(np.float64) ** 2
+    D = torch.from_numpy(diag).cuda()
+    g = torch.Generator().manual_seed(3)
+    x = torch.cat([tonal_clip(L, cfg[2], seed=2, n_batch=1), torch.rand((1, 1, L), generator=g) * 2 - 1]).cuda()
+    c = cqt(x)                                                      # (2, 2, F, M)
+    X = torch.fft.rfft(x[:, 0].double(), dim=-1)                    # (2, L/2 + 1)
+    energy = (c.double() ** 2).sum(dim=(1, 2, 3))
+    want = (X.abs() ** 2 * D).sum(-1) / M
+    assert float(((energy - want).abs() / want).max()) < 1e-4
+    covered = D > 0
+    upper = D.max() * (X.abs() ** 2).sum(-1) / M
+    lower = D[covered].min() * (X.abs() ** 2 * covered).sum(-1) / M
+    assert bool((energy <= upper * (1 + 1e-5)).all()) and bool((energy >= lower * (1 - 1e-5)).all())
+    raw, _ = cqt.decode_raw(c)
+    ideal = torch.fft.irfft(X * covered, n=L, dim=-1) / 2
+    # DC and (for even L) Nyquist are their own mirror images: the one-sided synthesis keeps them whole, not halved
+    assert not bool(covered[0]) and not bool(covered[-1])
+    emax, el2 = rel_err(raw[:, 0].cpu().numpy(), ideal.cpu().numpy())
+    # (the complex64 CPU oracle holds this identity to 2e-5 on the noise item, 6e-7 on the tonal one)
+    assert emax < TOL and el2 < TOL, (emax, el2)
 
 
 def test_rejects_cpu_and_ragged_inputs():

@@ -67,6 +67,87 @@ def test_geometry_and_state_dict_match_reference(golden_dir):
     assert 'skip_weights' in ms.state_dict() and ms.sliCQ.n_bins == 540
 
 
+def test_models_with_live_plans_pickle_and_deepcopy():
+    """The reference checkpoints WHOLE modules (experiments/train.py:511 torch.save(model, path); every script torch.load()s
+    them): a model that has already run on a device (= holds a plan with raw device handles) must still pickle / deep-copy."""
+    import copy
+    import io
+    from timbre_trap_b200.framework import TimbreTrap
+
+    class FakePlan:                                        # what CQT._plan() caches after the first GPU call
+        handle = ctypes.c_void_p(0x1234)
+        device = 'cuda:0'
+
+    m = TimbreTrap(8000, 6, 12, 0.5, latent_size=16, model_complexity=1, skip_connections=True)
+    m.sliCQ._plans[('cuda', 0)] = FakePlan()
+    m._windows[('cuda', 0)] = torch.ones(4)
+    m.encoder.block1.block1._packed('planar')              # a live packed-weight cache entry
+    with pytest.raises(Exception):
+        import pickle
+        pickle.dumps(FakePlan.handle)                      # the thing that used to break torch.save(model)
+    c = copy.deepcopy(m)
+    assert c.sliCQ._plans == {} and c._windows == {} and m.sliCQ._plans          # the copy starts without plans, the original keeps its own
+    buf = io.BytesIO()
+    torch.save(m, buf)
+    buf.seek(0)
+    r = torch.load(buf, weights_only=False)
+    assert r.sliCQ._plans == {} and r.sliCQ.block_length == m.sliCQ.block_length
+    assert np.array_equal(r.sliCQ._bank.win, m.sliCQ._bank.win)
+    for (k, a), (_, b) in zip(m.state_dict().items(), r.state_dict().items()):
+        assert torch.equal(a, b), k
+    m.sliCQ._plans.clear()
+
+
+def test_filter_bank_from_checkpoint_buffers():
+    """CQT.load_state_dict drives the kernels with the tables a reference checkpoint carries (sliCQ.windows /
+    windows_range_indices / windows_inverse) - here emitted by the oracle in the dense upstream shape, in two variants."""
+    import oracle.nsgt_ref as N
+    from timbre_trap_b200.framework import CQT
+    from timbre_trap_b200.nsgt_tables import FilterBank
+    cfg = (6, 12, 8000, 0.5)
+    for periodic in (True, False):
+        old = N.U4_HANN_PERIODIC
+        N.U4_HANN_PERIODIC = periodic
+        try:
+            t = N.make_tables(*cfg)
+        finally:
+            N.U4_HANN_PERIODIC = old
+        for inverse in (t.win_inv, np.where(t.frame_diagonal > 0, 1.0 / np.where(t.frame_diagonal > 0, t.frame_diagonal, 1.0), 0.0)):
+            c = CQT(*cfg)
+            c.load_state_dict({'windows': torch.from_numpy(t.win).float(), 'windows_range_indices': torch.from_numpy(t.idx),
+                               'windows_inverse': torch.from_numpy(inverse).float()})
+            b = c._bank
+            assert b.source == 'checkpoint buffers' and list(c.state_dict()) == []
+            # expand the packed tables again: they must reproduce the dense ones
+            for k in range(0, t.n_bins, 5):
+                dense_w, dense_d = np.zeros(t.max_window_length), np.zeros(t.max_window_length)
+                sl = slice(b.first[k], b.first[k] + b.length[k])
+                dense_w[sl] = b.win[b.offset[k]:b.offset[k + 1]]
+                dense_d[sl] = b.dual[b.offset[k]:b.offset[k + 1]]
+                assert np.abs(dense_w - t.win[k]).max() < 1e-7 and np.abs(dense_d - t.win_inv[k]).max() <= 1e-6 * t.win_inv.max()
+                assert b.start[k] == t.idx[k, b.first[k]]
+    # incomplete / placeholder buffers keep the constructed tables; a wrong geometry is an error, not a silent fallback
+    c = CQT(*cfg)
+    c.load_state_dict({'windows': torch.zeros(72, 256)})
+    assert c._bank.source.startswith('constructor')
+    with pytest.raises(ValueError):
+        c.load_state_dict({'windows': torch.ones(72, 128), 'windows_range_indices': torch.zeros(72, 128, dtype=torch.long),
+                           'windows_inverse': torch.ones(72, 128)})
+    with pytest.raises(ValueError):
+        FilterBank.from_buffers(4000, np.ones((2, 8)), np.stack([np.arange(8) * 2, np.arange(8)]), np.ones((2, 8)))   # taps not consecutive
+
+
+def test_unsupported_channel_plans_fail_at_construction():
+    from timbre_trap_b200.framework import Decoder, Encoder, TimbreTrap
+    for cls in (Encoder, Decoder):
+        with pytest.raises(ValueError, match='model_complexity 1 and 2'):
+            cls(feature_size=540, latent_size=None, model_complexity=3)
+    with pytest.raises(ValueError):
+        TimbreTrap(22050, 9, 60, 3, model_complexity=3)
+    TimbreTrap(22050, 9, 60, 3, model_complexity=1)
+    TimbreTrap(22050, 9, 60, 3, latent_size=128, model_complexity=2)
+
+
 def test_cpu_tensors_are_rejected_loudly():
     from timbre_trap_b200._lib import TimbreTrapB200Error
     from timbre_trap_b200.framework import TimbreTrap

@@ -95,7 +95,13 @@ def _clip_worker(rank, world, port, out_dir):
     local = R.chunked_inference_ref(sub, sd, cqt, True, prepadded=True)             # (1, 2, F, (b1 - b0) * M)
     whole = R.chunked_inference_ref(audio, sd, cqt, True)
     err_local = float((local - whole[..., b0 * M: b1 * M]).abs().max())
-    gathered = _gather_frames(local.contiguous(), -1, M, audio, L, dist.group.WORLD, world)
+    # the product resolves `group=None` to the default process group under torch.distributed (a call that shards by the
+    # default group's ranks must gather over the same ranks)
+    from timbre_trap_b200.framework.modules import _resolve_group
+    group, r_, w_ = _resolve_group(None)
+    assert group is dist.group.WORLD and (r_, w_) == (rank, world)
+    assert _resolve_group(None, 1, 3) == (None, 1, 3)                  # explicit rank / world: emulation, no collective
+    gathered = _gather_frames(local.contiguous(), -1, M, audio, L, group, w_)
     err_gather = float((gathered - whole).abs().max()) if gathered.shape == whole.shape else 1e9
     np.save(os.path.join(out_dir, f'cerr{rank}.npy'), np.array([err_local, err_gather, b1 - b0]))
     dist.destroy_process_group()

@@ -7,15 +7,29 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+def _selftest_lib():
+    """tests/csrc/libtt_selftest.so - built by __graft_entry__.build(); test infrastructure, not in the product ABI."""
+    import os
+    from timbre_trap_b200 import build
+    path = build.SELFTEST_OUT
+    if not os.path.exists(path):
+        build.build_selftest()
+    lib = ctypes.CDLL(path)
+    lib.tt_umma_probe.restype = ctypes.c_int
+    lib.tt_umma_probe.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
+    lib.tt_selftest_last_error.restype = ctypes.c_char_p
+    return lib
+
+
 def _run(n, k, swap):
-    from timbre_trap_b200 import _lib
+    lib = _selftest_lib()
     g = torch.Generator(device='cuda').manual_seed(n * 1000 + k)
     a = torch.randn((128, k), device='cuda', generator=g).bfloat16()
     b = torch.randn((n, k), device='cuda', generator=g).bfloat16()
     d = torch.full((128, n), float('nan'), device='cuda')
-    _lib.check(_lib.lib().tt_umma_probe(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
-                                        ctypes.c_void_p(d.data_ptr()), n, k, swap,
-                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    rc = lib.tt_umma_probe(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()), ctypes.c_void_p(d.data_ptr()), n, k, swap,
+                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert rc == 0, lib.tt_selftest_last_error()
     torch.cuda.synchronize()
     want = a.float() @ b.float().t()
     return float((d - want).abs().max()), float(want.abs().max())

@@ -31,13 +31,11 @@ SIGNATURES = {
     'tt_scale_by_peak': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'tt_magnitude': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'tt_chunk_crossfade': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    'tt_res_block': (c_int, [c_void_p] * 6 + [c_int] * 5 + [c_void_p]),
     'tt_res_block_rs': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    'tt_set_strip_rows': (c_int, [c_int]),
     'tt_conv_down_strip': (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
     'tt_conv_up_strip': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     'tt_conv_same': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
-    'tt_conv_down': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
-    'tt_conv_up': (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     'tt_conv_lat': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'tt_deconv_in': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'tt_conv_in': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
@@ -55,7 +53,6 @@ SIGNATURES = {
     'tt_activations_bwd': (c_int, [c_void_p] * 3 + [c_int64, c_void_p]),
     'tt_grad_sumsq': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'tt_adamw_step': (c_int, [c_void_p] * 4 + [c_int64, c_void_p] + [ctypes.c_float] * 6 + [c_int, c_void_p]),
-    'tt_umma_probe': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'tt_to_decibels': (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     'tt_filter_non_peaks': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     'tt_peak_threshold': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, ctypes.c_float, c_int, c_int, c_int, c_void_p]),

@@ -48,5 +48,20 @@ def build(force=False, verbose=False):
     return OUT
 
 
+SELFTEST_SRC = os.path.join(HERE, '..', 'tests', 'csrc', 'umma_probe.cu')
+SELFTEST_OUT = os.path.join(HERE, '..', 'tests', 'csrc', 'libtt_selftest.so')
+
+
+def build_selftest(force=False):
+    """tests/csrc/libtt_selftest.so: the tcgen05 / TMEM plumbing self-test (test infrastructure, not part of the product ABI)."""
+    deps = [SELFTEST_SRC] + glob.glob(os.path.join(CSRC, '*.cuh'))
+    if not force and os.path.exists(SELFTEST_OUT) and all(os.path.getmtime(d) <= os.path.getmtime(SELFTEST_OUT) for d in deps):
+        return SELFTEST_OUT
+    nvcc = os.environ.get('NVCC', 'nvcc')
+    subprocess.check_call([nvcc] + NVCC_FLAGS + ['-shared', SELFTEST_SRC, '-o', SELFTEST_OUT, '-lcuda'])
+    return SELFTEST_OUT
+
+
 if __name__ == '__main__':
     print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    print(build_selftest(force='--force' in sys.argv))

@@ -8,16 +8,14 @@
 // tile: the im2col matrix is never materialised.  Two core matrices along K (one MMA, K = 16) are either two channel
 // groups of one tap (LBO = plane stride) or, for 8-channel layers, two taps (LBO = their address difference).
 //
-// conv_rows_kernel is the one generic kernel: a CTA owns R "row groups" x 128 pixels; for every row group it issues a
+// conv_rows_kernel is the generic tile kernel: a CTA owns R "row groups" x 128 pixels; for every row group it issues a
 // list of MMAs (tap table from the host) into its own TMEM columns, then an epilogue (bias, ELU, bf16 pack, coalesced
-// 16 B stores).  Optionally a second GEMM stage (the 1x1 conv of a residual block) runs on the bf16 result of the first,
-// staged through shared memory, with the residual add fused in its epilogue.
+// 16 B stores).  It serves the layers below; the residual blocks and the strided / transposed convs of the model run in the
+// row-pipelined kernels of res_rs.cu / updown_strip.cu.
 //
 //   layer (modules.py)                       row group      MMAs / group            N
-//   ResidualConv2dBlock :721-777 (fused)     1 output row   9*C/16 (+1 if C = 8)    C     then 1x1: C/16 (1 if C = 8)
-//   EncoderBlock.sconv  :626-629             1 output row   4*Cin/16                Cout
-//   DecoderBlock.tconv  :685-688             2 output rows  2*Cin/16                2*Cout   (polyphase: rows 2q, 2q+1)
 //   Decoder.convin      :533-536             1 output row   latent/16               C0       (weights depend on the row)
+//   single 3x3 / 1x1 conv (backward pass)    1 output row   9*C/16 (+1 if C = 8)    C
 //
 // Weights arrive pre-packed in the B-operand canonical layout [K/8][N][8] bf16 (timbre_trap_b200/framework/packing.py).
 
@@ -42,8 +40,6 @@ struct ConvRowsParams {
     __nv_bfloat16* y;
     const __nv_bfloat16* w1;
     const float* b1;
-    const __nv_bfloat16* w2;
-    const float* b2;
     int B, CGin, Hin, T, CGout, Hout;
     int groups;            // row groups in total (Hout, or ceil(Hout/2) for out_mode 1)
     int R;                 // row groups per CTA (<= kMaxRows)
@@ -51,13 +47,9 @@ struct ConvRowsParams {
     int row_lo;            // input row held by tile row 0 = g0 * sh + row_lo
     int in_rows;           // tile rows
     int padT;              // T halo on each side
-    int n_mma1, kg1;       // stage-1 MMAs per group, K groups of 8 in the packed weights
-    int n_mma2, kg2;       // stage 2 (1x1): MMAs per group, K groups in the packed weights
-    int mid_planes;        // channel-group planes of the staged intermediate (1 when C = 8: its pair partner is the next row)
+    int n_mma1, kg1;       // MMAs per group, K groups of 8 in the packed weights
     int out_mode;          // 0: N channels -> one output row;  1: two output rows of N/2 channels
-    int act;               // ELU on the final output
-    int two_stage;
-    int res_off;           // byte offset of the residual pixel 0 (plane 0) from the group's tile base
+    int act;               // ELU on the output
     int w_group_stride;    // bytes between the packed weights of consecutive row groups (0: shared)
     int b_group_stride;    // floats between the biases of consecutive row groups (0: shared)
     uint32_t tap_off[kMaxTaps];
@@ -91,15 +83,13 @@ __device__ __forceinline__ void unpack8(uint4 r, float* v) {
 
 constexpr int kConvThreads = 512;   // 16 warps: warp w owns TMEM lane quadrant w % 4 and row groups (w / 4) mod 4
 
-template <int N1, int N2>
+template <int N1>
 __global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_constant__ ConvRowsParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int NC = N1 > N2 ? N1 : N2;           // TMEM columns per row group
+    constexpr int NC = N1;                          // TMEM columns per row group
     uint64_t* bar1 = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* bar2 = bar1 + kMaxRows;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 256);
     float* sB1 = reinterpret_cast<float*>(smem + 512);
-    float* sB2 = reinterpret_cast<float*>(smem + 1280);
 
     constexpr int NT = kConvThreads, NW = NT / 32, NWG = NW / 4;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -114,22 +104,15 @@ __global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_co
     const uint32_t row_bytes = (uint32_t)TW * 16u;
     const uint32_t plane_bytes = (uint32_t)p.in_rows * row_bytes;
     const uint32_t w1_bytes = (uint32_t)p.kg1 * N1 * 16u;
-    const uint32_t w2_bytes = p.two_stage ? (uint32_t)p.kg2 * N2 * 16u : 0u;
-    const uint32_t mid_plane = (uint32_t)(p.R + 1) * 2048u;
     uint8_t* sW1 = smem + kHeaderBytes;
-    uint8_t* sW2 = sW1 + (size_t)w1_bytes * wrows;
-    uint8_t* sIn = sW2 + w2_bytes;
-    uint8_t* sMid = sIn + (size_t)p.CGin * plane_bytes + 256;
+    uint8_t* sIn = sW1 + (size_t)w1_bytes * wrows;
 
     // ---- setup --------------------------------------------------------------------------------------
     uint32_t ncols = 32;
     while (ncols < (uint32_t)(p.R * NC)) ncols <<= 1;
     if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
     if (tid == 0) {
-        for (int i = 0; i < kMaxRows; ++i) {
-            umma::mbar_init(&bar1[i], 1);
-            umma::mbar_init(&bar2[i], 1);
-        }
+        for (int i = 0; i < kMaxRows; ++i) umma::mbar_init(&bar1[i], 1);
         umma::mbar_fence_init();
     }
     // weights and biases
@@ -140,11 +123,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_co
             for (int i = tid; i < (int)(w1_bytes / 16); i += NT)
                 umma::cp_async16(reinterpret_cast<uint4*>(sW1 + (size_t)r * w1_bytes) + i, src + i, 16u);
     }
-    if (p.two_stage)
-        for (int i = tid; i < (int)(w2_bytes / 16); i += NT)
-            umma::cp_async16(reinterpret_cast<uint4*>(sW2) + i, reinterpret_cast<const uint4*>(p.w2) + i, 16u);
     if (p.b_group_stride == 0 && tid < N1) sB1[tid] = p.b1[tid];
-    if (N2 > 0 && p.two_stage && tid < N2) sB2[tid] = p.b2[tid];
 
     // input tile, zero-filled outside the image ('same' padding, transposed-conv borders)
     {
@@ -163,13 +142,6 @@ __global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_co
             }
         }
         if (tid < 16) reinterpret_cast<uint4*>(sIn + (size_t)p.CGin * plane_bytes)[tid] = make_uint4(0u, 0u, 0u, 0u);
-        if (p.two_stage) {
-            // when C = 8 an MMA pairs mid row i with row i + 1 (times zero weights): the row after the last one this
-            // CTA produces must hold finite values, not stale shared memory
-            const int planes = p.mid_planes;
-            for (int i = tid; i < planes * 128; i += NT)
-                reinterpret_cast<uint4*>(sMid + (size_t)(i / 128) * mid_plane + (size_t)rows * 2048u)[i % 128] = make_uint4(0u, 0u, 0u, 0u);
-        }
     }
     umma::cp_async_wait_all();
     umma::fence_proxy_async();
@@ -178,7 +150,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_co
     umma::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
 
-    // ---- stage 1: all MMAs of all row groups, one commit per group -------------------------------------
+    // ---- all MMAs of all row groups, one commit per group -------------------------------------
     if (tid == 0) {
         const uint32_t idesc = umma::make_idesc_bf16(128, N1);
         const uint32_t in0 = umma::smem_u32(sIn), w0 = umma::smem_u32(sW1);
@@ -198,7 +170,7 @@ __global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_co
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
     const bool t_ok = t0 + j < p.T;
 
-    // ---- epilogue 1 ------------------------------------------------------------------------------------
+    // ---- epilogue ------------------------------------------------------------------------------------
     for (int i = wg; i < rows; i += NWG) {
         umma::mbar_wait(&bar1[i], 0);
         umma::fence_after_sync();
@@ -210,72 +182,19 @@ __global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_co
             umma::tmem_ld_wait();
 #pragma unroll
             for (int k = 0; k < 16; ++k) v[k] += bias[c0 + k];
-            if (p.two_stage) {
+            if (p.act) {
 #pragma unroll
                 for (int k = 0; k < 16; ++k) v[k] = elu(v[k]);
-                uint8_t* dst = sMid + (size_t)(c0 / 8) * mid_plane + (size_t)i * 2048u + (size_t)j * 16u;
-                *reinterpret_cast<uint4*>(dst) = pack8(v);
-                if (c0 / 8 + 1 < p.mid_planes) *reinterpret_cast<uint4*>(dst + mid_plane) = pack8(v + 8);
-            } else {
-                if (p.act) {
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) v[k] = elu(v[k]);
-                }
-                if (t_ok) {
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int c = c0 + 8 * hh;          // first of 8 channels
-                        int ho, cg;
-                        if (p.out_mode == 0) { ho = g0 + i; cg = c >> 3; }
-                        else { ho = 2 * (g0 + i) + (c >= N1 / 2 ? 1 : 0); cg = (c % (N1 / 2)) >> 3; }
-                        if (cg < p.CGout && ho < p.Hout)
-                            reinterpret_cast<uint4*>(p.y)[(((size_t)b * p.CGout + cg) * p.Hout + ho) * p.T + t0 + j] = pack8(v + 8 * hh);
-                    }
-                }
             }
-        }
-    }
-
-    // ---- stage 2: 1x1 conv on the staged bf16 activations + residual ------------------------------------
-    if constexpr (N2 > 0) {
-        if (p.two_stage) {
-            umma::fence_proxy_async();
-            umma::fence_before_sync();
-            __syncthreads();
-            umma::fence_after_sync();
-            if (tid == 0) {
-                const uint32_t idesc = umma::make_idesc_bf16(128, N2);
-                const uint32_t m0 = umma::smem_u32(sMid), w0 = umma::smem_u32(sW2);
-                const uint32_t lbo = p.mid_planes < 2 ? 2048u : mid_plane;
-                for (int i = 0; i < rows; ++i) {
-                    for (int m = 0; m < p.n_mma2; ++m) {
-                        const uint64_t da = umma::make_desc(m0 + (uint32_t)i * 2048u + (uint32_t)m * 2u * mid_plane, lbo, 128u);
-                        const uint64_t db = umma::make_desc(w0 + (uint32_t)m * 2u * N2 * 16u, N2 * 16u, 128u);
-                        umma::mma_bf16(tmem + (uint32_t)(i * NC), da, db, idesc, m > 0);
-                    }
-                    umma::commit(&bar2[i]);
-                }
-            }
-            for (int i = wg; i < rows; i += NWG) {
-                umma::mbar_wait(&bar2[i], 0);
-                umma::fence_after_sync();
-                const uint8_t* res = sIn + (size_t)(i * p.sh) * row_bytes + p.res_off + (size_t)j * 16u;
+            if (t_ok) {
 #pragma unroll
-                for (int c0 = 0; c0 < N2; c0 += 16) {
-                    float v[16];
-                    umma::tmem_ld16(lane_addr + (uint32_t)(i * NC + c0), v);
-                    umma::tmem_ld_wait();
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const int cg = (c0 >> 3) + hh;
-                        if (cg >= p.CGout) continue;
-                        float r[8];
-                        unpack8(*reinterpret_cast<const uint4*>(res + (size_t)cg * plane_bytes), r);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) r[k] += elu(v[8 * hh + k] + sB2[c0 + 8 * hh + k]);
-                        if (t_ok)
-                            reinterpret_cast<uint4*>(p.y)[(((size_t)b * p.CGout + cg) * p.Hout + g0 + i) * p.T + t0 + j] = pack8(r);
-                    }
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int c = c0 + 8 * hh;          // first of 8 channels
+                    int ho, cg;
+                    if (p.out_mode == 0) { ho = g0 + i; cg = c >> 3; }
+                    else { ho = 2 * (g0 + i) + (c >= N1 / 2 ? 1 : 0); cg = (c % (N1 / 2)) >> 3; }
+                    if (cg < p.CGout && ho < p.Hout)
+                        reinterpret_cast<uint4*>(p.y)[(((size_t)b * p.CGout + cg) * p.Hout + ho) * p.T + t0 + j] = pack8(v + 8 * hh);
                 }
             }
         }
@@ -289,35 +208,26 @@ __global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_co
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-static size_t conv_rows_smem(const ConvRowsParams& p, int n1, int n2) {
+static size_t conv_rows_smem(const ConvRowsParams& p, int n1) {
     const size_t TW = kTileT + 2 * p.padT;
     const size_t plane = (size_t)p.in_rows * TW * 16;
-    size_t s = kHeaderBytes + (size_t)p.kg1 * n1 * 16 * (p.w_group_stride ? p.R : 1);
-    if (p.two_stage) s += (size_t)p.kg2 * n2 * 16;
-    s += (size_t)p.CGin * plane + 256;
-    if (p.two_stage) s += (size_t)p.mid_planes * (p.R + 1) * 2048;
-    return s;
+    return kHeaderBytes + (size_t)p.kg1 * n1 * 16 * (p.w_group_stride ? p.R : 1) + (size_t)p.CGin * plane + 256;
 }
 
-template <int N1, int N2>
+template <int N1>
 static int launch_conv_rows(const ConvRowsParams& p, cudaStream_t stream) {
-    const size_t smem = conv_rows_smem(p, N1, N2);
+    const size_t smem = conv_rows_smem(p, N1);
     TT_REQUIRE(smem <= 227 * 1024, "conv tile needs %zu bytes of shared memory", smem);
     static size_t configured = 0;
     if (smem > configured) {
-        TT_CUDA_CHECK(cudaFuncSetAttribute(conv_rows_kernel<N1, N2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TT_CUDA_CHECK(cudaFuncSetAttribute(conv_rows_kernel<N1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     dim3 grid((p.T + kTileT - 1) / kTileT, (p.groups + p.R - 1) / p.R, p.B);
-    conv_rows_kernel<N1, N2><<<grid, kConvThreads, smem, stream>>>(p);
+    conv_rows_kernel<N1><<<grid, kConvThreads, smem, stream>>>(p);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
-}
-
-static int env_int(const char* name, int fallback) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : fallback;
 }
 
 }  // namespace tt
@@ -332,57 +242,14 @@ static void fill_common(ConvRowsParams& p, const void* x, void* y, const void* w
     p.B = B; p.CGin = CGin; p.Hin = Hin; p.T = T; p.CGout = CGout; p.Hout = Hout;
 }
 
-template <int N2>
 static int dispatch_n1(const ConvRowsParams& p, int n1, cudaStream_t s) {
     switch (n1) {
-        case 16: return launch_conv_rows<16, N2>(p, s);
-        case 32: return launch_conv_rows<32, N2>(p, s);
-        case 64: return launch_conv_rows<64, N2>(p, s);
-        case 128: return launch_conv_rows<128, N2>(p, s);
+        case 16: return launch_conv_rows<16>(p, s);
+        case 32: return launch_conv_rows<32>(p, s);
+        case 64: return launch_conv_rows<64>(p, s);
+        case 128: return launch_conv_rows<128>(p, s);
         default: tt_set_error("unsupported GEMM N = %d", n1); return TT_ERR_UNSUPPORTED;
     }
-}
-
-extern "C" int tt_res_block(const void* x, void* y, const void* w1, const float* b1, const void* w2, const float* b2,
-                            int B, int C, int H, int T, int dilation, void* stream) {
-    TT_REQUIRE(x && y && w1 && b1 && w2 && b2, "null argument");
-    TT_REQUIRE(C == 8 || C == 16 || C == 32, "res block: padded channel count must be 8, 16 or 32 (got %d)", C);
-    TT_REQUIRE(dilation >= 1 && dilation <= 4, "dilation must be in [1,4]");
-    if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
-    ConvRowsParams p;
-    const int d = dilation, CG = C / 8;
-    fill_common(p, x, y, w1, b1, B, CG, H, T, CG, H);
-    p.w2 = (const __nv_bfloat16*)w2; p.b2 = b2;
-    p.groups = H;
-    p.R = std::min(env_int("TT_RES_ROWS", C == 8 ? 16 : (C == 16 ? 8 : 4)), kMaxRows);
-    p.sh = 1; p.row_lo = -d; p.in_rows = p.R + 2 * d; p.padT = d;
-    p.out_mode = 0; p.act = 1; p.two_stage = 1;
-    const uint32_t TW = kTileT + 2 * d, row_bytes = TW * 16, plane = (uint32_t)p.in_rows * row_bytes;
-    auto tap_addr = [&](int tap) { return (uint32_t)(((tap / 3) * d) * TW + (tap % 3) * d) * 16u; };
-    p.res_off = (int)tap_addr(4);
-    int m = 0;
-    if (CG == 1) {
-        // K order: tap-major, 8 channels per tap; an MMA pairs two consecutive taps, the 10th K group has zero weights
-        for (int t = 0; t < 10; t += 2) {
-            p.tap_off[m] = tap_addr(t);
-            p.tap_lbo[m] = t + 1 < 9 ? tap_addr(t + 1) - tap_addr(t) : 16u;
-            ++m;
-        }
-        p.kg1 = 10;
-        p.kg2 = 2; p.n_mma2 = 1; p.mid_planes = 1;
-    } else {
-        for (int t = 0; t < 9; ++t)
-            for (int q = 0; q < CG / 2; ++q) {
-                p.tap_off[m] = tap_addr(t) + (uint32_t)(2 * q) * plane;
-                p.tap_lbo[m] = plane;
-                ++m;
-            }
-        p.kg1 = 9 * CG;
-        p.kg2 = CG; p.n_mma2 = CG / 2; p.mid_planes = CG;
-    }
-    p.n_mma1 = m;
-    cudaStream_t s = (cudaStream_t)stream;
-    return C == 32 ? launch_conv_rows<32, 32>(p, s) : launch_conv_rows<16, 16>(p, s);
 }
 
 // A single 3x3 dilated 'same' conv (optionally + ELU) or 1x1 conv on C8 planar tensors through the generic tile kernel: used by
@@ -408,7 +275,7 @@ extern "C" int tt_conv_same(const void* x, void* y, const void* w, const float* 
     p.groups = H;
     p.R = std::min(C == 8 ? 16 : (C == 16 ? 8 : 4), kMaxRows);
     p.sh = 1; p.row_lo = -d; p.in_rows = p.R + 2 * d; p.padT = d;
-    p.out_mode = 0; p.act = act_elu; p.two_stage = 0;
+    p.out_mode = 0; p.act = act_elu;
     const uint32_t TW = kTileT + 2 * d, row_bytes = TW * 16, plane = (uint32_t)p.in_rows * row_bytes;
     int m = 0;
     if (k == 3) {
@@ -430,63 +297,7 @@ extern "C" int tt_conv_same(const void* x, void* y, const void* w, const float* 
         else { for (int q = 0; q < CG / 2; ++q) { p.tap_off[m] = (uint32_t)(2 * q) * plane; p.tap_lbo[m] = plane; ++m; } p.kg1 = CG; }
     }
     p.n_mma1 = m;
-    return dispatch_n1<0>(p, std::max(16, C), (cudaStream_t)stream);
-}
-
-// EncoderBlock.sconv (+ELU): Conv2d(Cin, Cout, (4,1), stride (2,1)).  K order (kh, channel group).
-extern "C" int tt_conv_down(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin, int T,
-                            void* stream) {
-    TT_REQUIRE(x && y && w && bias, "null argument");
-    TT_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin >= 8 && Cin <= 64, "conv_down: padded channels must be multiples of 8");
-    if (B <= 0 || T <= 0) return TT_OK;
-    const int Hout = (Hin - 4) / 2 + 1;
-    TT_REQUIRE(Hout >= 1, "conv_down: input too short");
-    ConvRowsParams p;
-    const int CG = Cin / 8;
-    fill_common(p, x, y, w, bias, B, CG, Hin, T, Cout / 8, Hout);
-    p.groups = Hout;
-    p.R = std::min(env_int("TT_DOWN_ROWS", Cin >= 32 ? 4 : 8), kMaxRows);
-    p.sh = 2; p.row_lo = 0; p.in_rows = (p.R - 1) * 2 + 4; p.padT = 0;
-    p.out_mode = 0; p.act = 1;
-    const uint32_t row_bytes = kTileT * 16, plane = (uint32_t)p.in_rows * row_bytes;
-    int m = 0;
-    if (CG == 1) {
-        for (int kh = 0; kh < 4; kh += 2) { p.tap_off[m] = kh * row_bytes; p.tap_lbo[m] = row_bytes; ++m; }
-    } else {
-        for (int kh = 0; kh < 4; ++kh)
-            for (int q = 0; q < CG / 2; ++q) { p.tap_off[m] = kh * row_bytes + 2 * q * plane; p.tap_lbo[m] = plane; ++m; }
-    }
-    p.n_mma1 = m; p.kg1 = 4 * CG;
-    const int n1 = std::max(16, Cout);
-    return dispatch_n1<0>(p, n1, (cudaStream_t)stream);
-}
-
-// DecoderBlock.tconv (+ELU): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding (op,0)), polyphase:
-//   out[2q + r] = bias + W[.,.,r+2] x[q-1] + W[.,.,r] x[q];  K order (a' in {row q-1, row q}, channel group), N = (r, co).
-extern "C" int tt_conv_up(const void* x, void* y, const void* w, const float* bias, int B, int Cin, int Cout, int Hin,
-                          int out_pad, int T, void* stream) {
-    TT_REQUIRE(x && y && w && bias, "null argument");
-    TT_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0 && Cin >= 8 && Cin <= 64, "conv_up: padded channels must be multiples of 8");
-    if (B <= 0 || T <= 0 || Hin <= 0) return TT_OK;
-    const int Hout = 2 * Hin + 2 + out_pad;
-    ConvRowsParams p;
-    const int CG = Cin / 8;
-    fill_common(p, x, y, w, bias, B, CG, Hin, T, Cout / 8, Hout);
-    p.groups = (Hout + 1) / 2;
-    p.R = std::min(env_int("TT_UP_ROWS", Cin >= 64 ? 4 : 8), kMaxRows);
-    p.sh = 1; p.row_lo = -1; p.in_rows = p.R + 1; p.padT = 0;
-    p.out_mode = 1; p.act = 1;
-    const uint32_t row_bytes = kTileT * 16, plane = (uint32_t)p.in_rows * row_bytes;
-    int m = 0;
-    if (CG == 1) {
-        p.tap_off[m] = 0; p.tap_lbo[m] = row_bytes; ++m;
-    } else {
-        for (int a = 0; a < 2; ++a)
-            for (int q = 0; q < CG / 2; ++q) { p.tap_off[m] = a * row_bytes + 2 * q * plane; p.tap_lbo[m] = plane; ++m; }
-    }
-    p.n_mma1 = m; p.kg1 = 2 * CG;
-    const int n1 = std::max(16, 2 * Cout);
-    return dispatch_n1<0>(p, n1, (cudaStream_t)stream);
+    return dispatch_n1(p, std::max(16, C), (cudaStream_t)stream);
 }
 
 // Decoder.convin (+ELU): ConvTranspose2d(latent+1, C0, (H0,1)) on a height-1 input = one GEMM per output row h with
@@ -501,7 +312,7 @@ extern "C" int tt_deconv_in(const void* lat, void* y, const void* w, const float
     const int CG = Clat / 8;
     fill_common(p, lat, y, w, bias, B, CG, 1, T, C0 / 8, H0);
     p.groups = H0;
-    p.R = std::min(env_int("TT_DECIN_ROWS", 4), kMaxRows);
+    p.R = 4;
     p.sh = 0; p.row_lo = 0; p.in_rows = 1; p.padT = 0;
     p.out_mode = 0; p.act = 1;
     const uint32_t plane = kTileT * 16;
@@ -510,7 +321,7 @@ extern "C" int tt_deconv_in(const void* lat, void* y, const void* w, const float
     p.n_mma1 = m; p.kg1 = CG;
     p.w_group_stride = CG * C0 * 16;
     p.b_group_stride = C0;
-    return dispatch_n1<0>(p, C0, (cudaStream_t)stream);
+    return dispatch_n1(p, C0, (cudaStream_t)stream);
 }
 
 // =========================================================================================================

@@ -28,6 +28,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <type_traits>
 
 #include "../../include/timbre_trap_b200.h"
@@ -496,9 +497,18 @@ static int launch_rs_d(const void* x, const ResRsParams& p, int dilation, cudaSt
     return launch_rs<CG, NREAL, 3, MODE>(x, p, stream);
 }
 
+static std::atomic<int> g_strip_rows{0};
+int strip_rows_override() { return g_strip_rows.load(std::memory_order_relaxed); }
+
 }  // namespace tt
 
 using namespace tt;
+
+extern "C" int tt_set_strip_rows(int rows) {
+    TT_REQUIRE(rows >= 0, "rows must be >= 0 (0 = automatic)");
+    g_strip_rows.store(rows, std::memory_order_relaxed);
+    return TT_OK;
+}
 
 extern "C" int tt_res_block_rs(const void* x, void* y, const void* w1, const void* w2, const float* bias, int B, int C, int c_real,
                                int H, int T, int dilation, int layout, void* stream) {
@@ -527,8 +537,7 @@ extern "C" int tt_res_block_rs(const void* x, void* y, const void* w1, const voi
         const int splits = (int)std::min<long long>((target + tiles - 1) / tiles, std::max(1, H / 32));
         rows = (H + splits - 1) / splits;
     }
-    const char* env = getenv("TT_STRIP_ROWS");
-    if (env) rows = std::max(1, atoi(env));
+    if (strip_rows_override() > 0) rows = strip_rows_override();
     p.rows_per_strip = std::min(rows, H);
     cudaStream_t s = (cudaStream_t)stream;
     if (layout == kRsFold4) return launch_rs_d<2, 16, kRsFold4>(x, p, dilation, s);

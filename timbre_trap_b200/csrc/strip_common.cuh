@@ -11,6 +11,9 @@ namespace tt {
 
 constexpr int kStripTileT = 128;   // frames per strip = M of one tcgen05.mma
 
+// rows (row groups) per strip forced by tt_set_strip_rows(); 0 = the automatic split (defined in res_rs.cu)
+int strip_rows_override();
+
 // ---- extra PTX: TMA tile load, mbarrier arrive variants ---------------------------------------------------------
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(umma::smem_u32(bar)), "r"(bytes) : "memory");

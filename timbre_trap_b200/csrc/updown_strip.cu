@@ -234,8 +234,7 @@ static int strip_groups(int B, int T, int groups) {
         const int splits = (int)std::min<long long>((target + tiles - 1) / tiles, std::max(1, groups / 16));
         per = (groups + splits - 1) / splits;
     }
-    const char* env = getenv("TT_STRIP_ROWS");
-    if (env) per = std::max(1, atoi(env));
+    if (strip_rows_override() > 0) per = strip_rows_override();
     return std::min(per, groups);
 }
 

@@ -85,12 +85,41 @@ class CQT(torch.nn.Module):
             self._plans[key] = _Plan(self._bank, device, self.BLOCKS_PER_LAUNCH)
         return self._plans[key]
 
+    # the buffers cqt_pytorch.CQT registers, as reference checkpoints carry them under `sliCQ.`
+    CHECKPOINT_BUFFERS = ('windows', 'windows_range_indices', 'windows_inverse')
+
     def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
-        # checkpoints of the reference carry cqt_pytorch's buffers (windows, indices); the tables are
-        # rebuilt from the constructor arguments here, so those entries are accepted and dropped.
+        # A checkpoint of the reference carries cqt_pytorch's tables.  When all three are present the kernels are driven by
+        # THEM (the transform the weights were trained with); otherwise the tables built from the constructor arguments stay.
+        # Either way the entries are consumed here: this module has no parameters or buffers of its own.
+        found = {name: state_dict[prefix + name] for name in self.CHECKPOINT_BUFFERS if prefix + name in state_dict}
         for key in [k for k in state_dict if k.startswith(prefix)]:
             state_dict.pop(key)
+        if len(found) == len(self.CHECKPOINT_BUFFERS):
+            w = found['windows']
+            if tuple(w.shape) != (self.n_bins, self.max_window_length):
+                raise ValueError(f'checkpoint {prefix}windows {tuple(w.shape)} does not fit this CQT '
+                                 f'({self.n_bins} bins, max_window_length {self.max_window_length})')
+            if bool(torch.count_nonzero(w)):        # all-zero placeholders: keep the constructed tables
+                self.set_filter_bank(FilterBank.from_buffers(self.block_length, w.detach().cpu().numpy(),
+                                                             found['windows_range_indices'].detach().cpu().numpy(),
+                                                             found['windows_inverse'].detach().cpu().numpy()))
         super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
+    def set_filter_bank(self, bank):
+        """Drive the kernels with other tables (same geometry): drops the device plans, which are rebuilt on next use."""
+        if (bank.n_bins, bank.block_length, bank.max_window_length) != (self.n_bins, self.block_length, self.max_window_length):
+            raise ValueError('filter bank geometry differs from this CQT')
+        self._bank = bank
+        self._plans = {}
+
+    def __getstate__(self):
+        # plans hold raw device handles (ctypes pointers cannot be pickled, and a copied handle would be freed twice):
+        # torch.save(model) / copy.deepcopy(model), which the reference's training loop relies on (experiments/train.py:511),
+        # carry the host tables only; plans are rebuilt lazily on the first call on a device.
+        state = self.__dict__.copy()
+        state['_plans'] = {}
+        return state
 
     def _interleaved(self, coefficients):
         """(B, 2, F, T) real in any layout -> the (B, F, T, 2) contiguous buffer behind it (copy only if needed)."""

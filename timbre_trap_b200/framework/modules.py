@@ -32,6 +32,11 @@ class _PackedCache:
         self._key = None
         self._val = None
 
+    def __getstate__(self):
+        # pickling / deep-copying a module (the reference checkpoints whole modules, experiments/train.py:511) drops the packed
+        # copies: they are rebuilt lazily from the parameters of the new object
+        return dict(_key=None, _val=None)
+
     def get(self, params, build):
         key = (_PackedCache.epoch,) + tuple((p.data_ptr(), p._version, p.device) for p in params)
         if key != self._key:
@@ -168,6 +173,15 @@ def _channels(model_complexity):
     return tuple(round(c * 2 ** (model_complexity - 1)) for c in (2, 4, 8, 16, 32))
 
 
+def _check_channel_plan(channels):
+    """The residual-block kernels exist for 8 / 16 / 32 padded channels (csrc/res_rs.cu): model_complexity 1 and 2 (the reference's
+    base model, experiments/train.py:98).  Anything wider is rejected here, at construction, not at the first forward."""
+    widest_res = max(channels[:4])
+    if channels[0] > 8 or widest_res > 32 or max(channels) % 16:
+        raise ValueError(f'timbre_trap_b200 supports model_complexity 1 and 2 (residual stages of at most 32 channels); the channel '
+                         f'plan {tuple(channels)} has a {widest_res}-channel residual stage')
+
+
 class Encoder(nn.Module):
     """modules.py:396-483."""
 
@@ -176,8 +190,7 @@ class Encoder(nn.Module):
         channels = _channels(model_complexity)
         if latent_size is None:
             latent_size = 32 * 2 ** (model_complexity - 1)
-        if channels[0] > 8 or channels[4] % 16:
-            raise ValueError('timbre_trap_b200 supports model_complexity 1..3 channel plans (first stage <= 8 channels)')
+        _check_channel_plan(channels)
         self.convin = nn.Sequential(nn.Conv2d(2, channels[0], kernel_size=3, padding='same'), nn.ELU(inplace=True))
         self.block1 = EncoderBlock(channels[0], channels[1], stride=2)
         self.block2 = EncoderBlock(channels[1], channels[2], stride=2)
@@ -225,6 +238,7 @@ class Decoder(nn.Module):
     def __init__(self, feature_size, latent_size=None, model_complexity=1):
         super().__init__()
         channels = _channels(model_complexity)[::-1]
+        _check_channel_plan(channels[::-1])
         if latent_size is None:
             latent_size = 32 * 2 ** (model_complexity - 1)
         padding = []
@@ -319,11 +333,20 @@ def shard_audio(padded, block_length, rank, world):
     return haloed[..., b0 * L: b1 * L + 2 * hop], b0, b1
 
 
-def _rank_world(group, rank, world):
-    if rank is None or world is None:
-        import torch.distributed as dist
-        rank, world = dist.get_rank(group), dist.get_world_size(group)
-    return rank, world
+def _resolve_group(group, rank=None, world=None):
+    """(group, rank, world) of a sharded call.  With explicit `rank` / `world` and no group the caller emulates the ranks one after
+    the other (no collective).  Otherwise the ranks are those of `group`, or of the DEFAULT process group when torch.distributed is
+    initialised - so that `model.transcribe_sharded(audio)` under torchrun shards AND gathers over the same ranks."""
+    if rank is not None and world is not None:
+        return group, rank, world
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        if group is not None:
+            raise ValueError('a process group was passed but torch.distributed is not initialised')
+        return None, 0, 1
+    if group is None:
+        group = dist.group.WORLD
+    return group, dist.get_rank(group), dist.get_world_size(group)
 
 
 def _gather_frames(local, dim, per_block, audio, block_length, group, world):
@@ -357,6 +380,12 @@ class TimbreTrap(nn.Module):
         self.decoder = Decoder(feature_size=self.sliCQ.n_bins, latent_size=latent_size, model_complexity=model_complexity)
         self.skip_weights = torch.nn.Parameter(torch.ones(5)) if skip_connections else None
         self._windows = {}
+        self._warned_local_peak = False
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['_windows'] = {}                     # per-device Hann windows are rebuilt on demand
+        return state
 
     # ---- C8 fast paths -----------------------------------------------------------------------------
     def _skips_c8(self, emb):
@@ -478,6 +507,13 @@ class TimbreTrap(nn.Module):
         over the ranks of `group`: one scalar MAX all-reduce of the per-rank peaks, then a local scale.
         """
         if group is None:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1 and not self._warned_local_peak:
+                # the caller shards the batch by hand but asks for a rank-local normalise: legal (independent clips), but say so once
+                import warnings
+                warnings.warn('reconstruct(group=None) under torch.distributed normalises by the LOCAL peak of this rank; pass '
+                              'group=... for the reference\'s global peak (cqtwrapper.py:209-211) over a sharded batch')
+                self._warned_local_peak = True
             return self.sliCQ.decode(coefficients)
         import torch.distributed as dist
         audio, peak = self.sliCQ.decode_raw(coefficients, normalise=False)
@@ -507,7 +543,7 @@ class TimbreTrap(nn.Module):
     def transcribe_sharded(self, audio, group=None, rank=None, world=None, gather=True):
         """transcribe() of a clip every rank holds, each rank computing a contiguous range of blocks.  Returns the whole
         (B, F, T) activations on every rank (gather=True, via all_gather over `group`) or the rank's own frames."""
-        rank, world = _rank_world(group, rank, world)
+        group, rank, world = _resolve_group(group, rank, world)
         sub, b0, b1 = self.shard_audio(audio, rank, world)
         M, F = self.sliCQ.max_window_length, self.sliCQ.n_bins
         if b1 > b0:
@@ -519,7 +555,7 @@ class TimbreTrap(nn.Module):
     def reconstruct_sharded(self, audio, group=None, rank=None, world=None, gather=True):
         """reconstruct() of a clip every rank holds, sharded like transcribe_sharded; the reference's global peak normalise
         (cqtwrapper.py:209-211) is one scalar MAX all-reduce over `group`."""
-        rank, world = _rank_world(group, rank, world)
+        group, rank, world = _resolve_group(group, rank, world)
         sub, b0, b1 = self.shard_audio(audio, rank, world)
         L = self.sliCQ.block_length
         if b1 > b0:

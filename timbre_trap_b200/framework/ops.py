@@ -25,33 +25,6 @@ def _check_c8(x, name='x'):
         raise ValueError(f'{name} must be a contiguous C8 planar bf16 tensor (B, CG, H, T, 8), got {tuple(x.shape)} {x.dtype}')
 
 
-def res_block(x, w1, b1, w2, b2, dilation, out=None):
-    _check_c8(x)
-    B, CG, H, T, _ = x.shape
-    y = torch.empty_like(x) if out is None else out
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_res_block(_p(x), _p(y), _p(w1), _p(b1), _p(w2), _p(b2), B, CG * 8, H, T, dilation, _s(x)))
-    return y
-
-
-def conv_down(x, w, b, cout_pad):
-    _check_c8(x)
-    B, CG, H, T, _ = x.shape
-    y = torch.empty((B, cout_pad // 8, (H - 4) // 2 + 1, T, 8), dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_conv_down(_p(x), _p(y), _p(w), _p(b), B, CG * 8, cout_pad, H, T, _s(x)))
-    return y
-
-
-def conv_up(x, w, b, cout_pad, out_pad):
-    _check_c8(x)
-    B, CG, H, T, _ = x.shape
-    y = torch.empty((B, cout_pad // 8, 2 * H + 2 + out_pad, T, 8), dtype=torch.bfloat16, device=x.device)
-    with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_conv_up(_p(x), _p(y), _p(w), _p(b), B, CG * 8, cout_pad, H, out_pad, T, _s(x)))
-    return y
-
-
 def conv_lat(x, w, b, latent_pad):
     _check_c8(x)
     B, CG, H, T, _ = x.shape
