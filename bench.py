@@ -111,21 +111,29 @@ WORKLOAD = ('BASELINE.json configs[2]: transcribe+reconstruct, 256 x 3 s blocks 
             '(9 oct x 60 bpo, 22.05 kHz, latent 128, complexity 2), random init')
 
 
+CPU_BLOCKS = 8        # blocks per CPU step: the reference's chunk loop runs the whole batch through each chunk position
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2])
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     state = cpu_state()
-    n_blocks = 1                              # bounded sample: one 3 s block per step (= BASELINE.json configs[0])
+    n_blocks = CPU_BLOCKS                     # bounded sample of the 256-block batch: 8 blocks per step, all host threads
     for _ in range(max(1, min(args.warmup, 1))):
         cpu_reference_step(state, n_blocks)
     times = [cpu_reference_step(state, n_blocks) for _ in range(args.steps)]
-    per_step = sum(times) / len(times)
+    per_step = median(times)                  # median of >= 5 runs after one warm-up
     value = n_blocks * SECS / per_step
     cores = torch.get_num_threads()
     line = dict(metric=METRIC, value=value, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=per_step * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload=WORKLOAD, sample=f'bounded sample of that workload: {n_blocks} x 3 s block per step on the host CPU '
-                                                      '(the reference\'s sequential chunk loop)'),
+                config=dict(workload=WORKLOAD, sample=f'bounded sample of that workload: a batch of {n_blocks} x 3 s blocks per step on the host '
+                                                      'CPU (the reference\'s sequential chunk loop over the batch), median step time'),
                 cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='port',
                                   sample=f'{args.steps} steps x {n_blocks} block(s) of 3 s; oracle/model_ref.py + oracle/nsgt_ref.py (the reference is '
                                          'pure Python with an un-vendored CQT dependency; /root/reference is absent on the GPU box)'),
@@ -149,10 +157,96 @@ def time_kernel(fn, iters, warm=3):
     return a.elapsed_time(b) / iters          # ms
 
 
+def synthetic_targets(n_items, n_frames, seed):
+    """Multi-pitch targets in the manner of PitchDataset.multi_pitch_to_activations (datasets/PitchDataset.py:233-307): exact 1.0
+    at a few bins per frame held for >= 50 frames, Gaussian-blurred neighbours (sigma = 1 bin), clipped to [0, 1]."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    gt = np.zeros((n_items, F, n_frames), dtype=np.float32)
+    blur = np.exp(-0.5 * np.arange(-3, 4) ** 2)
+    for b in range(n_items):
+        t = 0
+        while t < n_frames:
+            hold = int(rng.integers(50, 400))
+            for k in rng.integers(30, F - 30, size=int(rng.integers(1, 7))):
+                for o, g in zip(range(-3, 4), blur):
+                    gt[b, k + o, t:t + hold] = np.maximum(gt[b, k + o, t:t + hold], g)
+            t += hold
+    return torch.from_numpy(gt)
+
+
+class EagerGpuReference:
+    """
+    DIAGNOSTIC ANCHOR ONLY (what the reference's own code does when it is given a GPU): the oracle's functional
+    restatement of the reference model (oracle/model_ref.py: F.conv2d / F.conv_transpose2d / F.elu = cuDNN + ATen) under bf16
+    autocast, with the NSGT as torch.fft calls (cuFFT) on the oracle's tables, run as the reference runs it - model.transcribe(audio)
+    then model.reconstruct(audio), each a sequential loop over the chunk positions with the whole batch per iteration
+    (modules.py:247-263).  Never on the product path; bench.py only.
+    """
+
+    def __init__(self, device):
+        from oracle import model_ref as R
+        self.R = R
+        self.device = device
+        cq = R.CQTRef(N_OCT, BPO, SR, SECS)
+        t = cq.nsgt.tables
+        self.block_length, self.max_window_length, self.n_bins = cq.block_length, cq.max_window_length, cq.n_bins
+        self.idx = torch.from_numpy(t.idx).to(device)
+        self.win = torch.from_numpy(t.win).float().to(device)
+        self.win_inv = torch.from_numpy(t.win_inv).float().to(device)
+        self.sd = {k: v.to(device) for k, v in R.init_state_dict(F, LATENT, COMPLEXITY, seed=0).items()}
+        self.to_magnitude = R.CQTRef.to_magnitude
+
+    def pad_to_block_length(self, audio):
+        return torch.nn.functional.pad(audio, (0, -audio.size(-1) % self.block_length))
+
+    def get_expected_frames(self, n):
+        import math
+        return math.ceil((n / self.block_length) * self.max_window_length)
+
+    def __call__(self, audio):                   # CQT.forward: (B, 1, n L) -> (B, 2, F, n M)
+        B, _, N = audio.shape
+        n = N // self.block_length
+        spec = torch.fft.fft(audio.float().reshape(B, n, self.block_length))
+        c = torch.fft.ifft(spec[..., self.idx] * self.win)                     # (B, n, F, M)
+        c = c.permute(0, 2, 1, 3).reshape(B, self.n_bins, n * self.max_window_length)
+        return torch.view_as_real(c).permute(0, 3, 1, 2)
+
+    def decode(self, coeffs):                    # CQT.decode incl. the global peak normalise and its host sync
+        B, _, Fq, T = coeffs.shape
+        n = T // self.max_window_length
+        c = torch.view_as_complex(coeffs.float().permute(0, 2, 3, 1).contiguous()).reshape(B, Fq, n, self.max_window_length).permute(0, 2, 1, 3)
+        taps = torch.fft.fft(c) * self.win_inv
+        Y = torch.zeros((B, n, self.block_length), dtype=taps.dtype, device=taps.device)
+        Y.scatter_add_(-1, self.idx.reshape(1, 1, -1).expand(B, n, -1), taps.reshape(B, n, -1))
+        audio = torch.fft.ifft(Y).real.reshape(B, 1, n * self.block_length)
+        peak = audio.abs().max()
+        if peak:
+            audio = audio / peak
+        return audio
+
+    def step(self, audio):
+        """chunked_inference (modules.py:204-269) twice, exactly the oracle's loop but with device-side buffers."""
+        R, hop, Mw = self.R, self.block_length // 2, self.max_window_length
+        window = R.hann_sym(Mw).to(self.device)
+        outs = []
+        with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+            for transcribe in (True, False):
+                x = torch.nn.functional.pad(self.pad_to_block_length(audio), [hop, hop])
+                n_chunks = (x.size(-1) - hop) // hop
+                out = torch.zeros((audio.size(0), 2, self.n_bins, self.get_expected_frames(x.size(-1))), device=self.device)
+                for i in range(n_chunks):
+                    piece = x[..., i * hop: i * hop + self.block_length]
+                    out[..., i * Mw // 2: i * Mw // 2 + Mw] += window * R.inference_ref(piece, self.sd, self, transcribe).float()
+                out = out[..., Mw // 2: -Mw // 2]
+                outs.append(torch.tanh(self.to_magnitude(out)) if transcribe else self.decode(out))
+        return outs
+
+
 def run_ours(args, rank, world, local_rank):
     import torch.distributed as dist
     from timbre_trap_b200 import _lib
-    from timbre_trap_b200.framework import TimbreTrap, ops, packing as P
+    from timbre_trap_b200.framework import HostPipeline, TimbreTrap, TrainStep
 
     device = torch.device('cuda', local_rank)
     torch.cuda.set_device(device)
@@ -166,6 +260,7 @@ def run_ours(args, rank, world, local_rank):
     n_blocks = args.blocks
     host_audio = synthetic_audio(n_blocks, seed=1000 + rank, pin=True)
     dev_audio = host_audio.to(device)
+    pk = peaks()
 
     def barrier():
         if world > 1:
@@ -174,15 +269,6 @@ def run_ours(args, rank, world, local_rank):
 
     def step_resident():
         return model.transcribe_and_reconstruct(dev_audio, group=group)
-
-    host_act = torch.empty((n_blocks, F, M), dtype=torch.float32).pin_memory()
-    host_wav = torch.empty((n_blocks, 1, L), dtype=torch.float32).pin_memory()
-
-    def step_e2e():
-        x = host_audio.to(device, non_blocking=True)
-        act, wav = model.transcribe_and_reconstruct(x, group=group)
-        host_act.copy_(act, non_blocking=True)
-        host_wav.copy_(wav, non_blocking=True)
 
     def max_over_ranks(ms):
         if world == 1:
@@ -210,33 +296,109 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
     value = world * n_blocks * SECS / (ms_step * 1e-3)
+    # whole-step arithmetic against the SUSTAINED bf16 peak: 3 chunks per block, encoder once + decoder twice per chunk
+    step_flops = 3 * n_blocks * 28.12e9
+    step_tensor_frac = step_flops / (ms_step * 1e-3) / 1e12 / pk['bf16_sustained']
 
-    # ---- end-to-end arm (pinned host buffers in, host buffers out, every step) ----
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    # ---- end-to-end arm: pinned host audio in, pinned host results out, EVERY step, through framework.HostPipeline (copy-in /
+    # compute / copy-out streams, double-buffered pinned outputs: the read-back of step k overlaps the compute of step k+1) ----
+    pipe = HostPipeline(model, device, depth=2, group=group)
+    for _ in range(max(2, args.warmup // 2)):
+        pipe.collect(pipe.submit(host_audio))
     barrier()
     t0 = time.perf_counter()
+    prev = None
     for _ in range(args.steps):
-        step_e2e()
-    torch.cuda.synchronize()
+        k = pipe.submit(host_audio)
+        if prev is not None:
+            pipe.collect(prev)
+        prev = k
+    pipe.collect(prev)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / args.steps
     barrier()
-    e2e = dict(value=world * n_blocks * SECS / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms,
-               h2d_bytes_per_step=host_audio.numel() * 4, d2h_bytes_per_step=(host_act.numel() + host_wav.numel()) * 4)
+    h2d, d2h = pipe.bytes_per_step(host_audio)
+    e2e = dict(value=world * n_blocks * SECS / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+               how='framework.HostPipeline: H2D of the step\'s audio, transcribe_and_reconstruct, D2H of activations + audio into pinned '
+                   'buffers on copy streams, double-buffered; wall clock from the first submit to the last result on the host')
+    del pipe
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[3]: the loss step, batch 8 x 9 s per GPU, data-parallel (one flat-bucket NCCL all-reduce) ----
+    train = None
+    if not args.no_train:
+        tb = 8
+        g = torch.Generator().manual_seed(200 + rank)
+        t_audio = (torch.rand((tb, 1, 3 * L), generator=g) * 2 - 1).to(device)
+        t_gt = synthetic_targets(tb, 3 * M, seed=300 + rank).to(device)
+        tmodel = TimbreTrap(SR, N_OCT, BPO, SECS, latent_size=LATENT, model_complexity=COMPLEXITY).to(device)
+        ts = TrainStep(tmodel, group=group)
+        for _ in range(2):
+            res = ts.step(t_audio, t_gt)
+        barrier()
+        a.record()
+        n_train = 3
+        for _ in range(n_train):
+            res = ts.step(t_audio, t_gt)
+        b.record()
+        barrier()
+        t_ms = max_over_ranks(a.elapsed_time(b)) / n_train
+        ar_us = None
+        if world > 1:
+            flat = torch.zeros(614490, device=device)
+            ar_us = 1e3 * max_over_ranks(time_kernel(lambda: dist.all_reduce(flat, group=group), iters=20))
+        train = dict(workload='BASELINE.json configs[3]: loss step (reconstruction + transcription + consistency), base model, batch 8 x 9 s per GPU',
+                     ms_per_step=t_ms, audio_s_per_s=world * tb * 9 / (t_ms * 1e-3), tflops=4.05 / (t_ms * 1e-3),
+                     frac_of_sustained_bf16=4.05 / (t_ms * 1e-3) / pk['bf16_sustained'], allreduce_us=ar_us, allreduce_bytes=614490 * 4,
+                     total_loss=float(res['total']), grad_norm=float(res['grad_norm']))
+        del ts, tmodel, t_audio, t_gt, res
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE.json configs[4]: ONE 1-hour clip (1200 blocks -> 2401 overlapped chunks) sharded by blocks over the ranks ----
+    hour = None
+    if not args.no_hour:
+        gh = torch.Generator().manual_seed(77)
+        clip = ((torch.rand((1, 1, 1200 * L), generator=gh) * 2 - 1) * 0.5).to(device)      # every rank holds the clip
+        for _ in range(1):
+            model.transcribe_sharded(clip, group=group)
+            model.reconstruct_sharded(clip, group=group)
+        barrier()
+        a.record()
+        n_hour = 2
+        for _ in range(n_hour):
+            h_act = model.transcribe_sharded(clip, group=group)
+            h_wav = model.reconstruct_sharded(clip, group=group)
+        b.record()
+        barrier()
+        h_ms = max_over_ranks(a.elapsed_time(b)) / n_hour
+        hour = dict(workload='BASELINE.json configs[4]: transcribe_sharded + reconstruct_sharded of one 3600 s clip (2401 chunks), contiguous '
+                             'block ranges per rank with half-block halos, all_gather of the frames, one scalar MAX all-reduce',
+                    ms=h_ms, audio_s_per_s=3600.0 / (h_ms * 1e-3), activations=list(h_act.shape), audio_out=list(h_wav.shape))
+        del clip, h_act, h_wav
+        torch.cuda.empty_cache()
 
     line = None
     if rank == 0:
-        pk = peaks()
-        # ---- roofline of the dominant kernel: the fused residual-block kernel (res_rs_kernel, ~60 % of the step).  Every
-        # instance is HBM-bound (arithmetic intensity 17..136 FLOP/B against a ridge of ~210); the line reports the first-stage
-        # instance (C = 4, packed layout, the largest tensors) against the measured copy bandwidth, and the C = 32 instance
-        # against the measured bf16 peak as `roofline_tensor` (the north star's tensor-pipe view).
+        # ---- roofline of the dominant kernel family: the fused residual-block kernel (res_rs_kernel, ~60 % of the step).  Every
+        # instance is HBM-bound un-fused (arithmetic intensity 17..136 FLOP/B against a ridge of ~210).  `roofline` reports the
+        # first-stage instance (C = 4, packed layout, the largest tensors) against the measured copy bandwidth, `family_frac` all
+        # twelve (stage, dilation) instances of the model timed alone back to back, and `roofline_tensor` the C = 32 instance
+        # against the measured bf16 burst peak (the north star's tensor-pipe view).
         n_chunks = min(3 * n_blocks, model.MAX_CHUNKS_PER_BATCH)
-        blk4 = model.encoder.block1.block1
-        x4 = torch.randn((n_chunks, F, M, 4), device=device).to(torch.bfloat16)
-        y4 = torch.empty_like(x4)
-        ms_4 = time_kernel(lambda: blk4.forward_c8(x4, out=y4), iters=10)
-        bytes_4 = 2.0 * x4.numel() * 2                      # read x + write y, un-padded 4 channels, bf16
+        fam_bytes = fam_ms = 0.0
+        per_instance = {}
+        shapes = {4: (n_chunks, F, M, 4), 8: (n_chunks, 1, 269, M, 8), 16: (n_chunks, 2, 133, M, 8), 32: (n_chunks, 4, 65, M, 8)}
+        for blk_e, c in ((model.encoder.block1, 4), (model.encoder.block2, 8), (model.encoder.block3, 16), (model.encoder.block4, 32)):
+            x = torch.randn(shapes[c], device=device).to(torch.bfloat16)
+            y = torch.empty_like(x)
+            for rb in (blk_e.block1, blk_e.block2, blk_e.block3):
+                ms = time_kernel(lambda: rb.forward_c8(x, out=y), iters=10)
+                h = x.shape[1] if c == 4 else x.shape[2]
+                nbytes = 2.0 * n_chunks * c * h * M * 2                    # read x + write y, un-padded channels, bf16
+                per_instance[(c, rb.dilation)] = (ms, nbytes)
+                fam_bytes += nbytes
+                fam_ms += ms
+            del x, y
+        ms_4, bytes_4 = per_instance[(4, 1)]
         traffic = None
         tpath = os.path.join(ROOT, 'profiles', 'r01_res_rs_c4_traffic.json')
         if os.path.exists(tpath):
@@ -245,19 +407,19 @@ def run_ours(args, rank, world, local_rank):
         roofline = dict(kernel='res_rs_kernel<2,16,1,4> (fused ResidualConv2dBlock, C=4 packed layout folded to 4 frames per GEMM row, dilation 1, H=540)', bound='hbm',
                         achieved=bytes_4 / (ms_4 * 1e-3) / 1e9, peak=pk['hbm'], unit='GB/s', frac=bytes_4 / (ms_4 * 1e-3) / 1e9 / pk['hbm'],
                         traffic=traffic, peak_source=f"{pk['source']} HBM copy bandwidth", us_per_launch=ms_4 * 1e3,
-                        bytes_per_launch=bytes_4, chunks_per_launch=n_chunks)
-        del x4, y4
-        blk = model.encoder.block4.block2
-        x32 = torch.randn((n_chunks, 4, 65, M, 8), device=device).to(torch.bfloat16)
-        y32 = torch.empty_like(x32)
-        ms_k = time_kernel(lambda: blk.forward_c8(x32, out=y32), iters=10)
+                        bytes_per_launch=bytes_4, chunks_per_launch=n_chunks,
+                        family_frac=fam_bytes / (fam_ms * 1e-3) / 1e9 / pk['hbm'],
+                        family=f'all 12 (stage, dilation) instances of res_rs_kernel in the model, {fam_bytes / 1e9:.1f} GB in {fam_ms:.2f} ms',
+                        step_tensor_frac=step_tensor_frac,
+                        step_tensor=f'whole step: {step_flops / 1e12:.1f} TFLOP (3 chunks per block x 28.12 GFLOP) in {ms_step:.1f} ms against the '
+                                    f"{pk['source']} SUSTAINED bf16 peak {pk['bf16_sustained']} TFLOP/s")
+        ms_k, _ = per_instance[(32, 2)]
         flops = 2.0 * (9 * 32 * 32 + 32 * 32) * 65 * M * n_chunks
         achieved = flops / (ms_k * 1e-3) / 1e12
         roofline_tensor = dict(kernel='res_rs_kernel<4,32,2,0> (fused ResidualConv2dBlock, C=32, dilation 2, H=65)', bound='tensor',
                                achieved=achieved, peak=pk['bf16_burst'], unit='TFLOP/s', frac=achieved / pk['bf16_burst'],
                                peak_source=f"{pk['source']} bf16 burst (kernel timed alone)", us_per_launch=ms_k * 1e3,
-                               flops_per_launch=flops, hbm_gbs=2.0 * x32.numel() * 2 / (ms_k * 1e-3) / 1e9)
-        del x32, y32
+                               flops_per_launch=flops, hbm_gbs=per_instance[(32, 2)][1] / (ms_k * 1e-3) / 1e9)
         # ---- CQT forward / inverse against the HBM roofline (BASELINE.json configs[1]: 1024 blocks) ----
         cq = {}
         nb = 1024
@@ -274,17 +436,35 @@ def run_ours(args, rank, world, local_rank):
         del big, coeffs
         torch.cuda.empty_cache()
 
+        # ---- diagnostic anchor: the reference's own code path given a GPU (cuFFT + cuDNN + ATen, bf16 autocast), same batch ----
+        eager = None
+        if world == 1 and not args.no_eager:
+            try:
+                ref = EagerGpuReference(device)
+                ref.step(dev_audio[:8])
+                torch.cuda.synchronize()
+                ms_e = time_kernel(lambda: ref.step(dev_audio), iters=2, warm=1)
+                eager = dict(value=n_blocks * SECS / (ms_e * 1e-3), unit=UNIT, ms_per_step=ms_e,
+                             what='oracle/model_ref.py on CUDA under bf16 autocast (cuDNN convs, ATen element-wise) + torch.fft NSGT (cuFFT), '
+                                  'model.transcribe then model.reconstruct as sequential chunk loops over the same 256-block batch; '
+                                  'diagnostic anchor, not the reference arm')
+                del ref
+            except Exception as exc:                      # an anchor must not take the bench down (e.g. out of memory)
+                eager = dict(unavailable=f'{type(exc).__name__}: {exc}'[:200])
+            torch.cuda.empty_cache()
+
         cpu = None
         if world == 1 and not args.no_cpu:
             state = cpu_state()
-            cpu_reference_step(state, 1)
+            cpu_reference_step(state, CPU_BLOCKS)
             times = []
             t_start = time.perf_counter()
-            while len(times) < 3 or (time.perf_counter() - t_start < 10 and len(times) < 10):
-                times.append(cpu_reference_step(state, 1))
-            v = SECS / (sum(times) / len(times))
+            while len(times) < 3 or (time.perf_counter() - t_start < 15 and len(times) < 7):
+                times.append(cpu_reference_step(state, CPU_BLOCKS))
+            v = CPU_BLOCKS * SECS / median(times)
             cpu = dict(value=v, unit=UNIT, cores=torch.get_num_threads(), kind='port',
-                       sample=f'{len(times)} x (transcribe + reconstruct of one 3 s block, sequential 3-chunk loops) with oracle/model_ref.py')
+                       sample=f'median of {len(times)} x (transcribe + reconstruct of a batch of {CPU_BLOCKS} x 3 s blocks, sequential 3-chunk '
+                              'loops over the batch) with oracle/model_ref.py + oracle/nsgt_ref.py')
 
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
                     higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16 convs (fp32 accumulate), fp32 CQT',
@@ -292,7 +472,8 @@ def run_ours(args, rank, world, local_rank):
                     config=dict(workload=WORKLOAD,
                                 blocks_per_gpu=n_blocks, chunks_per_gpu=3 * n_blocks, parallelism=f'dp{world} (block sharding)',
                                 l2='working set per step ~40 GB >> 126 MB L2; no explicit flush'),
-                    e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_tensor=roofline_tensor, cqt=cq, cpu_baseline=cpu, clocks=clocks)
+                    e2e=e2e, gpu_launches=launches, roofline=roofline, roofline_tensor=roofline_tensor, cqt=cq, train_step=train,
+                    one_hour_sharded=hour, gpu_eager_baseline=eager, cpu_baseline=cpu, clocks=clocks)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -308,6 +489,9 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--blocks', type=int, default=256, help='3 s blocks per GPU per step')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-train', action='store_true', help='skip the loss-step leg (BASELINE.json configs[3])')
+    ap.add_argument('--no-hour', action='store_true', help='skip the sharded one-hour-clip leg (BASELINE.json configs[4])')
+    ap.add_argument('--no-eager', action='store_true', help='skip the eager-PyTorch GPU anchor')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))

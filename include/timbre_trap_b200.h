@@ -166,6 +166,15 @@ int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, 
 /* Decoder.convout (modules.py:543): C8 planar or packed 4-channel input -> fp32 interleaved coefficients (B,F,T,2); w fp32 [2][C][3][3] */
 int tt_conv_out(const void* x, float* coeffs, const float* w, const float* bias, int B, int C, int H, int T, int packed4, void* stream);
 
+/* Decoder.convout FUSED with the Hann cross-fade + trim of TimbreTrap.chunked_inference (modules.py:237-267) and, for act_out,
+ * with TimbreTrap.to_activations (modules.py:271-289): the last decoder stage of ALL chunks in, cross-faded results out - the
+ * per-chunk coefficients never exist in memory.
+ *   x           (batch * n_chunks, H, M, 4) bf16 packed 4-channel layout - chunk i of item b at index b * n_chunks + i
+ *   window      (M) fp32 device (torch.signal.windows.hann, modules.py:239);  w fp32 [2][C][3][3], bias fp32 [2]
+ *   coeffs_out  (batch, H, (n_chunks-1) * M/2, 2) fp32 or NULL;  act_out (batch, H, (n_chunks-1) * M/2) fp32 or NULL */
+int tt_conv_out_crossfade(const void* x, const float* window, const float* w, const float* bias, int batch, int n_chunks, int C,
+                          int H, int M, float* coeffs_out, float* act_out, void* stream);
+
 /*
  * ---- objectives (timbre_trap/framework/objectives.py), deterministic two-stage reductions ------------------------
  * scratch: tt_loss_scratch_floats() floats of device memory.

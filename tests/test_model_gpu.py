@@ -114,6 +114,20 @@ def test_chunk_batching_is_invisible():
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize('cfg,latent,complexity', [(SMALL, None, 1), (BASE, 128, 2)])
+def test_fused_convout_crossfade_is_bit_identical(cfg, latent, complexity):
+    """tt_conv_out_crossfade (convout + Hann cross-fade + trim + tanh|.| over all chunks in one kernel) against the un-fused
+    sequence convout per chunk -> tt_chunk_crossfade: same products, same order, identical bits."""
+    model, sd, c = _build(cfg, latent, complexity, False, seed=1)
+    audio = tonal_clip(int(2.6 * c.block_length), cfg['sample_rate'], seed=6, n_batch=2).cuda()
+    act, rec = model._chunked(audio, True, True)
+    trn_c = model._chunked(audio, True, False, activations=False)[0]
+    model.FUSE_CONVOUT_CROSSFADE = False
+    act_u, rec_u = model._chunked(audio, True, True)
+    trn_u = model._chunked(audio, True, False, activations=False)[0]
+    assert torch.equal(act, act_u) and torch.equal(rec, rec_u) and torch.equal(trn_c, trn_u)
+
+
 def test_sharded_long_clip_equals_unsharded():
     """transcribe_sharded / reconstruct_sharded with the ranks emulated one after the other on one GPU (the 2-rank NCCL run of the
     same methods is scripts/sharded_nccl_check.py, executed with `gpurun --gpus 2`, log under profiles/)."""
@@ -154,14 +168,15 @@ def test_reconstruct_end_to_end_vs_oracle(cfg, latent, complexity, n_blocks):
     """
     TimbreTrap.reconstruct (modules.py:315-336) END TO END against the oracle's reconstruct_ref, with a stated tolerance.
 
-    Two numbers are gated.  (1) The synthesis stage on IDENTICAL coefficients (the CUDA cross-faded coefficients decoded by the
-    oracle): <= 1e-4 norm-relative, the north star's fp32 bound.  (2) The whole chain, bf16 convs included, as an SNR of the
-    peak-normalised audio against the fp32 oracle audio.  The restated NSGT's dual window is ill-conditioned at the top of the
-    last bin (gain up to 5.8e4 where a single Hann tail covers the spectrum), so ANY coefficient error is
-    amplified there - a numpy experiment with 1e-2 relative white noise on the oracle's own coefficients gives 4 dB at the base
-    configuration.  The gate is therefore two-part: SNR over the well-conditioned band (spectrum positions whose frame-operator
-    diagonal is >= 1e-3 of its maximum) >= 30 dB, and full-band SNR >= the value a 1.5e-2 relative perturbation of the oracle's
-    coefficients (the stated logits tolerance) produces on the same clip, minus 3 dB.
+    Three numbers are gated.  (1) The synthesis stage on IDENTICAL coefficients (the CUDA cross-faded coefficients decoded by
+    the oracle): <= 1e-4 norm-relative, the north star's fp32 bound.  (2) The whole chain, bf16 convs included, BEFORE the peak
+    normalise and over the well-conditioned band (spectrum positions whose frame-operator diagonal is >= 1e-3 of its maximum):
+    SNR against the fp32 oracle >= 30 dB (the stated logits tolerance of 1.5e-2 rel-L2 is 36.5 dB).  (3) The final, peak-normalised
+    audio over the full band.  The restated NSGT's dual window is ill-conditioned at the top of the last bin (gain up to 5.8e4 where
+    a single Hann tail covers the spectrum), so ANY error of non-consistent coefficients is amplified there
+    and moves the global peak: 1.5e-2 relative white noise on the oracle's OWN coefficients gives about -8 dB at the base
+    configuration with a random-init model.  The full-band gate is therefore relative: at least the SNR that perturbation of the
+    oracle's coefficients produces on the same clip, minus 3 dB (measured on B200: -8.9 dB against a floor of -11.1 dB).
     """
     from oracle import model_ref as R
     model, sd, c = _build(cfg, latent, complexity, False, seed=0)
@@ -176,15 +191,19 @@ def test_reconstruct_end_to_end_vs_oracle(cfg, latent, complexity, n_blocks):
     emax, el2 = rel_err(model.sliCQ.decode(coeffs_gpu).cpu().numpy(), c.decode(coeffs_gpu.cpu()).numpy())
     assert emax < 1e-4 and el2 < 1e-4, (emax, el2)
     _check_logits(coeffs_gpu.cpu().numpy(), coeffs_ref.numpy(), 'cross-faded coefficients')
-    # (2) whole chain
+    # (2) whole chain before the normalise, well-conditioned band
+    diag = c.nsgt.tables.frame_diagonal[: L // 2 + 1]
+    good = torch.from_numpy(diag >= 1e-3 * diag.max())
+    band = lambda x: torch.fft.irfft(torch.fft.rfft(x.reshape(-1, L).double(), dim=-1) * good, n=L, dim=-1)
+    raw_got = model.sliCQ.decode_raw(coeffs_gpu)[0].cpu()
+    raw_want = c.decode_raw(coeffs_ref)
+    banded = _snr_db(band(raw_got).numpy(), band(raw_want).numpy())
+    # (3) the final audio, full band, against the same-size perturbation of the oracle's own coefficients
     rng = np.random.default_rng(0)
     noise = torch.from_numpy(rng.standard_normal(tuple(coeffs_ref.shape)).astype(np.float32)) * (1.5e-2 * float(coeffs_ref.pow(2).mean().sqrt()))
     floor = _snr_db(c.decode(coeffs_ref + noise).numpy(), want.numpy()) - 3.0
     full = _snr_db(got.numpy(), want.numpy())
-    diag = c.nsgt.tables.frame_diagonal[: L // 2 + 1]
-    good = torch.from_numpy((diag >= 1e-3 * diag.max()).astype(np.float32))
-    band = lambda x: torch.fft.irfft(torch.fft.rfft(x.reshape(-1, L).double(), dim=-1) * good, n=L, dim=-1)
-    banded = _snr_db(band(got).numpy(), band(want).numpy())
-    print(f'reconstruct end to end ({cfg["sample_rate"]} Hz): full-band SNR {full:.1f} dB (floor {floor:.1f}), well-conditioned band {banded:.1f} dB')
-    assert full >= floor, (full, floor)
+    print(f'reconstruct end to end ({cfg["sample_rate"]} Hz): well-conditioned band before normalise {banded:.1f} dB; '
+          f'final audio full band {full:.1f} dB (floor {floor:.1f})')
     assert banded >= 30.0, banded
+    assert full >= floor, (full, floor)

@@ -632,6 +632,121 @@ __global__ void __launch_bounds__(128) conv_out_p4_kernel(const uint2* __restric
     }
 }
 
+// Decoder.convout FUSED with the Hann cross-fade of 50 %-overlapped chunks and the trim (TimbreTrap.chunked_inference,
+// modules.py:237-267), optionally with tanh|.| (TimbreTrap.to_activations, modules.py:271-289): output frame t of item b (after
+// the M/2 trim) is  window[p + M/2] * convout(chunk i-1)[p + M/2] + window[p] * convout(chunk i)[p]  with i = t / (M/2) + 1,
+// p = t mod (M/2).  A thread owns 4 output frames and walks down the rows of BOTH source chunks (two accumulator sets), so the
+// per-chunk fp32 coefficients (2 x 8.8 MB per block) never exist in HBM: read 2 x 4 channels bf16, write one fp32 pair (or one
+// fp32 activation) per output frame.  Products are rounded separately and added in chunk order, like the reference's
+// `coefficients[...] += window * chunk` (and like crossfade_kernel, which remains for the un-fused API path).
+//   x (batch * n_chunks, H, M, 4) bf16 packed4;  coeffs_out (batch, H, (n_chunks-1) M/2, 2) and / or act_out (batch, H, (n_chunks-1) M/2)
+__global__ void __launch_bounds__(128) conv_out_xfade_p4_kernel(const uint2* __restrict__ x, const float* __restrict__ window,
+                                                                const float* __restrict__ w /* [2][C][3][3] */, const float* __restrict__ bias,
+                                                                int C, int H, int M, int n_chunks, int rows, float2* __restrict__ coeffs_out,
+                                                                float* __restrict__ act_out) {
+    __shared__ __align__(16) float2 sw[3][3][4];     // [ky][kx][c] -> (w for output 0, w for output 1)
+    __shared__ float2 sb;
+    for (int i = threadIdx.x; i < 36; i += 128) {
+        const int ky = i / 12, kx = (i / 4) % 3, c = i % 4;
+        sw[ky][kx][c] = c < C ? make_float2(w[(0 * C + c) * 9 + ky * 3 + kx], w[(1 * C + c) * 9 + ky * 3 + kx]) : make_float2(0.f, 0.f);
+    }
+    if (threadIdx.x == 0) sb = make_float2(bias[0], bias[1]);
+    __syncthreads();
+    const int half = M / 2;
+    const long long n_out = (long long)(n_chunks - 1) * half;
+    const long long t0 = ((long long)blockIdx.x * 128 + threadIdx.x) * 4;
+    if (t0 >= n_out) return;
+    const int b = blockIdx.z, h0 = blockIdx.y * rows, h1 = min(H, h0 + rows);
+    const int i1 = (int)(t0 / half) + 1;                         // the later chunk; the earlier one is i1 - 1
+    const int p1 = (int)(t0 - (long long)(i1 - 1) * half);       // position in the later chunk; + half in the earlier one
+    // source s = 0: earlier chunk at frames p1 + half .., s = 1: later chunk at frames p1 ..
+    const int pos[2] = {p1 + half, p1};
+    const uint2* xs[2] = {x + ((size_t)b * n_chunks + i1 - 1) * H * M + pos[0], x + ((size_t)b * n_chunks + i1) * H * M + pos[1]};
+    const float4 wv0 = __ldg(reinterpret_cast<const float4*>(window + pos[0])), wv1 = __ldg(reinterpret_cast<const float4*>(window + pos[1]));
+    const float win[2][4] = {{wv0.x, wv0.y, wv0.z, wv0.w}, {wv1.x, wv1.y, wv1.z, wv1.w}};
+    const float2 bias2 = sb;
+    float2 P[2][4], Q[2][4], R[2][4];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int f = 0; f < 4; ++f) P[s][f] = Q[s][f] = R[s][f] = bias2;
+    auto load = [&](int hh, uint2 (&raw)[2][6]) {
+        if (hh >= 0 && hh < H) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const uint2* xr = xs[s] + (size_t)hh * M;
+                const uint4 m0 = __ldg(reinterpret_cast<const uint4*>(xr)), m1 = __ldg(reinterpret_cast<const uint4*>(xr) + 1);
+                raw[s][0] = pos[s] > 0 ? __ldg(xr - 1) : make_uint2(0u, 0u);          // 'same' padding at the chunk's own borders
+                raw[s][1] = make_uint2(m0.x, m0.y); raw[s][2] = make_uint2(m0.z, m0.w);
+                raw[s][3] = make_uint2(m1.x, m1.y); raw[s][4] = make_uint2(m1.z, m1.w);
+                raw[s][5] = pos[s] + 4 < M ? __ldg(xr + 4) : make_uint2(0u, 0u);
+            }
+        }
+    };
+    uint2 raw[2][6], nxt[2][6];
+    auto step = [&](int hh, float2 (&A)[2][4], float2 (&Bq)[2][4], float2 (&Cq)[2][4]) {
+        if (hh < h1) load(hh + 1, nxt);
+        if (hh >= 0 && hh < H) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                for (int i = 0; i < 6; ++i) {
+                    const float v[4] = {__uint_as_float(raw[s][i].x << 16), __uint_as_float(raw[s][i].x & 0xFFFF0000u),
+                                        __uint_as_float(raw[s][i].y << 16), __uint_as_float(raw[s][i].y & 0xFFFF0000u)};
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float2 vv = dup2(v[c]);
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const int f = i - kx;
+                            if (f >= 0 && f < 4) {
+                                Cq[s][f] = __ffma2_rn(vv, sw[0][kx][c], Cq[s][f]);
+                                Bq[s][f] = __ffma2_rn(vv, sw[1][kx][c], Bq[s][f]);
+                                A[s][f] = __ffma2_rn(vv, sw[2][kx][c], A[s][f]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        const int ho = hh - 1;
+        if (ho >= h0 && ho < h1) {
+            float2 r[4];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+                r[f].x = __fadd_rn(__fmul_rn(win[0][f], A[0][f].x), __fmul_rn(win[1][f], A[1][f].x));
+                r[f].y = __fadd_rn(__fmul_rn(win[0][f], A[0][f].y), __fmul_rn(win[1][f], A[1][f].y));
+            }
+            const size_t o = ((size_t)b * H + ho) * n_out + t0;
+            if (coeffs_out) {
+                float4* dst = reinterpret_cast<float4*>(coeffs_out + o);
+                __stcs(dst, make_float4(r[0].x, r[0].y, r[1].x, r[1].y));
+                __stcs(dst + 1, make_float4(r[2].x, r[2].y, r[3].x, r[3].y));
+            }
+            if (act_out) {
+                float a[4];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) a[f] = tanhf(sqrtf(r[f].x * r[f].x + r[f].y * r[f].y));
+                __stcs(reinterpret_cast<float4*>(act_out + o), make_float4(a[0], a[1], a[2], a[3]));
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+            for (int f = 0; f < 4; ++f) A[s][f] = bias2;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) raw[s][i] = nxt[s][i];
+        }
+    };
+    int hh = h0 - 1;
+    load(hh, raw);
+    while (true) {
+        step(hh, P, Q, R); if (++hh > h1) break;
+        step(hh, Q, R, P); if (++hh > h1) break;
+        step(hh, R, P, Q); if (++hh > h1) break;
+    }
+}
+
 // Encoder.convin, fp32 interleaved (B, H, T, 2) -> packed4 (B, H, T, 4) bf16, + ELU
 __global__ void __launch_bounds__(128) conv_in_p4_kernel(const float2* __restrict__ x, uint2* __restrict__ y, const float* __restrict__ w /* [C0][2][3][3] */,
                                                          const float* __restrict__ bias, int C0, int H, int T, int rows) {
@@ -779,6 +894,24 @@ extern "C" int tt_conv_out(const void* x, float* coeffs, const float* w, const f
                                                                                                              T, rows);
     } else if (C <= 4) conv_out_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T, packed4);
     else conv_out_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (float2*)coeffs, w, bias, C, H, T, 0);
+    tt_count_launches(1);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
+extern "C" int tt_conv_out_crossfade(const void* x, const float* window, const float* w, const float* bias, int batch, int n_chunks, int C,
+                                     int H, int M, float* coeffs_out, float* act_out, void* stream) {
+    TT_REQUIRE(x && window && w && bias && (coeffs_out || act_out), "null argument");
+    TT_REQUIRE(C >= 1 && C <= 4, "conv_out_crossfade: the packed layout holds at most 4 channels");
+    TT_REQUIRE(n_chunks >= 2 && M >= 8 && M % 8 == 0, "conv_out_crossfade: at least two chunks, chunk length a multiple of 8 (got %d, %d)", n_chunks, M);
+    if (batch <= 0 || H <= 0) return TT_OK;
+    const long long n_out = (long long)(n_chunks - 1) * (M / 2);
+    const long long col_ctas = (n_out / 4 + 127) / 128;
+    int rows = 36;
+    while (rows > 6 && (long long)batch * col_ctas * ((H + rows - 1) / rows) < 4 * 148) rows /= 2;
+    TT_REQUIRE(col_ctas < (1ll << 31), "conv_out_crossfade: clip too long for one launch");
+    conv_out_xfade_p4_kernel<<<dim3((unsigned)col_ctas, (H + rows - 1) / rows, batch), 128, 0, (cudaStream_t)stream>>>(
+        (const uint2*)x, window, w, bias, C, H, M, n_chunks, rows, (float2*)coeffs_out, act_out);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;

@@ -5,6 +5,7 @@ from .objectives import __all__ as _objectives_all
 from .cqt import CQT
 from .modules import *          # noqa: F401,F403
 from .modules import __all__ as _modules_all
-from .train import compute_step_losses
+from .train import TrainStep, compute_step_losses
+from .pipeline import HostPipeline
 
-__all__ = list(_objectives_all) + ['CQT', 'compute_step_losses'] + list(_modules_all)
+__all__ = list(_objectives_all) + ['CQT', 'compute_step_losses', 'TrainStep', 'HostPipeline'] + list(_modules_all)

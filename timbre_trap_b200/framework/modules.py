@@ -156,13 +156,14 @@ class DecoderBlock(nn.Module):
         for blk in (self.block1, self.block2, self.block3):
             blk.packed4 = flag
 
-    def forward_c8(self, x):
+    def forward_c8(self, x, out=None):
+        """`out`: where the stage's result goes (e.g. a slice of the all-chunks buffer the fused convout / cross-fade reads)."""
         c = self.tconv[0]
         (w,) = self._cache.get((c.weight, c.bias), lambda: (P.pack_up_strip(c.weight, c.bias),))
         a = ops.conv_up_strip(x, w, P.pad8(self.out_channels), self.out_pad, packed4_out=self.packed4)
         b = self.block1.forward_c8(a)
         a = self.block2.forward_c8(b, out=a)
-        return self.block3.forward_c8(a, out=b)
+        return self.block3.forward_c8(a, out=b if out is None else out)
 
     def forward(self, x):
         y = self.forward_c8(P.to_c8(x))
@@ -275,18 +276,25 @@ class Decoder(nn.Module):
             return w, tables, co.weight.detach().float().contiguous(), co.bias.detach().float().contiguous()
         return self._cache.get((ci.weight, ci.bias, co.weight, co.bias), build)
 
-    def forward_c8(self, lat_c8, reconstruct, skips=None):
-        """latents C8 (B, Dp/8, 1, T, 8) (without the indicator channel) -> coefficients (B, F, T, 2) fp32 interleaved."""
-        w_in, tables, w_out, b_out = self._packed()
+    def last_stage_c8(self, lat_c8, reconstruct, skips=None, out=None):
+        """Everything before `convout`: latents C8 (B, Dp/8, 1, T, 8) (without the indicator channel) -> the last stage's
+        activations in their internal layout (packed4 (B, F, T, 4) for the supported channel plans), written to `out` if given."""
+        w_in, tables, _, _ = self._packed()
         x = ops.deconv_in(lat_c8, w_in, tables[1 if reconstruct else 0], P.pad8(self.channels[0]), self.embedding_size)
         blocks = (self.block1, self.block2, self.block3, self.block4)
         for i, blk in enumerate(blocks):
             if skips is not None:
                 x = x + skips[-1 - i]
-            x = blk.forward_c8(x)
+            last = i == len(blocks) - 1
+            x = blk.forward_c8(x, out=out if (last and skips is None) else None)
         if skips is not None:
-            x = x + skips[0]
-        return ops.conv_out(x, w_out, b_out, self.channels[4])
+            x = torch.add(x, skips[0], out=out) if out is not None else x + skips[0]
+        return x
+
+    def forward_c8(self, lat_c8, reconstruct, skips=None):
+        """latents C8 (B, Dp/8, 1, T, 8) (without the indicator channel) -> coefficients (B, F, T, 2) fp32 interleaved."""
+        _, _, w_out, b_out = self._packed()
+        return ops.conv_out(self.last_stage_c8(lat_c8, reconstruct, skips), w_out, b_out, self.channels[4])
 
     def forward(self, latents, encoder_embeddings=None):
         """Decoder.forward (modules.py:545-594): latents (B, D+1, T) WITH the indicator channel -> (B, 2, F, T)."""
@@ -371,6 +379,9 @@ class TimbreTrap(nn.Module):
 
     # chunks per kernel batch of the chunked paths (bounds activation memory: ~2.3 GB per live tensor at 256 chunks)
     MAX_CHUNKS_PER_BATCH = 256
+    # convout + Hann cross-fade + trim (+ tanh|.|) as one kernel over all chunks; False = per-chunk convout, then tt_chunk_crossfade
+    # (same arithmetic in the same order: results are bit-identical, tests/test_model_gpu.py)
+    FUSE_CONVOUT_CROSSFADE = True
 
     def __init__(self, sample_rate, n_octaves, bins_per_octave, secs_per_block=3, latent_size=None, model_complexity=1,
                  skip_connections=False):
@@ -454,6 +465,10 @@ class TimbreTrap(nn.Module):
         Batched form of chunked_inference (modules.py:204-269) for one or both switch settings with a shared
         encoder pass.  Returns (transcription, reconstruction) coefficient tensors (B, F, T, 2) interleaved - or the
         activations (B, F, T) for the transcription when `activations` - None where not requested.
+
+        The last decoder stage of every chunk goes into one (B * n_chunks, F, M, 4) bf16 buffer per output; `convout`, the Hann
+        cross-fade, the trim and (for activations) tanh|.| then run as ONE kernel over it (tt_conv_out_crossfade): the
+        per-chunk fp32 coefficients of the reference's loop never exist.
         """
         _lib.require_cuda(audio, 'audio')
         with torch.no_grad():
@@ -461,18 +476,26 @@ class TimbreTrap(nn.Module):
             chunks, n_chunks = self._chunks(audio.detach().float(), prepadded)
             n_out = (n_chunks - 1) * (M // 2)
             window = self._window(audio.device)
-            outs = []
-            for want, reconstruct in ((want_transcription, False), (want_reconstruction, True)):
-                outs.append(torch.empty((B * n_chunks, F, M, 2), dtype=torch.float32, device=audio.device) if want else None)
+            fused = self.FUSE_CONVOUT_CROSSFADE and self.decoder.packed4 and M % 8 == 0
+            wants = (want_transcription, want_reconstruction)
+            if fused:
+                stages = [torch.empty((B * n_chunks, F, M, 4), dtype=torch.bfloat16, device=audio.device) if w else None for w in wants]
+            else:
+                stages = [torch.empty((B * n_chunks, F, M, 2), dtype=torch.float32, device=audio.device) if w else None for w in wants]
             step = self.MAX_CHUNKS_PER_BATCH
             for c0 in range(0, B * n_chunks, step):
                 lat, skips = self._codes(chunks[c0:c0 + step])
-                for out, reconstruct in zip(outs, (False, True)):
-                    if out is not None:
-                        out[c0:c0 + step] = self.decoder.forward_c8(lat, reconstruct, skips)
+                for stage, reconstruct in zip(stages, (False, True)):
+                    if stage is None:
+                        continue
+                    if fused:
+                        self.decoder.last_stage_c8(lat, reconstruct, skips, out=stage[c0:c0 + step])
+                    else:
+                        stage[c0:c0 + step] = self.decoder.forward_c8(lat, reconstruct, skips)
+            _, _, w_out, b_out = self.decoder._packed()
             results = []
-            for out, as_act in zip(outs, (activations, False)):
-                if out is None:
+            for stage, as_act in zip(stages, (activations, False)):
+                if stage is None:
                     results.append(None)
                     continue
                 if as_act:
@@ -481,10 +504,15 @@ class TimbreTrap(nn.Module):
                 else:
                     res = torch.empty((B, F, n_out, 2), dtype=torch.float32, device=audio.device)
                     args = (ctypes.c_void_p(res.data_ptr()), None)
+                stream = ctypes.c_void_p(torch.cuda.current_stream(audio.device).cuda_stream)
                 with torch.cuda.device(audio.device):
-                    _lib.check(_lib.lib().tt_chunk_crossfade(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(window.data_ptr()),
-                                                             B, n_chunks, F, M, args[0], args[1],
-                                                             ctypes.c_void_p(torch.cuda.current_stream(audio.device).cuda_stream)))
+                    if fused:
+                        _lib.check(_lib.lib().tt_conv_out_crossfade(ctypes.c_void_p(stage.data_ptr()), ctypes.c_void_p(window.data_ptr()),
+                                                                    ctypes.c_void_p(w_out.data_ptr()), ctypes.c_void_p(b_out.data_ptr()),
+                                                                    B, n_chunks, self.decoder.channels[4], F, M, args[0], args[1], stream))
+                    else:
+                        _lib.check(_lib.lib().tt_chunk_crossfade(ctypes.c_void_p(stage.data_ptr()), ctypes.c_void_p(window.data_ptr()),
+                                                                 B, n_chunks, F, M, args[0], args[1], stream))
                 results.append(res)
             return results
 
