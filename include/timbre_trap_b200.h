@@ -176,6 +176,44 @@ int tt_conv_out_crossfade(const void* x, const float* window, const float* w, co
                           int H, int M, float* coeffs_out, float* act_out, void* stream);
 
 /*
+ * ---- model variants and skip connections (modules.py:95-117, 568-589, 780-1075): single-pass element-wise kernels ----------
+ */
+/* out = x + (*scale) * e on bf16 tensors of one layout, n elements (multiple of 8): the decoder's skip connection with the learnable
+ * weight of TimbreTrap.apply_skip_connections read from device memory; out may alias x */
+int tt_add_scaled_bf16(const void* x, const void* e, const float* scale, void* out, int64_t n, void* stream);
+/* (x) -> interleaved (x, 0): a one-channel feature map (TimbreTrapMag / MagDB encoder input, modules.py:927-950, 1019-1031) in the
+ * two-channel layout tt_conv_in reads */
+int tt_widen_pairs(const float* x, int64_t n, float* out, void* stream);
+/* channel 0 of n interleaved pairs through an output non-linearity: 0 identity, 1 relu (TimbreTrapMag.decode, modules.py:976),
+ * 2 sigmoid (TimbreTrapMagDB.decode :1052), 3 tanh(relu(.)) (Mag decode + to_activations :996) */
+int tt_channel0_activation(const float* pairs, int64_t n, int mode, float* out, void* stream);
+
+/*
+ * ---- audio front-end and evaluation metric on the device -----------------------------------
+ */
+/* AudioDataset.get_audio after the file read (datasets/AudioDataset.py:69-77): mono mix (mean over channels) + band-limited
+ * polyphase resampling (torchaudio.functional.resample) in one pass; *peak receives max|out| (zeroed by the call) for the
+ * infinity-norm normalise, which is tt_scale_by_peak(out, n_out, peak).
+ *   audio   (channels, n_in) fp32 device, channel-major as torchaudio.load returns it
+ *   kernel  (new_f, 2*width + orig) fp32 device: the windowed-sinc filter of every output phase (orig, new_f already divided by
+ *           their gcd; table from timbre_trap_b200/framework/frontend.py::sinc_resample_kernel); orig == new_f == 1 with the
+ *           one-tap kernel {1} is the plain mono mix
+ *   out     (n_out) fp32, n_out = ceil(new_f * n_in / orig) */
+int tt_resample_mono(const float* audio, int channels, int64_t n_in, const float* kernel, int orig, int new_f, int width,
+                     float* out, int64_t n_out, float* peak, void* stream);
+/* PitchDataset.multi_pitch_to_activations (datasets/PitchDataset.py:233-307): pitches_hz (T, P) fp64 device, 0 = no pitch;
+ * midi_freqs (F) fp64 device (ascending); blur (2R+1) fp32 device = the normalised Gaussian taps (R = 0, {1}: no blur);
+ * activations (F, T) fp32 out; min_scratch one device float */
+int tt_rasterise_pitches(const double* pitches_hz, int T, int P, const double* midi_freqs, int F, const float* blur, int R,
+                         float* activations, float* min_scratch, void* stream);
+/* The O(N) part of the signal-to-distortion ratio the reference's evaluation reports (experiments/evaluate.py:51,122-127,
+ * torchmetrics SignalDistortionRatio, filter_length 512): per item the first `lags` auto-correlation values of target,
+ * r0[l] = sum_n t[n] t[n+l], the cross-correlation b[l] = sum_n t[n] p[n+l], and the two squared norms (|t|^2, |p|^2), all
+ * accumulated in fp64.  target, preds (batch, n) fp32; r0, b (batch, lags) fp64; norms (batch, 2) fp64 (all zeroed by the call). */
+int tt_sdr_correlations(const float* target, const float* preds, int batch, int64_t n, int lags, double* r0, double* b,
+                        double* norms, void* stream);
+
+/*
  * ---- objectives (timbre_trap/framework/objectives.py), deterministic two-stage reductions ------------------------
  * scratch: tt_loss_scratch_floats() floats of device memory.
  */

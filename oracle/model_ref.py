@@ -22,7 +22,8 @@ from .nsgt_ref import NSGTOracle
 __all__ = ['CQTRef', 'encoder_ref', 'decoder_ref', 'decode_ref', 'inference_ref', 'chunked_inference_ref',
            'transcribe_ref', 'reconstruct_ref', 'forward_ref', 'reconstruction_loss_ref',
            'transcription_loss_ref', 'consistency_loss_ref', 'channel_plan', 'feature_sizes', 'init_state_dict',
-           'to_decibels_ref', 'hann_sym']
+           'to_decibels_ref', 'hann_sym', 'features_ref', 'decode_variant_ref', 'activations_variant_ref',
+           'forward_variant_ref', 'chunked_inference_variant_ref']
 
 
 # ---------------------------------------------------------------------------------------
@@ -43,7 +44,7 @@ def feature_sizes(n_bins):
     return sizes, pads[::-1]
 
 
-def init_state_dict(n_bins, latent_size=None, model_complexity=1, seed=0):
+def init_state_dict(n_bins, latent_size=None, model_complexity=1, seed=0, variant='base'):
     """
     A deterministic, torch-version-independent random state_dict with the reference's 120
     names and shapes.  Values follow the fan-in-uniform recipe of
@@ -67,7 +68,9 @@ def init_state_dict(n_bins, latent_size=None, model_complexity=1, seed=0):
         add(prefix + '.conv1.0', (c, c, 3, 3), c * 9)
         add(prefix + '.conv2.0', (c, c, 1, 1), c)
 
-    add('encoder.convin.0', (ch[0], 2, 3, 3), 2 * 9)
+    # variant: 'base' | 'film' (modules.py:780-840) | 'mag' / 'magdb' (modules.py:892-1075: one-channel convin / convout)
+    cin = 1 if variant in ('mag', 'magdb') else 2
+    add('encoder.convin.0', (ch[0], cin, 3, 3), cin * 9)
     for i in range(4):
         for j in range(3):
             add_res(f'encoder.block{i + 1}.block{j + 1}', ch[i])
@@ -76,12 +79,15 @@ def init_state_dict(n_bins, latent_size=None, model_complexity=1, seed=0):
 
     dch = ch[::-1]
     # ConvTranspose2d weights are (C_in, C_out, kh, kw); torch derives fan_in from dim 1
-    add('decoder.convin.0', (latent_size + 1, dch[0], sizes[4], 1), dch[0] * sizes[4], True)
+    add('decoder.convin.0', (latent_size + (0 if variant == 'film' else 1), dch[0], sizes[4], 1), dch[0] * sizes[4], True)
     for i in range(4):
         add(f'decoder.block{i + 1}.tconv.0', (dch[i], dch[i + 1], 4, 1), dch[i + 1] * 4, True)
         for j in range(3):
             add_res(f'decoder.block{i + 1}.block{j + 1}', dch[i + 1])
-    add('decoder.convout', (2, dch[4], 3, 3), dch[4] * 9)
+    add('decoder.convout', (cin, dch[4], 3, 3), dch[4] * 9)
+    if variant == 'film':
+        add('film_layer.gamma', (latent_size, 2), 2)
+        add('film_layer.beta', (latent_size, 2), 2)
     return sd
 
 
@@ -292,6 +298,75 @@ def forward_ref(audio, sd, cqt, consistency=False):
         trn_rec = decode_ref(lat2, sd, cqt.n_bins, False, sk2)
         trn_scr = decode_ref(lat2, sd, cqt.n_bins, True, sk2)
     return rec, latents, trn, trn_rec, trn_scr
+
+
+# ---------------------------------------------------------------------------------------
+# model variants (modules.py:780-1075)
+# ---------------------------------------------------------------------------------------
+
+def features_ref(variant, audio, cqt):
+    """The encoder's input: TimbreTrap.encode :88, TimbreTrapMag.encode :947, TimbreTrapMagDB.encode :1024-1027."""
+    c = cqt(audio)
+    if variant in ('base', 'film'):
+        return c
+    mag = cqt.to_magnitude(c)
+    return (to_decibels_ref(mag) if variant == 'magdb' else mag).unsqueeze(-3)
+
+
+def decode_variant_ref(variant, latents, sd, n_bins, transcribe=False, skips=None):
+    """TimbreTrap.decode :119-147 / TimbreTrapFiLM.decode :811-840 / TimbreTrapMag.decode :952-978 / TimbreTrapMagDB.decode :1033-1054."""
+    if variant == 'film':
+        cond = torch.tensor([float(transcribe), float(not transcribe)])
+        gamma = F.linear(cond, sd['film_layer.gamma.weight'], sd['film_layer.gamma.bias'])
+        beta = F.linear(cond, sd['film_layer.beta.weight'], sd['film_layer.beta.bias'])
+        return decoder_ref((latents.transpose(-1, -2) * gamma + beta).transpose(-1, -2), sd, n_bins, skips)
+    out = decode_ref(latents, sd, n_bins, transcribe, skips)
+    if variant == 'mag':
+        return F.relu(out)
+    if variant == 'magdb':
+        return torch.sigmoid(out)
+    return out
+
+
+def activations_variant_ref(variant, coefficients):
+    """to_activations: TimbreTrap :271-289, TimbreTrapMag :980-1001, TimbreTrapMagDB :1056-1075."""
+    if variant == 'mag':
+        return torch.tanh(coefficients.squeeze(-3))
+    if variant == 'magdb':
+        return coefficients.squeeze(-3)
+    return torch.tanh(CQTRef.to_magnitude(coefficients))
+
+
+def forward_variant_ref(variant, audio, sd, cqt, consistency=False):
+    """TimbreTrap.forward :338-393 with the variant's encode / decode."""
+    latents, emb = encoder_ref(features_ref(variant, audio, cqt), sd)
+    sk = _skips(sd, emb)
+    rec = decode_variant_ref(variant, latents, sd, cqt.n_bins, False, sk)
+    trn = decode_variant_ref(variant, latents, sd, cqt.n_bins, True, sk)
+    trn_rec = trn_scr = None
+    if consistency:
+        lat2, emb2 = encoder_ref(trn, sd)
+        sk2 = _skips(sd, emb2)
+        trn_rec = decode_variant_ref(variant, lat2, sd, cqt.n_bins, False, sk2)
+        trn_scr = decode_variant_ref(variant, lat2, sd, cqt.n_bins, True, sk2)
+    return rec, latents, trn, trn_rec, trn_scr
+
+
+def chunked_inference_variant_ref(variant, audio, sd, cqt, transcribe=False):
+    """The inherited TimbreTrap.chunked_inference (modules.py:204-269) as a variant runs it: the buffer has two channels whatever
+    the variant's output has (:244), a one-channel chunk output broadcasts into both (:259-263)."""
+    B, nb = audio.size(0), cqt.n_bins
+    hop = cqt.block_length // 2
+    audio = F.pad(cqt.pad_to_block_length(audio), [hop, hop])
+    n_chunks = (audio.size(-1) - hop) // hop
+    M = cqt.max_window_length
+    window = hann_sym(M)
+    out = torch.zeros((B, 2, nb, cqt.get_expected_frames(audio.size(-1))))
+    for i in range(n_chunks):
+        piece = audio[..., i * hop: i * hop + cqt.block_length]
+        latents, emb = encoder_ref(features_ref(variant, piece, cqt), sd)
+        out[..., i * M // 2: i * M // 2 + M] += window * decode_variant_ref(variant, latents, sd, nb, transcribe, _skips(sd, emb))
+    return out[..., M // 2: -M // 2]
 
 
 # ---------------------------------------------------------------------------------------

@@ -182,10 +182,108 @@ def main():
                         transcription_sub=sub(trn, 9, 31), transcription_norm=float(trn.norm()),
                         transcribe_sub=sub(act, 9, 31), transcribe_norm=float(act.norm()), transcribe_max=float(act.max()),
                         reconstruct_sub=wav[..., ::41].numpy(), reconstruct_norm=float(wav.norm()))
+    make_variants()
+    make_frontend()
     make_postproc()
     print('golden vectors written to', GOLDEN)
     for fn in sorted(os.listdir(GOLDEN)):
         print(f'  {fn:28s} {os.path.getsize(os.path.join(GOLDEN, fn)) / 1024:8.1f} KiB')
+
+
+def make_variants():
+    """tests/golden/model_small_{film,mag,magdb}.npz: the reference's TimbreTrapFiLM / TimbreTrapMag / TimbreTrapMagDB classes
+    (modules.py:780-1075, imported unmodified) on the small configuration, complexity 2, skip connections on for the FiLM one."""
+    install_stubs()
+    from timbre_trap.framework import modules as M
+    torch.set_grad_enabled(False)
+    for tag, cls, skip in (('film', M.TimbreTrapFiLM, True), ('mag', M.TimbreTrapMag, False), ('magdb', M.TimbreTrapMagDB, False)):
+        model = cls(SMALL['sample_rate'], SMALL['n_octaves'], SMALL['bins_per_octave'], SMALL['secs_per_block'],
+                    latent_size=24, model_complexity=2, skip_connections=skip).eval()
+        sd = init_state_dict(model.sliCQ.n_bins, 24, 2, seed=7, variant=tag)
+        if skip:
+            sd['skip_weights'] = torch.tensor([0.9, 1.1, 0.8, 1.2, 0.7])
+        missing = model.load_state_dict(sd, strict=False)
+        assert not missing.unexpected_keys and all(k.startswith('sliCQ.') for k in missing.missing_keys), missing
+        audio = tonal_clip(int(1.3 * model.sliCQ.block_length), SMALL['sample_rate'], seed=5, n_batch=2)
+        whole = model.sliCQ.pad_to_block_length(audio)
+        lat, emb, _ = model.encode(whole)
+        rec, _, trn, trn_rec, trn_scr, _ = model(whole, consistency=True)
+        np.savez_compressed(os.path.join(GOLDEN, f'model_small_{tag}.npz'),
+                            audio=audio.numpy(), latents=lat.numpy(), out_shape=np.array(rec.shape),
+                            reconstruction_sub=sub(rec, 2, 3), transcription_sub=sub(trn, 2, 3),
+                            transcription_rec_sub=sub(trn_rec, 2, 3), transcription_scr_sub=sub(trn_scr, 2, 3),
+                            activations_sub=sub(model.to_activations(trn), 2, 3),
+                            chunked_trn_sub=sub(model.chunked_inference(audio, True), 2, 3),
+                            transcribe_shape=np.array(model.transcribe(audio).shape))
+
+
+def reference_function(path, class_name, func_name, extra_globals):
+    """A function of the reference, executed from its own source file WITHOUT importing the surrounding package (whose __init__
+    pulls in dependencies missing from the image): the def is cut out of the file's AST at run time and exec'd unmodified."""
+    import ast
+    src = open(path).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == class_name:
+            for item in node.body:
+                if isinstance(item, ast.FunctionDef) and item.name == func_name:
+                    item.decorator_list = []
+                    mod = ast.Module(body=[item], type_ignores=[])
+                    ns = dict(extra_globals)
+                    exec(compile(mod, path, 'exec'), ns)
+                    return ns[func_name]
+    raise KeyError(func_name)
+
+
+def make_frontend():
+    """tests/golden/frontend.npz: (a) AudioDataset.get_audio's arithmetic (datasets/AudioDataset.py:69-77) with the library calls the
+    reference makes (torch.mean, torchaudio.functional.resample, infinity-norm divide) on seeded multi-channel clips at several
+    source rates; (b) the reference's own PitchDataset.multi_pitch_to_activations (datasets/PitchDataset.py:233-307)."""
+    import scipy
+    import scipy.interpolate
+    import scipy.ndimage
+    import torchaudio
+    import warnings
+    install_stubs()
+    import librosa
+    rng = np.random.default_rng(17)
+    out = {}
+    for fs, ch in ((44100, 2), (48000, 1), (16000, 2), (22050, 3), (32000, 1)):
+        t = np.arange(int(0.25 * fs)) / fs
+        x = np.stack([np.sin(2 * np.pi * f0 * t + ph) for f0, ph in zip(rng.uniform(100, 3000, ch), rng.uniform(0, 6, ch))])
+        x = (x + 0.05 * rng.standard_normal(x.shape)).astype(np.float32) * 0.3
+        audio = torch.from_numpy(x)
+        a = torch.mean(audio, dim=0, keepdim=True)                       # AudioDataset.py:71
+        a = torchaudio.functional.resample(a, fs, 22050)                 # :73
+        if a.abs().max():                                                # :75-77
+            a /= a.abs().max()
+        out[f'audio_{fs}_{ch}'] = x
+        out[f'prepared_{fs}_{ch}'] = a.numpy()
+    fn = reference_function('/root/reference/timbre_trap/datasets/PitchDataset.py', 'PitchDataset', 'multi_pitch_to_activations',
+                            dict(np=np, scipy=scipy, filters=scipy.ndimage, librosa=librosa, warnings=warnings))
+    midi_freqs = 16.765 + np.arange(540) / 5.0                            # the base CQT's bin grid (cqtwrapper.py:48)
+    T = 200
+    multi_pitch = []
+    for i in range(T):
+        n = int(rng.integers(0, 5)) if i % 17 else 0
+        p = 440.0 * 2 ** ((rng.uniform(20, 120, n) - 69) / 12)
+        if i % 29 == 3:
+            p = np.concatenate([p, [0.0, 5.0, 30000.0]])                 # silence marker + out-of-range pitches
+        if i == 50:
+            p = np.concatenate([p, 440.0 * 2 ** ((midi_freqs[[0, 300, 301, 302, 539]] - 69) / 12)])   # edges + neighbours
+        multi_pitch.append(p)
+    P = max(len(p) for p in multi_pitch)
+    dense = np.zeros((T, P))
+    for i, p in enumerate(multi_pitch):
+        dense[i, :len(p)] = p
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        out['activations'] = fn(multi_pitch, midi_freqs)
+        out['activations_noblur'] = fn(multi_pitch, midi_freqs, 0)
+        out['activations_empty'] = fn([np.empty(0)] * 7, midi_freqs)
+    out['pitches_dense'] = dense
+    out['midi_freqs'] = midi_freqs
+    np.savez_compressed(os.path.join(GOLDEN, 'frontend.npz'), **out)
 
 
 def make_postproc():
@@ -212,5 +310,9 @@ def make_postproc():
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'postproc':
         make_postproc()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'variants':
+        make_variants()
+    elif len(sys.argv) > 1 and sys.argv[1] == 'frontend':
+        make_frontend()
     else:
         main()

@@ -142,3 +142,27 @@ def test_postprocessing_oracle_vs_reference_functions(golden_dir):
     same = (rng.random((30, 50)) < 0.1).astype(np.uint8)
     assert R.prf(*R.multipitch_counts(same, same, 0))[:2] == (1.0, 1.0)
     assert R.prf(*R.multipitch_counts(same, np.zeros_like(same), 2)) == (0.0, 0.0, 0.0)
+
+
+def test_model_variants_small(golden_dir):
+    """TimbreTrapFiLM / TimbreTrapMag / TimbreTrapMagDB (modules.py:780-1075): the oracle's variant functions against the reference's
+    own classes (scripts/make_golden.py variants), including the inherited chunk loop's two-channel broadcast quirk."""
+    import pytest
+    c = R.CQTRef(**{k: SMALL[k] for k in ('n_octaves', 'bins_per_octave', 'sample_rate', 'secs_per_block')})
+    for tag in ('film', 'mag', 'magdb'):
+        g = np.load(os.path.join(golden_dir, f'model_small_{tag}.npz'))
+        sd = R.init_state_dict(c.n_bins, 24, 2, seed=7, variant=tag)
+        if tag == 'film':
+            sd['skip_weights'] = torch.tensor([0.9, 1.1, 0.8, 1.2, 0.7])
+        audio = torch.from_numpy(g['audio'])
+        whole = c.pad_to_block_length(audio)
+        rec, lat, trn, trn_rec, trn_scr = R.forward_variant_ref(tag, whole, sd, c, consistency=True)
+        assert tuple(rec.shape) == tuple(g['out_shape']) and rec.shape[1] == (2 if tag == 'film' else 1)
+        _close(lat, g['latents'], rtol=2e-5)
+        for name, t in (('reconstruction', rec), ('transcription', trn), ('transcription_rec', trn_rec), ('transcription_scr', trn_scr)):
+            _close(_sub(t), g[name + '_sub'], rtol=2e-5)
+        _close(_sub(R.activations_variant_ref(tag, trn)), g['activations_sub'], rtol=2e-5)
+        ch = R.chunked_inference_variant_ref(tag, audio, sd, c, True)
+        _close(_sub(ch), g['chunked_trn_sub'], rtol=2e-5)
+        # transcribe() of the magnitude variants keeps the broadcast channel axis (reference quirk: squeeze(-3) of a 2-channel tensor)
+        assert len(g['transcribe_shape']) == (3 if tag == 'film' else 4)

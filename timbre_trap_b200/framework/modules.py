@@ -20,7 +20,8 @@ from . import ops
 from . import packing as P
 from .cqt import CQT
 
-__all__ = ['TimbreTrap', 'Encoder', 'Decoder', 'EncoderBlock', 'DecoderBlock', 'ResidualConv2dBlock', 'shard_block_range', 'shard_audio']
+__all__ = ['TimbreTrap', 'TimbreTrapFiLM', 'FiLM', 'TimbreTrapMag', 'TimbreTrapMagDB', 'Encoder', 'Decoder', 'EncoderBlock', 'DecoderBlock',
+           'ResidualConv2dBlock', 'shard_block_range', 'shard_audio']
 
 
 class _PackedCache:
@@ -211,9 +212,13 @@ class Encoder(nn.Module):
 
     def _packed(self):
         ci, cl = self.convin[0], self.convlat
-        return self._cache.get((ci.weight, ci.bias, cl.weight, cl.bias),
-                               lambda: (ci.weight.detach().float().contiguous(), ci.bias.detach().float().contiguous(),
-                                        P.pack_lat(cl.weight, self.latent_pad), P.pad_vec(cl.bias, self.latent_pad)))
+
+        def build():
+            w = ci.weight.detach().float()
+            if w.size(1) == 1:          # TimbreTrapMag / MagDB (modules.py:908-911): one input channel = pairs (x, 0) against (w, 0)
+                w = torch.cat((w, torch.zeros_like(w)), dim=1)
+            return w.contiguous(), ci.bias.detach().float().contiguous(), P.pack_lat(cl.weight, self.latent_pad), P.pad_vec(cl.bias, self.latent_pad)
+        return self._cache.get((ci.weight, ci.bias, cl.weight, cl.bias), build)
 
     def forward_c8(self, coeffs_bft2):
         """coeffs (B, F, T, 2) fp32 interleaved -> (latents C8 (B, Dp/8, 1, T, 8), [5 embeddings C8])."""
@@ -224,8 +229,11 @@ class Encoder(nn.Module):
         return ops.conv_lat(emb[-1], w_lat, b_lat, self.latent_pad), emb
 
     def forward(self, coefficients):
-        """Encoder.forward (modules.py:448-483): (B, 2, F, T) -> (latents (B, D, T), embeddings, {})."""
+        """Encoder.forward (modules.py:448-483): (B, 2, F, T) -> (latents (B, D, T), embeddings, {}); (B, 1, F, T) for the
+        magnitude variants, whose convin has one input channel."""
         _lib.require_cuda(coefficients, 'coefficients')
+        if coefficients.size(1) != self.convin[0].in_channels:
+            raise ValueError(f'expected {self.convin[0].in_channels} input channels, got {coefficients.size(1)}')
         with torch.no_grad():
             lat, emb = self.forward_c8(_interleave(coefficients))
             latents = P.from_c8(lat, self.latent_size).squeeze(-2)
@@ -261,6 +269,7 @@ class Decoder(nn.Module):
         self.packed4 = channels[4] <= 4 and channels[3] <= 8
         self.block4.set_packed4(self.packed4)
         self._cache = _PackedCache()
+        self._film = None           # set by TimbreTrapFiLM: the FiLM layer folded into convin's packed weights
 
     def _embeddings_internal(self, encoder_embeddings):
         """(B, C, H, T) encoder embeddings (API form) -> the internal layouts the decoder stages use."""
@@ -270,35 +279,67 @@ class Decoder(nn.Module):
         return out
 
     def _packed(self):
+        """((w_in[transcribe], w_in[reconstruct]), (bias table[transcribe], [reconstruct]), w_out, b_out)."""
         ci, co = self.convin[0], self.convout
-        def build():
-            w, tables = P.pack_deconv_in(ci.weight, ci.bias, self.latent_pad)
-            return w, tables, co.weight.detach().float().contiguous(), co.bias.detach().float().contiguous()
-        return self._cache.get((ci.weight, ci.bias, co.weight, co.bias), build)
+        film = self._film
+        params = (ci.weight, ci.bias, co.weight, co.bias)
+        if film is not None:
+            params += (film.gamma.weight, film.gamma.bias, film.beta.weight, film.beta.bias)
 
-    def last_stage_c8(self, lat_c8, reconstruct, skips=None, out=None):
+        def build():
+            if film is None:
+                w, tables = P.pack_deconv_in(ci.weight, ci.bias, self.latent_pad)
+                ws, tables = (w, w), (tables[0], tables[1])
+            else:
+                ws, tables = [], []
+                for transcribe in (True, False):
+                    # TimbreTrapFiLM.decode (modules.py:835-838): condition = one-hot [transcribe, not transcribe]
+                    cond = torch.tensor([float(transcribe), float(not transcribe)], dtype=film.gamma.weight.dtype, device=ci.weight.device)
+                    w, t = P.pack_deconv_in_film(ci.weight, ci.bias, film.gamma(cond), film.beta(cond), self.latent_pad)
+                    ws.append(w)
+                    tables.append(t)
+            w_out, b_out = co.weight.detach().float(), co.bias.detach().float()
+            if w_out.size(0) == 1:      # TimbreTrapMag / MagDB (modules.py:913): one output channel = channel 0 of the pair
+                w_out, b_out = torch.cat((w_out, torch.zeros_like(w_out)), dim=0), torch.cat((b_out, torch.zeros_like(b_out)))
+            return tuple(ws), tuple(tables), w_out.contiguous(), b_out.contiguous()
+        return self._cache.get(params, build)
+
+    def last_stage_c8(self, lat_c8, reconstruct, skips=None, out=None, convin=None):
         """Everything before `convout`: latents C8 (B, Dp/8, 1, T, 8) (without the indicator channel) -> the last stage's
         activations in their internal layout (packed4 (B, F, T, 4) for the supported channel plans), written to `out` if given."""
         w_in, tables, _, _ = self._packed()
-        x = ops.deconv_in(lat_c8, w_in, tables[1 if reconstruct else 0], P.pad8(self.channels[0]), self.embedding_size)
+        sw = 1 if reconstruct else 0
+        w_sel, t_sel = (w_in[sw], tables[sw]) if convin is None else convin
+        x = ops.deconv_in(lat_c8, w_sel, t_sel, P.pad8(self.channels[0]), self.embedding_size)
         blocks = (self.block1, self.block2, self.block3, self.block4)
         for i, blk in enumerate(blocks):
-            if skips is not None:
-                x = x + skips[-1 - i]
+            if skips is not None:                      # modules.py:568-585: x + weight * encoder embedding, one native pass, in place
+                x = _add_scaled(x, skips[-1 - i][1], skips[-1 - i][0], out=x)
             last = i == len(blocks) - 1
             x = blk.forward_c8(x, out=out if (last and skips is None) else None)
         if skips is not None:
-            x = torch.add(x, skips[0], out=out) if out is not None else x + skips[0]
+            x = _add_scaled(x, skips[0][1], skips[0][0], out=out if out is not None else x)
         return x
 
-    def forward_c8(self, lat_c8, reconstruct, skips=None):
+    def forward_c8(self, lat_c8, reconstruct, skips=None, convin=None):
         """latents C8 (B, Dp/8, 1, T, 8) (without the indicator channel) -> coefficients (B, F, T, 2) fp32 interleaved."""
         _, _, w_out, b_out = self._packed()
-        return ops.conv_out(self.last_stage_c8(lat_c8, reconstruct, skips), w_out, b_out, self.channels[4])
+        return ops.conv_out(self.last_stage_c8(lat_c8, reconstruct, skips, convin=convin), w_out, b_out, self.channels[4])
 
     def forward(self, latents, encoder_embeddings=None):
         """Decoder.forward (modules.py:545-594): latents (B, D+1, T) WITH the indicator channel -> (B, 2, F, T)."""
         _lib.require_cuda(latents, 'latents')
+        if self._film is not None:
+            # TimbreTrapFiLM: the decoder proper takes latents the FiLM layer has ALREADY been applied to and has no indicator channel
+            # (modules.py:838-840); model.decode() folds the layer into convin instead
+            with torch.no_grad():
+                ci = self.convin[0]
+                d = ci.weight.size(0)
+                plain = P.pack_deconv_in_film(ci.weight, ci.bias, torch.ones(d, device=latents.device), torch.zeros(d, device=latents.device),
+                                              self.latent_pad)
+                skips = None if encoder_embeddings is None else _unit_skips(self._embeddings_internal(encoder_embeddings))
+                pairs = self.forward_c8(_latents_to_c8(latents, self.latent_pad), True, skips, convin=plain)
+            return pairs.permute(0, 3, 1, 2)
         with torch.no_grad():
             flag = latents[:, -1]
             is_one, is_zero = bool((flag == 1).all()), bool((flag == 0).all())
@@ -306,16 +347,59 @@ class Decoder(nn.Module):
                 raise ValueError('the indicator channel must be all ones (reconstruct) or all zeros (transcribe), as '
                                  'TimbreTrap.decode builds it (modules.py:139-142)')
             lat = _latents_to_c8(latents[:, :-1], self.latent_pad)
-            skips = None if encoder_embeddings is None else self._embeddings_internal(encoder_embeddings)
-            return self.forward_c8(lat, is_one, skips).permute(0, 3, 1, 2)
+            skips = None if encoder_embeddings is None else _unit_skips(self._embeddings_internal(encoder_embeddings))
+            pairs = self.forward_c8(lat, is_one, skips)
+            return pairs.permute(0, 3, 1, 2) if self.convout.out_channels == 2 else pairs[..., :1].permute(0, 3, 1, 2)
+
+
+def _widen(x):
+    """(B, F, T) fp32 -> interleaved (B, F, T, 2) pairs (x, 0) (tt_widen_pairs)."""
+    x = x.detach().float().contiguous()
+    out = torch.empty(tuple(x.shape) + (2,), dtype=torch.float32, device=x.device)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().tt_widen_pairs(ctypes.c_void_p(x.data_ptr()), x.numel(), ctypes.c_void_p(out.data_ptr()),
+                                                 ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return out
+
+
+def _channel0(pairs, mode):
+    """interleaved (B, F, T, 2) -> (B, F, T): channel 0 through a non-linearity (tt_channel0_activation modes)."""
+    out = torch.empty(pairs.shape[:-1], dtype=torch.float32, device=pairs.device)
+    if out.numel():
+        with torch.cuda.device(pairs.device):
+            _lib.check(_lib.lib().tt_channel0_activation(ctypes.c_void_p(pairs.data_ptr()), out.numel(), mode, ctypes.c_void_p(out.data_ptr()),
+                                                         ctypes.c_void_p(torch.cuda.current_stream(pairs.device).cuda_stream)))
+    return out
+
+
+def _add_scaled(x, e, scale, out=None):
+    """x + scale * e on two bf16 tensors of one layout, one pass (tt_add_scaled_bf16); scale is a 0-dim device tensor."""
+    if x.shape != e.shape or x.dtype != torch.bfloat16 or e.dtype != torch.bfloat16:
+        raise ValueError(f'skip connection: {tuple(x.shape)} {x.dtype} vs {tuple(e.shape)} {e.dtype}')
+    out = torch.empty_like(x) if out is None else out
+    s = scale.detach().float().reshape(1)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().tt_add_scaled_bf16(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(e.contiguous().data_ptr()), ctypes.c_void_p(s.data_ptr()),
+                                                 ctypes.c_void_p(out.data_ptr()), x.numel(), ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)))
+    return out
 
 
 def _interleave(coefficients):
-    """(B, 2, F, T) real (any strides) -> contiguous (B, F, T, 2) fp32 (free for the CQT's own output)."""
+    """(B, 2, F, T) real (any strides) -> contiguous (B, F, T, 2) fp32 (free for the CQT's own output); a one-channel feature map
+    (B, 1, F, T) becomes pairs (x, 0)."""
+    if coefficients.size(1) == 1:
+        return _widen(coefficients[:, 0])
     c = coefficients.detach().permute(0, 2, 3, 1)
     if c.dtype != torch.float32:
         c = c.float()
     return c if c.is_contiguous() else c.contiguous()
+
+
+def _unit_skips(embeddings_internal):
+    """Already-weighted embeddings (the API form of Decoder.forward / TimbreTrap.decode) as (weight 1, embedding) pairs."""
+    one = torch.ones((), dtype=torch.float32, device=embeddings_internal[0].device)
+    return [(one, e) for e in embeddings_internal]
 
 
 def _latents_to_c8(latents, latent_pad):
@@ -400,20 +484,39 @@ class TimbreTrap(nn.Module):
 
     # ---- C8 fast paths -----------------------------------------------------------------------------
     def _skips_c8(self, emb):
+        """apply_skip_connections (modules.py:95-117) for the internal layouts: (learnable weight, embedding) pairs - the product is
+        formed inside the one-pass add kernel (tt_add_scaled_bf16)."""
         if self.skip_weights is None:
             return None
-        return [(self.skip_weights[i].to(torch.bfloat16) * e) for i, e in enumerate(emb)]
+        return [(self.skip_weights[i], e) for i, e in enumerate(emb)]
+
+    def _features(self, audio):
+        """audio (B, 1, n*L) -> the encoder's input as interleaved (B, F, T, 2) fp32: the CQT coefficients (modules.py:88)."""
+        return self.sliCQ.encode_interleaved(audio)
+
+    # output head of the variant (tt_channel0_activation mode; None = the two-channel coefficients as they are)
+    HEAD_MODE = None
+
+    def _head(self, pairs):
+        """decoder output (B, F, T, 2) interleaved -> what `decode` returns: (B, 2, F, T) view, or (B, 1, F, T) for the magnitude variants."""
+        if self.HEAD_MODE is None:
+            return pairs.permute(0, 3, 1, 2)
+        return _channel0(pairs, self.HEAD_MODE).unsqueeze(1)
 
     def _codes(self, audio):
         """audio (B, 1, n*L) -> (latents C8, skips C8 or None)."""
-        lat, emb = self.encoder.forward_c8(self.sliCQ.encode_interleaved(audio))
+        lat, emb = self.encoder.forward_c8(self._features(audio))
         return lat, self._skips_c8(emb)
 
     # ---- reference API -------------------------------------------------------------------------------
     def encode(self, audio):
         """modules.py:67-93."""
-        coefficients = self.sliCQ(audio)
-        return self.encoder(coefficients)
+        _lib.require_cuda(audio, 'audio')
+        with torch.no_grad():
+            lat, emb = self.encoder.forward_c8(self._features(audio))
+            latents = P.from_c8(lat, self.encoder.latent_size).squeeze(-2)
+            embeddings = [P.from_p4(e, c) if e.dim() == 4 else P.from_c8(e, c) for e, c in zip(emb, self.encoder.channels)]
+        return latents, embeddings, dict()
 
     def apply_skip_connections(self, embeddings):
         """modules.py:95-117."""
@@ -426,14 +529,14 @@ class TimbreTrap(nn.Module):
         _lib.require_cuda(latents, 'latents')
         with torch.no_grad():
             lat = _latents_to_c8(latents, self.decoder.latent_pad)
-            skips = None if embeddings is None else self.decoder._embeddings_internal(embeddings)
-            return self.decoder.forward_c8(lat, not transcribe, skips).permute(0, 3, 1, 2)
+            skips = None if embeddings is None else _unit_skips(self.decoder._embeddings_internal(embeddings))
+            return self._head(self.decoder.forward_c8(lat, not transcribe, skips))
 
     def _inference(self, audio, transcribe=False):
         """modules.py:149-177."""
         with torch.no_grad():
             lat, skips = self._codes(audio)
-            return self.decoder.forward_c8(lat, not transcribe, skips).permute(0, 3, 1, 2)
+            return self._head(self.decoder.forward_c8(lat, not transcribe, skips))
 
     def inference(self, audio, transcribe=False):
         """modules.py:179-202."""
@@ -476,7 +579,7 @@ class TimbreTrap(nn.Module):
             chunks, n_chunks = self._chunks(audio.detach().float(), prepadded)
             n_out = (n_chunks - 1) * (M // 2)
             window = self._window(audio.device)
-            fused = self.FUSE_CONVOUT_CROSSFADE and self.decoder.packed4 and M % 8 == 0
+            fused = self.FUSE_CONVOUT_CROSSFADE and self.decoder.packed4 and M % 8 == 0 and self.HEAD_MODE is None
             wants = (want_transcription, want_reconstruction)
             if fused:
                 stages = [torch.empty((B * n_chunks, F, M, 4), dtype=torch.bfloat16, device=audio.device) if w else None for w in wants]
@@ -491,13 +594,19 @@ class TimbreTrap(nn.Module):
                     if fused:
                         self.decoder.last_stage_c8(lat, reconstruct, skips, out=stage[c0:c0 + step])
                     else:
-                        stage[c0:c0 + step] = self.decoder.forward_c8(lat, reconstruct, skips)
+                        y = self.decoder.forward_c8(lat, reconstruct, skips)
+                        if self.HEAD_MODE is not None:
+                            # the reference's loop adds the variant's ONE output channel into its hard-coded two-channel buffer
+                            # (modules.py:244, 259-263): broadcast, i.e. both channels carry the head's output
+                            y = _channel0(y, self.HEAD_MODE).unsqueeze(-1).expand(-1, -1, -1, 2)
+                        stage[c0:c0 + step] = y
             _, _, w_out, b_out = self.decoder._packed()
             results = []
-            for stage, as_act in zip(stages, (activations, False)):
+            for stage, want_act in zip(stages, (activations, False)):
                 if stage is None:
                     results.append(None)
                     continue
+                as_act = want_act and self.HEAD_MODE is None         # the fused tanh|.| is the BASE model's to_activations
                 if as_act:
                     res = torch.empty((B, F, n_out), dtype=torch.float32, device=audio.device)
                     args = (None, ctypes.c_void_p(res.data_ptr()))
@@ -513,6 +622,8 @@ class TimbreTrap(nn.Module):
                     else:
                         _lib.check(_lib.lib().tt_chunk_crossfade(ctypes.c_void_p(stage.data_ptr()), ctypes.c_void_p(window.data_ptr()),
                                                                  B, n_chunks, F, M, args[0], args[1], stream))
+                if want_act and not as_act:
+                    res = self.to_activations(res.permute(0, 3, 1, 2))       # a variant's own activation function
                 results.append(res)
             return results
 
@@ -600,14 +711,123 @@ class TimbreTrap(nn.Module):
         """modules.py:338-393 (inference semantics; the training step with gradients is framework.train_step)."""
         with torch.no_grad():
             lat, skips = self._codes(audio)
-            reconstruction = self.decoder.forward_c8(lat, True, skips)
-            transcription = self.decoder.forward_c8(lat, False, skips)
+            reconstruction = self._head(self.decoder.forward_c8(lat, True, skips))
+            transcription = self._head(self.decoder.forward_c8(lat, False, skips))
             transcription_rec = transcription_scr = None
             if consistency:
-                lat_t, emb_t = self.encoder.forward_c8(transcription)
+                lat_t, emb_t = self.encoder.forward_c8(_interleave(transcription))
                 skips_t = self._skips_c8(emb_t)
-                transcription_rec = self.decoder.forward_c8(lat_t, True, skips_t).permute(0, 3, 1, 2)
-                transcription_scr = self.decoder.forward_c8(lat_t, False, skips_t).permute(0, 3, 1, 2)
+                transcription_rec = self._head(self.decoder.forward_c8(lat_t, True, skips_t))
+                transcription_scr = self._head(self.decoder.forward_c8(lat_t, False, skips_t))
             latents = P.from_c8(lat, self.encoder.latent_size).squeeze(-2)
-        return (reconstruction.permute(0, 3, 1, 2), latents, transcription.permute(0, 3, 1, 2), transcription_rec,
-                transcription_scr, dict())
+        return reconstruction, latents, transcription, transcription_rec, transcription_scr, dict()
+
+    # ---- full-track forward in time tiles (experiments/evaluate.py:81-95 feeds whole tracks through model(audio)) -------------------
+    # Only the convolutions see across frames, and only +-1 frame (convin / convout) and +-6 frames per block of three dilated
+    # residual stages: +-25 frames per encoder or decoder pass, +-50 for the outputs of forward(), +-100 for the consistency pair.
+    TILE_HALO = 128
+
+    def forward_tiled(self, audio, consistency=False, tile_frames=32768):
+        """
+        TimbreTrap.forward (modules.py:338-393) on a track of any length with bounded activation memory: the CQT runs over the whole
+        track (blocks are independent), the encoder / decoder passes over tiles of `tile_frames` frames plus TILE_HALO frames of true
+        context on either side, of which only the tile's own frames are kept.  Same outputs as forward(), bit for bit
+        (tests/test_model_gpu.py::test_forward_tiled_equals_untiled).
+        """
+        if tile_frames % 128 or tile_frames <= 0:
+            raise ValueError('tile_frames must be a positive multiple of 128')
+        with torch.no_grad():
+            feats = self._features(audio)                                   # (B, F, T, 2)
+            B, F, T, _ = feats.shape
+            h = self.TILE_HALO
+            n_out = 2 if self.HEAD_MODE is None else 1
+            outs = [torch.empty((B, n_out, F, T), dtype=torch.float32, device=feats.device) for _ in range(4 if consistency else 2)]
+            latents = torch.empty((B, self.encoder.latent_size, T), dtype=torch.float32, device=feats.device)
+            for t0 in range(0, T, tile_frames):
+                t1 = min(T, t0 + tile_frames)
+                a, b = max(0, t0 - h), min(T, t1 + h)
+                keep = slice(t0 - a, t0 - a + (t1 - t0))
+                lat, emb = self.encoder.forward_c8(feats[:, :, a:b].contiguous())
+                skips = self._skips_c8(emb)
+                rec = self._head(self.decoder.forward_c8(lat, True, skips))
+                trn = self._head(self.decoder.forward_c8(lat, False, skips))
+                outs[0][..., t0:t1] = rec[..., keep]
+                outs[1][..., t0:t1] = trn[..., keep]
+                latents[..., t0:t1] = P.from_c8(lat, self.encoder.latent_size).squeeze(-2)[..., keep]
+                if consistency:
+                    lat_t, emb_t = self.encoder.forward_c8(_interleave(trn))
+                    skips_t = self._skips_c8(emb_t)
+                    outs[2][..., t0:t1] = self._head(self.decoder.forward_c8(lat_t, True, skips_t))[..., keep]
+                    outs[3][..., t0:t1] = self._head(self.decoder.forward_c8(lat_t, False, skips_t))[..., keep]
+        return outs[0], latents, outs[1], (outs[2] if consistency else None), (outs[3] if consistency else None), dict()
+
+
+class FiLM(nn.Module):
+    """modules.py:842-889: y = x * gamma(condition) + beta(condition) per latent channel.  Parameter holder here - the layer is folded
+    into the packed weights / bias table of decoder.convin (packing.pack_deconv_in_film); `forward` is the reference arithmetic on
+    whatever device the tensors live (a (B, D, T) latent tensor, cheap) for callers that use the layer on its own."""
+
+    def __init__(self, embedding_size, n_conditions):
+        super().__init__()
+        self.gamma = nn.Linear(n_conditions, embedding_size)
+        self.beta = nn.Linear(n_conditions, embedding_size)
+
+    def forward(self, x, condition):
+        return (x.transpose(-1, -2) * self.gamma(condition) + self.beta(condition)).transpose(-1, -2)
+
+
+class TimbreTrapFiLM(TimbreTrap):
+    """modules.py:780-840: the switch is a FiLM layer on the latents instead of an indicator channel.  `latent_size` must be given
+    (the reference's `latent_size=None` branch reads `nn.Sequential.in_channels`, which does not exist, modules.py:799)."""
+
+    def __init__(self, sample_rate, n_octaves, bins_per_octave, secs_per_block=3, latent_size=None, model_complexity=1, skip_connections=False):
+        TimbreTrap.__init__(self, sample_rate, n_octaves, bins_per_octave, secs_per_block, latent_size, model_complexity, skip_connections)
+        if latent_size is None:
+            raise ValueError('TimbreTrapFiLM needs an explicit latent_size (so does the reference: modules.py:799 fails without one)')
+        old = self.decoder.convin[0]
+        self.decoder.convin = nn.Sequential(nn.ConvTranspose2d(latent_size, old.out_channels, kernel_size=old.kernel_size), nn.ELU(inplace=True))
+        self.film_layer = FiLM(latent_size, n_conditions=2)
+        # not a registered sub-module of the decoder (state_dict keys stay the reference's: film_layer.* at the top level only)
+        object.__setattr__(self.decoder, '_film', self.film_layer)
+
+    def __setstate__(self, state):
+        super().__setstate__(state)
+        object.__setattr__(self.decoder, '_film', self.film_layer)
+
+
+class TimbreTrapMag(TimbreTrap):
+    """modules.py:892-1001: magnitude-CQT variant - one-channel encoder input |c|, one-channel relu output, tanh activations."""
+
+    HEAD_MODE = 1               # relu (modules.py:976)
+
+    def __init__(self, sample_rate, n_octaves, bins_per_octave, secs_per_block=3, latent_size=None, model_complexity=1, skip_connections=False):
+        TimbreTrap.__init__(self, sample_rate, n_octaves, bins_per_octave, secs_per_block, latent_size, model_complexity, skip_connections)
+        c0 = self.encoder.convin[0].out_channels
+        cl = self.decoder.convout.in_channels
+        self.encoder.convin = nn.Sequential(nn.Conv2d(1, c0, kernel_size=3, padding='same'), nn.ELU(inplace=True))
+        self.decoder.convout = nn.Conv2d(cl, 1, kernel_size=3, padding='same')
+
+    def _features(self, audio):
+        """modules.py:947: to_magnitude(sliCQ(audio)) as pairs (|c|, 0)."""
+        return _widen(CQT._magnitude(self.sliCQ.encode_interleaved(audio).permute(0, 3, 1, 2), False))
+
+    def to_activations(self, coefficients):
+        """modules.py:980-1001: tanh of the (B, 1, F, T) magnitude coefficients -> (B, F, T).  Like the reference's `squeeze(-3)`, a
+        two-channel tensor (what the inherited chunk loop produces for this variant) keeps its channel axis."""
+        _lib.require_cuda(coefficients, 'coefficients')
+        return torch.tanh(coefficients.detach().float().squeeze(-3))
+
+
+class TimbreTrapMagDB(TimbreTrapMag):
+    """modules.py:1004-1075: decibel-magnitude variant - encoder input to_decibels(|c|) in [0, 1], sigmoid output, activations = output."""
+
+    HEAD_MODE = 2               # sigmoid (modules.py:1052)
+
+    def _features(self, audio):
+        """modules.py:1024-1027."""
+        mag = CQT._magnitude(self.sliCQ.encode_interleaved(audio).permute(0, 3, 1, 2), False)
+        return _widen(CQT.to_decibels(mag))
+
+    def to_activations(self, coefficients):
+        """modules.py:1056-1075."""
+        return coefficients.squeeze(-3)

@@ -12,7 +12,7 @@ The C8 planar activation layout is (B, ceil(C/8), H, T, 8) bf16.
 
 import torch
 
-__all__ = ['pack_down_pairs', 'pack_res_rs', 'pack_res_rs_pairs', 'pack_res_rs_fold', 'to_p4', 'from_p4', 'pack_down_strip', 'pack_up_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in',
+__all__ = ['pack_down_pairs', 'pack_res_rs', 'pack_res_rs_pairs', 'pack_res_rs_fold', 'to_p4', 'from_p4', 'pack_down_strip', 'pack_up_strip', 'pad8', 'to_c8', 'from_c8', 'pack_res3x3', 'pack_res1x1', 'pack_down', 'pack_up', 'pack_lat', 'pack_deconv_in', 'pack_deconv_in_film',
            'pad_vec']
 
 
@@ -129,6 +129,24 @@ def pack_deconv_in(w, b, latent_pad):
     bias = torch.zeros((2, H0, N), dtype=torch.float32, device=w.device)
     bias[0, :, :C0] = b.detach().float()[None, :]
     bias[1, :, :C0] = b.detach().float()[None, :] + wf[D].t()
+    return packed, bias
+
+
+def pack_deconv_in_film(w, b, gamma, beta, latent_pad):
+    """
+    decoder.convin of TimbreTrapFiLM (reference modules.py:801-809: ConvTranspose2d(D, C0, (H0, 1)), no indicator channel) with the
+    FiLM layer in front of it (modules.py:838-840: latents * gamma + beta per channel) FOLDED IN - the layer is linear in its input:
+        convin(gamma * z + beta) = (W scaled by gamma along its input channels) z  +  (bias + sum_d beta_d W[d])
+    w (D, C0, H0, 1), b (C0), gamma / beta (D) -> packed (H0, latent_pad/8, C0, 8) bf16 and the per-row bias table (H0, C0).
+    """
+    D, C0, H0 = w.shape[:3]
+    N = max(16, pad8(C0))
+    wf = w.detach().float()[..., 0]                      # (D, C0, H0)
+    k = torch.zeros((H0, N, latent_pad), dtype=torch.float32, device=w.device)
+    k[:, :C0, :D] = (wf * gamma.detach().float().view(-1, 1, 1)).permute(2, 1, 0)
+    packed = k.reshape(H0, N, latent_pad // 8, 8).permute(0, 2, 1, 3).contiguous().to(torch.bfloat16)
+    bias = torch.zeros((H0, N), dtype=torch.float32, device=w.device)
+    bias[:, :C0] = b.detach().float()[None, :] + torch.einsum('d,dch->hc', beta.detach().float(), wf)
     return packed, bias
 
 

@@ -348,8 +348,8 @@ def _decoder(dec, lat, reconstruct):
     ch = dec.channels
     w_in, tables, w_out, b_out = dec._packed()
     ci = dec.convin[0]
-    table = tables[1 if reconstruct else 0]
-    x = _IndicatorFn.apply(lat, ci.weight, ci.bias, lambda t: ops.deconv_in(t, w_in, table, P.pad8(ch[0]), dec.embedding_size),
+    sw = 1 if reconstruct else 0
+    x = _IndicatorFn.apply(lat, ci.weight, ci.bias, lambda t: ops.deconv_in(t, w_in[sw], tables[sw], P.pad8(ch[0]), dec.embedding_size),
                            1.0 if reconstruct else 0.0, dec.latent_size, ch[0])
     for i, blk in enumerate((dec.block1, dec.block2, dec.block3, dec.block4)):
         tc = blk.tconv[0]
