@@ -270,7 +270,10 @@ def make_frontend():
         if i % 29 == 3:
             p = np.concatenate([p, [0.0, 5.0, 30000.0]])                 # silence marker + out-of-range pitches
         if i == 50:
-            p = np.concatenate([p, 440.0 * 2 ** ((midi_freqs[[0, 300, 301, 302, 539]] - 69) / 12)])   # edges + neighbours
+            # the outermost bins (a hair inside the range: exactly ON the boundary the reference's own `>= lb` test hangs on the last
+            # bit of log2) and three neighbouring bins
+            edge = midi_freqs[[0, 300, 301, 302, 539]] + np.array([1e-6, 0, 0, 0, -1e-6])
+            p = np.concatenate([p, 440.0 * 2 ** ((edge - 69) / 12)])
         multi_pitch.append(p)
     P = max(len(p) for p in multi_pitch)
     dense = np.zeros((T, P))

@@ -58,7 +58,9 @@ def test_multi_pitch_to_activations_vs_golden(golden_dir):
     dense, freqs = g['pitches_dense'], g['midi_freqs']
     for blur, key in ((2.5, 'activations'), (0, 'activations_noblur')):
         got = FE.multi_pitch_to_activations(torch.from_numpy(dense).cuda(), freqs, blur).cpu().numpy()
-        assert got.shape == g[key].shape and np.abs(got - g[key]).max() < 1e-6, (key, np.abs(got - g[key]).max())
+        err = np.abs(got - g[key])
+        assert got.shape == g[key].shape and err.max() < 1e-6, (key, err.max(), np.unravel_index(err.argmax(), err.shape),
+                                                                 got.flat[err.argmax()], g[key].flat[err.argmax()])
         assert np.array_equal(got == 1.0, g[key] == 1.0)                       # the exact ones the transcription loss keys on (objectives.py:65)
     listed = FE.multi_pitch_to_activations([row[row != 0] for row in dense], freqs, device='cuda').cpu().numpy()
     assert np.abs(listed - g['activations']).max() < 1e-6
