@@ -239,6 +239,23 @@ int tt_conv_bwd_data_f32(const float* dz, const float* w, float* dx, int B, int 
                          int KH, int KW, int sh, int dh, int dw, int ph, int pw, int hout_override, void* stream);
 int tt_conv_bwd_weight_f32(const float* x, const float* dz, float* dw, float* db, int B, int Cin, int Hin, int T, int Cout,
                            int KH, int KW, int sh, int dh, int dw_, int ph, int pw, int hout_override, void* stream);
+/*
+ * Tensor-core weight gradients of the residual blocks' 'same' convolutions, straight from the inference layouts: x, dz C8 planar bf16
+ * (B, C/8, H, T, 8) with the PADDED channel counts Cin / Cout (8, 16 or 32); dw (cout_real, cin_real, k, k) fp32 and db (cout_real)
+ * fp32 (db may be NULL) are ACCUMULATED into.  k = 3 (dilation 1..3, zero padding = dilation) or k = 1.  The GEMM's K axis is the
+ * pixel axis: both operands are MN-major tcgen05 operands read from the rows the TMA brings in; per-CTA partial sums go through
+ * `scratch` (tt_wgrad_scratch_floats(B, H, T) floats) and are reduced in a fixed order (bit-reproducible).
+ */
+int64_t tt_wgrad_scratch_floats(int B, int H, int T);
+int tt_conv_wgrad_same(const void* x, const void* dz, float* dw, float* db, int B, int Cin, int Cout, int cin_real, int cout_real,
+                       int H, int T, int k, int dilation, float* scratch, void* stream);
+/* element-wise pieces of the backward pass on bf16 tensors of any common layout (n elements, multiple of 8):
+ * dz = gy * ELU'(z) through the activated output a;  residual block: dz = gy * ELU'(z2) with the activated 1x1 output = y - x */
+int tt_elu_bwd_bf16(const void* gy, const void* a, void* dz, int64_t n, void* stream);
+int tt_res_out_bwd_bf16(const void* gy, const void* y, const void* x, void* dz, int64_t n, void* stream);
+/* packed 4-channel (B, H, T, 4) <-> C8 planar with one channel group (B, 1, H, T, 8), n_pixels = B * H * T */
+int tt_p4_to_c8(const void* p4, void* c8, int64_t n_pixels, void* stream);
+int tt_c8_to_p4(const void* c8, void* p4, int64_t n_pixels, void* stream);
 /* db[c] += sum over (b, h, t) of dz (B, C, hw): the bias gradient of the transposed layers */
 int tt_channel_sum(const float* dz, float* db, int B, int C, int64_t hw, void* stream);
 /* dz = dy * ELU'(z), through the activated output a: ELU'(z) = 1 if a > 0 else a + 1 */

@@ -147,3 +147,27 @@ def test_training_reduces_the_loss():
         last = ts.step(audio.cuda(), gt.cuda())
     assert float(last['total']) < 0.8 * first, (first, float(last['total']))
     assert np.isfinite(float(last['grad_norm']))
+
+
+@pytest.mark.parametrize('C,H,T,k,d,B', [(4, 23, 256, 3, 1, 2), (8, 17, 384, 3, 2, 1), (16, 33, 200, 3, 3, 2), (32, 9, 128, 3, 1, 3), (32, 40, 512, 1, 1, 1),
+                                           (3, 11, 136, 1, 1, 2), (16, 300, 128, 3, 2, 1)])
+def test_tensor_core_weight_gradient(C, H, T, k, d, B):
+    """tt_conv_wgrad_same (MN-major tcgen05 GEMM over the pixel axis, deterministic two-stage reduction) against torch autograd on the
+    same bf16-rounded operands; products of bf16 values are exact in fp32, so only the summation order differs."""
+    import torch.nn.functional as F
+    from timbre_trap_b200.framework import packing as P, train as TR
+    g = torch.Generator().manual_seed(C * 100 + H)
+    x = torch.randn((B, C, H, T), generator=g).to(torch.bfloat16).float()
+    dz = (torch.randn((B, C, H, T), generator=g) * 0.1).to(torch.bfloat16).float()
+    w = torch.zeros((C, C, k, k), requires_grad=True)
+    bias = torch.zeros(C, requires_grad=True)
+    pad = d if k == 3 else 0
+    y = F.conv2d(x, w, bias, padding=pad, dilation=d if k == 3 else 1)
+    (y * dz).sum().backward()
+    dw, db = TR._wgrad_same(P.to_c8(x.cuda()), P.to_c8(dz.cuda()), C, C, k, d)
+    assert dw.shape == w.grad.shape
+    scale = float(w.grad.abs().max())
+    assert float((dw.cpu() - w.grad).abs().max()) <= 2e-4 * scale + 1e-4, (float((dw.cpu() - w.grad).abs().max()), scale)
+    assert float((db.cpu() - bias.grad).abs().max()) <= 2e-4 * float(bias.grad.abs().max()) + 1e-4
+    dw2, db2 = TR._wgrad_same(P.to_c8(x.cuda()), P.to_c8(dz.cuda()), C, C, k, d)
+    assert torch.equal(dw, dw2) and torch.equal(db, db2)                  # fixed reduction order: bit-reproducible

@@ -156,10 +156,6 @@ rows_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ S, FftSpec sp
 //       B[m0][n0] *= w1024^{(m0 + pp) n0}
 //       c[n0 + 32 n1] = sum_{m0} B[m0][n0] w32^{m0 n1}             (after a 32x32 transpose through smem)
 // ---------------------------------------------------------------------------------------------
-// The w1024 table is read with a lane stride of n0 (or lane): power-of-two strides would pile the 16 lanes of a half-warp onto a
-// few bank pairs.  Storing entry i at i ^ ((i >> 4) & 15) spreads every such stride over all 16 bank pairs.
-__device__ __forceinline__ int tw_swz(int i) { return i ^ ((i >> 4) & 15); }
-
 struct BinTables {
     const int* start;
     const int* length;
@@ -203,16 +199,15 @@ __device__ __forceinline__ void bin_fwd_stage1(const float2* __restrict__ spec_t
     }
 }
 
-__global__ void __launch_bounds__(kBinWarps * 32)
+__global__ void __launch_bounds__(kBinWarps * 32, 6)
 bins_fwd_kernel(const float2* __restrict__ S, float* __restrict__ coeffs, BinTables tab, int F, int SP,
                 int n_blocks_item, int block0, int n_blocks_launch, const float2* __restrict__ tw_m) {
     constexpr int M = 1024;
     extern __shared__ float2 smem[];
-    float2* tw = smem;                       // 1024 entries, exp(+2 pi i k / 1024)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2* tile = smem + M + warp * (32 * 33);
-    for (int i = threadIdx.x; i < M; i += blockDim.x) tw[tw_swz(i)] = tw_m[i];
-    __syncthreads();
+    float2* tile = smem + warp * (32 * 33);
+    // exp(+2 pi i k / 1024): five reads per transform, straight from the 8 KB global table (L1-resident) - no shared-memory copy, so
+    // six 4-warp CTAs fit an SM
 
     const long long w = (long long)blockIdx.x * kBinWarps + warp;
     if (w >= (long long)n_blocks_launch * F) return;
@@ -236,12 +231,18 @@ bins_fwd_kernel(const float2* __restrict__ S, float* __restrict__ coeffs, BinTab
     else if (rows <= 16) bin_fwd_stage1<16>(taps, win, len, shift, lane, B);
     else bin_fwd_stage1<32>(taps, win, len, shift, lane, B);
 
-    // twiddle w1024^{(m0 + pp) n0} and transpose
+    // twiddle w1024^{(m0 + pp) n0} and transpose.  The factors of one lane are a geometric sequence in n0: re-seeded from the table
+    // every 8 steps and advanced by one complex multiply in between (4 table reads instead of 32; error <= 8 roundings)
     const int base = (lane + pp) & (M - 1);
+    const float2 w1 = __ldg(tw_m + base);
 #pragma unroll
-    for (int n0 = 0; n0 < 32; ++n0) {
-        const float2 t = tw[tw_swz((base * n0) & (M - 1))];
-        tile[n0 * 33 + lane] = cmul(B[n0], t);
+    for (int n0 = 0; n0 < 32; n0 += 8) {
+        float2 t = __ldg(tw_m + ((base * n0) & (M - 1)));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            tile[(n0 + q) * 33 + lane] = (n0 + q == 0) ? B[0] : cmul(B[n0 + q], t);
+            if (q < 7) t = cmul(t, w1);
+        }
     }
     __syncwarp();
     float2 E[32];
@@ -277,30 +278,25 @@ __device__ __forceinline__ void bin_inv_stage3(float2 (&E)[32], float2* __restri
         for (int q = 0; q < Z; ++q) t[q] = E[D * q + r];
         if constexpr (Z > 1) fft_reg_dif<Z, -1>(t);
 #pragma unroll
-        for (int m1 = 0; m1 < Z; ++m1) C[m1] = cadd(C[m1], mul_tw32<-1>(t[brev<Z>(m1)], m1 * r));
+        for (int m1 = 0; m1 < Z; ++m1) C[m1] = cadd2(C[m1], mul_tw32<-1>(t[brev<Z>(m1)], m1 * r));
     }
 #pragma unroll
     for (int m1 = 0; m1 < Z; ++m1) {
         const int i = 32 * m1 + lane - shift;
         if (i >= 0 && i < len) {
             const float w = __ldg(dual + i);
-            float* dst = reinterpret_cast<float*>(spec_taps + i);
-            atomicAdd(dst, C[m1].x * w);
-            atomicAdd(dst + 1, C[m1].y * w);
+            atomicAdd(spec_taps + i, make_float2(C[m1].x * w, C[m1].y * w));      // one 64-bit vector reduction (sm_90+)
         }
     }
 }
 
-__global__ void __launch_bounds__(kBinWarps * 32)
+__global__ void __launch_bounds__(kBinWarps * 32, 6)
 bins_inv_kernel(const float* __restrict__ coeffs, float2* __restrict__ S, BinTables tab, int F, int SP,
                 int n_blocks_item, int block0, int n_blocks_launch, const float2* __restrict__ tw_m) {
     constexpr int M = 1024;
     extern __shared__ float2 smem[];
-    float2* tw = smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float2* tile = smem + M + warp * (32 * 33);
-    for (int i = threadIdx.x; i < M; i += blockDim.x) tw[tw_swz(i)] = tw_m[i];
-    __syncthreads();
+    float2* tile = smem + warp * (32 * 33);
 
     const long long w = (long long)blockIdx.x * kBinWarps + warp;
     if (w >= (long long)n_blocks_launch * F) return;
@@ -320,10 +316,16 @@ bins_inv_kernel(const float* __restrict__ coeffs, float2* __restrict__ S, BinTab
     const int pp = first & ~31;
     const int shift = first - pp;
     const int rows = (shift + len + 31) >> 5;
+    // twiddle w1024^{-(m0 + pp) n0}, n0 = lane: geometric in m0 with ratio w1024^{lane}, re-seeded every 8 steps (see bins_fwd)
+    const float2 wl = __ldg(tw_m + lane);
 #pragma unroll
-    for (int m0 = 0; m0 < 32; ++m0) {
-        const float2 t = tw[tw_swz((((m0 + pp) & (M - 1)) * lane) & (M - 1))];
-        tile[m0 * 33 + lane] = cmulc(v[brev<32>(m0)], t);
+    for (int m0 = 0; m0 < 32; m0 += 8) {
+        float2 t = __ldg(tw_m + ((((m0 + pp) & (M - 1)) * lane) & (M - 1)));
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            tile[(m0 + q) * 33 + lane] = cmulc(v[brev<32>(m0 + q)], t);
+            if (q < 7) t = cmul(t, wl);
+        }
     }
     __syncwarp();
     float2 E[32];
@@ -398,10 +400,7 @@ bins_inv_generic_kernel(const float* __restrict__ coeffs, float2* __restrict__ S
     float2* taps = S + (size_t)lb * SP + tab.start[k];
     const float* dual = tab.dual + tab.offset[k];
     for (int t = tid; t < len; t += 128) {
-        const float2 v = cscale(C[first + t], dual[t]);
-        float* dst = reinterpret_cast<float*>(taps + t);
-        atomicAdd(dst, v.x);
-        atomicAdd(dst + 1, v.y);
+        atomicAdd(taps + t, cscale(C[first + t], dual[t]));
     }
 }
 
@@ -639,7 +638,7 @@ static int upload(T** dst, const T* src, size_t count) {
 
 static size_t cols_smem(const tt_cqt_plan* p) { return ((size_t)kColsPerCta * p->N1 + p->N1) * sizeof(float2); }
 static size_t rows_smem(const tt_cqt_plan* p) { return ((size_t)2 * kRowsPerCta * p->N2 + p->N2) * sizeof(float2); }
-static size_t bins_smem() { return ((size_t)1024 + kBinWarps * 32 * 33) * sizeof(float2); }
+static size_t bins_smem() { return ((size_t)kBinWarps * 32 * 33) * sizeof(float2); }
 
 extern "C" int tt_cqt_plan_create(tt_cqt_plan** out, int block_length, int n_bins, int max_window_length,
                                   const int32_t* start, const int32_t* length, const int32_t* first,

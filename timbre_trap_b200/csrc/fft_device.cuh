@@ -277,8 +277,8 @@ __device__ __forceinline__ void fft_reg_dif(float2 (&v)[N]) {
 #pragma unroll
             for (int j = 0; j < half; ++j) {
                 float2 a = v[base + j], b = v[base + j + half];
-                v[base + j] = cadd(a, b);
-                v[base + j + half] = mul_tw32<SIGN>(csub(a, b), j * (16 / half));
+                v[base + j] = cadd2(a, b);
+                v[base + j + half] = mul_tw32<SIGN>(csub2(a, b), j * (16 / half));
             }
         }
     }

@@ -75,12 +75,12 @@ constexpr int kMaxBinWords = 32;      // up to 1024 frequency bins
 __global__ void rasterise_kernel(const double* __restrict__ pitches_hz, int T, int P, const double* __restrict__ midi_freqs, int F,
                                  const float* __restrict__ blur, int R, float* __restrict__ act, unsigned int* __restrict__ min_bits) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= T) return;
+    const bool live = t < T;                        // no early exit: every lane takes part in the warp reduction below
     unsigned int bits[kMaxBinWords];
 #pragma unroll
     for (int i = 0; i < kMaxBinWords; ++i) bits[i] = 0u;
     const double lb = midi_freqs[0], ub = midi_freqs[F - 1];
-    for (int p = 0; p < P; ++p) {
+    for (int p = 0; live && p < P; ++p) {
         const double hz = pitches_hz[(size_t)t * P + p];
         if (!(hz != 0.0)) continue;                                     // zeros are "no pitch" (PitchDataset.py:263)
         const double midi = 12.0 * (log2(hz) - log2(440.0)) + 69.0;     // librosa.hz_to_midi
@@ -95,7 +95,7 @@ __global__ void rasterise_kernel(const double* __restrict__ pitches_hz, int T, i
         bits[lo >> 5] |= 1u << (lo & 31);
     }
     float mn = __int_as_float(0x7f800000);
-    for (int f = 0; f < F; ++f) {
+    for (int f = 0; live && f < F; ++f) {
         float v = 0.f;
         for (int r = -R; r <= R; ++r) {
             const int q = f + r;

@@ -43,6 +43,9 @@ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
 __device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// packed f32x2 forms (sm_100: one FADD2 / FFMA2 per complex add / subtract instead of two scalar FADDs) - bit-identical results
+__device__ __forceinline__ float2 cadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
 // multiply by +i / -i
 __device__ __forceinline__ float2 cmul_i(float2 a) { return make_float2(-a.y, a.x); }
 __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }

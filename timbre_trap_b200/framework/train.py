@@ -202,8 +202,56 @@ def _conv_same_hi_lo(dz, wp, c, k, d):
     return (P.from_c8(ops.conv_same(hi, wp, None, k, d), c) + P.from_c8(ops.conv_same(lo, wp, None, k, d), c)).contiguous()
 
 
+# ---- residual blocks: the whole backward in the inference layouts (bf16), convolutions AND weight gradients on the tensor cores ----
+def _ew(fn_name, *tensors):
+    """element-wise bf16 kernel over tensors of one common layout -> new tensor like the first"""
+    out = torch.empty_like(tensors[0])
+    _lib.check(getattr(_lib.lib(), fn_name)(*[_p(t) for t in tensors], _p(out), out.numel(), _s(out)))
+    return out
+
+
+def _as_c8(t):
+    """packed 4-channel (B, H, T, 4) -> C8 planar (B, 1, H, T, 8) (native re-layout kernel); C8 tensors pass through"""
+    if t.dim() == 5:
+        return t
+    B, H, T, _ = t.shape
+    out = torch.empty((B, 1, H, T, 8), dtype=torch.bfloat16, device=t.device)
+    _lib.check(_lib.lib().tt_p4_to_c8(_p(t), _p(out), B * H * T, _s(t)))
+    return out
+
+
+def _to_layout_of(c8, ref):
+    """C8 planar (B, 1, H, T, 8) -> the layout of `ref` (packed 4-channel or C8)"""
+    if ref.dim() == 5:
+        return c8
+    out = torch.empty_like(ref)
+    _lib.check(_lib.lib().tt_c8_to_p4(_p(c8), _p(out), out.numel() // 4, _s(out)))
+    return out
+
+
+_WGRAD_SCRATCH = {}
+
+
+def _wgrad_same(x8, dz8, cin, cout, k, d):
+    """(dW (cout, cin, k, k), db (cout)) fp32 of a 'same' conv from C8 planar bf16 x and dz (tt_conv_wgrad_same, tensor cores)."""
+    B, CGi, H, T, _ = x8.shape
+    lib = _lib.lib()
+    n = int(lib.tt_wgrad_scratch_floats(B, H, T))
+    key = (x8.device, n)
+    if key not in _WGRAD_SCRATCH:
+        _WGRAD_SCRATCH.clear()
+        _WGRAD_SCRATCH[key] = torch.empty(n, dtype=torch.float32, device=x8.device)
+    dw = torch.zeros((cout, cin, k, k), dtype=torch.float32, device=x8.device)
+    db = torch.zeros(cout, dtype=torch.float32, device=x8.device)
+    _lib.check(lib.tt_conv_wgrad_same(_p(x8), _p(dz8), _p(dw), _p(db), B, CGi * 8, dz8.size(1) * 8, cin, cout, H, T, k, d,
+                                      _p(_WGRAD_SCRATCH[key]), _s(x8)))
+    return dw, db
+
+
 class _ResFn(torch.autograd.Function):
-    """ResidualConv2dBlock: fused forward kernel; backward recomputes the inner activation and chains the generic kernels."""
+    """ResidualConv2dBlock: fused forward kernel; the backward stays in bf16 C8 planar end to end - recompute of the inner activation
+    and both data-gradient convolutions through the tile kernel (tt_conv_same), both weight gradients through the MN-major tcgen05
+    kernel (tt_conv_wgrad_same), the ELU derivatives / residual add as one-pass element-wise kernels.  No NCHW fp32 round trips."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, run, c, d):
@@ -216,22 +264,20 @@ class _ResFn(torch.autograd.Function):
     def backward(ctx, gy):
         x, y, w1, b1, w2 = ctx.saved_tensors
         c, d = ctx.meta
-        g3, g1 = _geom(3, 3, dh=d, dw=d, ph=d, pw=d), _geom(1, 1)
-        xn, yn, dy = _nchw(x, c), _nchw(y, c), _nchw(gy, c)
         w1f, w2f = w1.detach().float(), w2.detach().float()
         n = max(16, P.pad8(c))
-        # the convolutions of the backward pass run on the tensor cores (tile kernel, bf16 operands):
-        #   inner activation a1 = ELU(W1 (*) x + b1), recomputed exactly as the forward kernel staged it (bf16);
-        #   data gradients = convs with transposed (1x1) / transposed + flipped (3x3) weights
-        x8 = x if x.dim() == 5 else P.to_c8(xn)
-        a1 = P.from_c8(ops.conv_same(x8, P.pack_res3x3(w1f), P.pad_vec(b1, n), 3, d, act=True), c).contiguous()   # the kernels take dense NCHW
-        dz2 = _elu_bwd(dy, yn - xn)
-        dw2, db2 = _conv_bwd_weight(a1, dz2, w2f.shape, g1, True)
-        da1 = _conv_same_hi_lo(dz2, P.pack_res1x1(w2f.transpose(0, 1).contiguous()), c, 1, 1)
-        dz1 = _elu_bwd(da1, a1)
-        dw1, db1 = _conv_bwd_weight(xn, dz1, w1f.shape, g3, True)
-        w1t = w1f.transpose(0, 1).flip(2, 3).contiguous()
-        gx = _like(dy + _conv_same_hi_lo(dz1, P.pack_res3x3(w1t), c, 3, d), x)
+        gy = gy.contiguous()
+        dz2 = _as_c8(_ew('tt_res_out_bwd_bf16', gy, y, x))                       # gy * ELU'(z2), activated 1x1 output = y - x
+        x8 = _as_c8(x)
+        a1 = ops.conv_same(x8, P.pack_res3x3(w1f), P.pad_vec(b1, n), 3, d, act=True)    # the inner activation, as the forward staged it
+        dw2, db2 = _wgrad_same(a1, dz2, c, c, 1, 1)
+        da1 = ops.conv_same(dz2, P.pack_res1x1(w2f.transpose(0, 1).contiguous()), None, 1, 1)
+        dz1 = _ew('tt_elu_bwd_bf16', da1, a1)
+        dw1, db1 = _wgrad_same(x8, dz1, c, c, 3, d)
+        gx8 = ops.conv_same(dz1, P.pack_res3x3(w1f.transpose(0, 1).flip(2, 3).contiguous()), None, 3, d)
+        gx = _to_layout_of(gx8, x)
+        one = torch.ones((), dtype=torch.float32, device=gx.device)
+        _lib.check(_lib.lib().tt_add_scaled_bf16(_p(gy), _p(gx), _p(one.reshape(1)), _p(gx), gx.numel(), _s(gx)))     # gx = gy + gx
         return gx, dw1, db1, dw2, db2, None, None, None
 
 
@@ -364,11 +410,16 @@ def _decoder(dec, lat, reconstruct):
     return _ConvFn.apply(x, co.weight, co.bias, lambda t: ops.conv_out(t, w_out, b_out, ch[4]), _geom(3, 3, ph=1, pw=1), ch[4], 2, False)
 
 
-def allreduce_mean_gradients(params, group):
+def allreduce_mean_gradients(params, group, flat=None):
     """Replicas with equal per-rank batches: the mean over ranks of the per-rank gradients is the gradient of the reference's
     global `.mean()` losses (objectives.py:31,72).  One flat bucket (base model: 614,490 fp32 = 2.46 MB), one all-reduce (NCCL on
-    the GPU path; any backend works - tests/test_sharding_gloo.py runs it over gloo), copied back into the `.grad` tensors."""
+    the GPU path; any backend works - tests/test_sharding_gloo.py runs it over gloo).  `flat`: the bucket the `.grad` tensors are
+    views of (TrainStep) - reduced in place; without it the gradients are gathered into a bucket and copied back."""
     import torch.distributed as dist
+    if flat is not None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat /= dist.get_world_size(group)
+        return
     flat = torch.cat([p.grad.reshape(-1) for p in params])
     dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
     flat /= dist.get_world_size(group)
@@ -395,8 +446,25 @@ class TrainStep:
         self.mult.update(multipliers or {})
         self.group = group
         self.t = 0
-        self.m = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
-        self.v = [torch.zeros_like(p, dtype=torch.float32) for p in self.params]
+        # ONE flat fp32 bucket each for parameters, gradients and the two AdamW moments: every parameter (and its .grad) is a view
+        # into it, so autograd accumulates straight into the bucket, the NCCL all-reduce runs on it in place, and clip + AdamW are
+        # two launches over 614,490 floats instead of 2 x 120 (train.py:493-496)
+        dev = self.params[0].device
+        total = sum(p.numel() for p in self.params)
+        self.flat_p = torch.empty(total, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat_v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self._grad_views = []
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat_p[off:off + n].view(p.shape)
+                self._grad_views.append(self.flat_g[off:off + n].view(p.shape))
+                off += n
+        _PackedCache.epoch += 1
 
     def losses(self, audio, ground_truth, late_start=False):
         """The four losses and their total, with the autograd graph attached."""
@@ -425,22 +493,32 @@ class TrainStep:
         return out
 
     def backward(self, total):
-        for p in self.params:
-            p.grad = None
+        self.flat_g.zero_()
+        for p, g in zip(self.params, self._grad_views):
+            p.grad = g                                  # autograd accumulates in place: the gradients land in the flat bucket
         total.backward()
         if self.group is not None:
-            allreduce_mean_gradients(self.params, self.group)
+            self._sync_grad_views()
+            allreduce_mean_gradients(self.params, self.group, flat=self.flat_g)
+
+    def _sync_grad_views(self):
+        """Gradients that were assigned from outside (p.grad = tensor) instead of accumulated by backward(): copy into the bucket."""
+        for p, g in zip(self.params, self._grad_views):
+            if p.grad is None:
+                g.zero_()
+            elif p.grad.data_ptr() != g.data_ptr():
+                g.copy_(p.grad)
+                p.grad = g
 
     def optimizer_step(self):
         self.t += 1
-        dev = self.params[0].device
-        acc = torch.zeros((), dtype=torch.float64, device=dev)
+        self._sync_grad_views()
+        acc = torch.zeros((), dtype=torch.float64, device=self.flat_p.device)
         lib = _lib.lib()
-        for p in self.params:
-            _lib.check(lib.tt_grad_sumsq(_p(p.grad), p.numel(), _p(acc), _s(p)))
-        for p, m, v in zip(self.params, self.m, self.v):
-            _lib.check(lib.tt_adamw_step(_p(p.data), _p(p.grad), _p(m), _p(v), p.numel(), _p(acc), self.max_norm, self.lr, self.betas[0],
-                                         self.betas[1], self.eps, self.wd, self.t, _s(p)))
+        n = self.flat_p.numel()
+        _lib.check(lib.tt_grad_sumsq(_p(self.flat_g), n, _p(acc), _s(self.flat_g)))
+        _lib.check(lib.tt_adamw_step(_p(self.flat_p), _p(self.flat_g), _p(self.flat_m), _p(self.flat_v), n, _p(acc), self.max_norm, self.lr,
+                                     self.betas[0], self.betas[1], self.eps, self.wd, self.t, _s(self.flat_p)))
         _PackedCache.epoch += 1                                                  # weights changed behind torch's back: repack lazily
         return acc.sqrt()
 
