@@ -152,16 +152,21 @@ int tt_conv_same(const void* x, void* y, const void* w, const float* bias, int B
 /* Testing / tuning knob of the row-pipelined kernels (residual blocks, strided and transposed convs): force the number of image
  * rows (row groups) one CTA walks; 0 restores the automatic split.  Results do not depend on it (tests/test_conv_ops_gpu.py). */
 int tt_set_strip_rows(int rows);
-int tt_conv_down_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int T, int packed4_in, void* stream);
+/* act_elu = 1: the model's layers (+ ELU); 0: linear - the same kernels as the data-gradient convolutions of the loss step (the data
+ * gradient of a strided conv is a transposed conv and vice versa) */
+int tt_conv_down_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int T, int packed4_in, int act_elu,
+                       void* stream);
 int tt_conv_up_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int out_pad, int T, int packed4_out,
-                     void* stream);
+                     int act_elu, void* stream);
 /* Encoder.convlat (modules.py:446,478): Conv2d(C4, latent, (H4,1)), no activation; lat is C8 planar with H = 1 */
 int tt_conv_lat(const void* x, void* lat, const void* w, const float* bias, int B, int C4, int H4, int NL, int T, void* stream);
 /* Decoder.convin + ELU (modules.py:533-536) with TimbreTrap.decode's indicator channel (modules.py:139-142) folded into
- * the per-row bias table bias[H0][C0] (one table per switch setting) */
-int tt_deconv_in(const void* lat, void* y, const void* w, const float* bias, int B, int Clat, int C0, int H0, int T, void* stream);
+ * the per-row bias table bias[H0][C0] (one table per switch setting); act_elu = 0: linear (the data gradient of Encoder.convlat) */
+int tt_deconv_in(const void* lat, void* y, const void* w, const float* bias, int B, int Clat, int C0, int H0, int T, int act_elu,
+                 void* stream);
 /* Encoder.convin + ELU (modules.py:430-433): fp32 interleaved coefficients (B,F,T,2) -> C8 planar (packed4 = 0) or the packed
- * 4-channel layout (B,F,T,4) (packed4 = 1, C0 <= 4); w fp32 [C0][2][3][3] */
+ * 4-channel layout (B,F,T,4) (packed4 = 1, C0 <= 4); w fp32 [C0][2][3][3].  packed4 = 2: packed output WITHOUT the ELU (the loss
+ * step's data gradient of Decoder.convout) */
 int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, int B, int C0, int H, int T, int packed4, void* stream);
 /* Decoder.convout (modules.py:543): C8 planar or packed 4-channel input -> fp32 interleaved coefficients (B,F,T,2); w fp32 [2][C][3][3] */
 int tt_conv_out(const void* x, float* coeffs, const float* w, const float* bias, int B, int C, int H, int T, int packed4, void* stream);
@@ -184,6 +189,8 @@ int tt_add_scaled_bf16(const void* x, const void* e, const float* scale, void* o
 /* (x) -> interleaved (x, 0): a one-channel feature map (TimbreTrapMag / MagDB encoder input, modules.py:927-950, 1019-1031) in the
  * two-channel layout tt_conv_in reads */
 int tt_widen_pairs(const float* x, int64_t n, float* out, void* stream);
+/* n fp32 interleaved pairs (B, F, T, 2) -> C8 planar bf16 (B, 1, F, T, 8), channels 2..7 zero (operand of the weight-gradient GEMM) */
+int tt_pairs_to_c8(const float* pairs, int64_t n, void* c8, void* stream);
 /* channel 0 of n interleaved pairs through an output non-linearity: 0 identity, 1 relu (TimbreTrapMag.decode, modules.py:976),
  * 2 sigmoid (TimbreTrapMagDB.decode :1052), 3 tanh(relu(.)) (Mag decode + to_activations :996) */
 int tt_channel0_activation(const float* pairs, int64_t n, int mode, float* out, void* stream);
@@ -249,6 +256,22 @@ int tt_conv_bwd_weight_f32(const float* x, const float* dz, float* dw, float* db
 int64_t tt_wgrad_scratch_floats(int B, int H, int T);
 int tt_conv_wgrad_same(const void* x, const void* dz, float* dw, float* db, int B, int Cin, int Cout, int cin_real, int cout_real,
                        int H, int T, int k, int dilation, float* scratch, void* stream);
+/* The same GEMM for the (4,1) / stride (2,1) layers: `coarse` (B, Ccoarse/8, Hcoarse, T, 8) row q meets `fine` (B, Cfine/8, Hfine, T, 8)
+ * rows 2q .. 2q+3.  EncoderBlock.sconv (modules.py:626-629): fine = layer input, coarse = output gradient, dw (ccoarse_real, cfine_real, 4, 1),
+ * db (ccoarse_real), transposed = 0.  DecoderBlock.tconv (modules.py:685-688): coarse = layer input, fine = output gradient, dw in the
+ * ConvTranspose2d layout (ccoarse_real, cfine_real, 4, 1), db (cfine_real) = pixel sums of `fine`, transposed = 1.  Accumulating. */
+int tt_conv_wgrad_updown(const void* fine, const void* coarse, float* dw, float* db, int B, int Cfine, int Ccoarse, int cfine_real,
+                         int ccoarse_real, int Hfine, int Hcoarse, int T, int transposed, float* scratch, void* stream);
+/* ... and for the two (H, 1)-kernel layers between the 31-row embedding and the latents: `tall` (B, Ctall/8, H, T, 8), `flat`
+ * (B, Cflat/8, 1, T, 8); dw (cflat_real, ctall_real, H, 1) += sum over (b, t) of flat[m] * tall[n, h]; db (cflat_real) += pixel sums
+ * of `flat` (may be NULL); tall_row_sums (ctall_real, H) += sums over (b, t) of `tall` (may be NULL).  Encoder.convlat
+ * (modules.py:446): tall = layer input, flat = output gradient, dw is the Conv2d weight gradient.  Decoder.convin (:533-536):
+ * flat = latents, tall = output gradient (after the ELU derivative): dw = rows 0 .. D-1 of the ConvTranspose2d weight gradient,
+ * tall_row_sums = its indicator row (times the indicator) and, summed over H, the bias gradient.  scratch:
+ * tt_wgrad_lat_scratch_floats(B, H, T) floats. */
+int64_t tt_wgrad_lat_scratch_floats(int B, int H, int T);
+int tt_conv_wgrad_lat(const void* tall, const void* flat, float* dw, float* db, float* tall_row_sums, int B, int Ctall, int Cflat,
+                      int ctall_real, int cflat_real, int H, int T, float* scratch, void* stream);
 /* element-wise pieces of the backward pass on bf16 tensors of any common layout (n elements, multiple of 8):
  * dz = gy * ELU'(z) through the activated output a;  residual block: dz = gy * ELU'(z2) with the activated 1x1 output = y - x */
 int tt_elu_bwd_bf16(const void* gy, const void* a, void* dz, int64_t n, void* stream);

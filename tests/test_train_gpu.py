@@ -171,3 +171,65 @@ def test_tensor_core_weight_gradient(C, H, T, k, d, B):
     assert float((db.cpu() - bias.grad).abs().max()) <= 2e-4 * float(bias.grad.abs().max()) + 1e-4
     dw2, db2 = TR._wgrad_same(P.to_c8(x.cuda()), P.to_c8(dz.cuda()), C, C, k, d)
     assert torch.equal(dw, dw2) and torch.equal(db, db2)                  # fixed reduction order: bit-reproducible
+
+
+@pytest.mark.parametrize('Cf,Cc,Hc,T,op,B', [(4, 8, 19, 256, 0, 2), (8, 16, 33, 200, 1, 1), (16, 32, 9, 384, 0, 2), (32, 64, 31, 128, 1, 2)])
+def test_tensor_core_weight_gradient_strided_and_transposed(Cf, Cc, Hc, T, op, B):
+    """tt_conv_wgrad_updown against torch autograd: EncoderBlock.sconv (fine = input, coarse = output gradient) and DecoderBlock.tconv
+    (coarse = input, fine = output gradient, bias gradient = pixel sums of the fine tensor)."""
+    from timbre_trap_b200.framework import packing as P, train as TR
+    g = torch.Generator().manual_seed(Cf * 10 + Hc)
+    Hf = 2 * Hc + 2 + op
+    fine = torch.randn((B, Cf, Hf, T), generator=g).to(torch.bfloat16).float()
+    coarse = (torch.randn((B, Cc, Hc, T), generator=g) * 0.1).to(torch.bfloat16).float()
+    # strided conv: y = conv(fine, w (Cc, Cf, 4, 1), stride 2) has (Hf - 4) // 2 + 1 = Hc rows; coarse plays dL/dy
+    w = torch.zeros((Cc, Cf, 4, 1), requires_grad=True)
+    bias = torch.zeros(Cc, requires_grad=True)
+    y = F.conv2d(fine, w, bias, stride=(2, 1))
+    assert y.shape[2] == Hc
+    (y * coarse).sum().backward()
+    dw, db = TR._wgrad_updown(P.to_c8(fine.cuda()), P.to_c8(coarse.cuda()), Cf, Cc, False)
+    assert float((dw.cpu() - w.grad).abs().max()) <= 2e-4 * float(w.grad.abs().max()) + 1e-4
+    assert float((db.cpu() - bias.grad).abs().max()) <= 2e-4 * float(bias.grad.abs().max()) + 1e-4
+    # transposed conv: y = convT(coarse, wt (Cc, Cf, 4, 1), stride 2, output_padding op) has Hf rows; fine plays dL/dy
+    wt = torch.zeros((Cc, Cf, 4, 1), requires_grad=True)
+    bt = torch.zeros(Cf, requires_grad=True)
+    yt = F.conv_transpose2d(coarse, wt, bt, stride=(2, 1), output_padding=(op, 0))
+    assert yt.shape[2] == Hf
+    (yt * fine).sum().backward()
+    dwt, dbt = TR._wgrad_updown(P.to_c8(fine.cuda()), P.to_c8(coarse.cuda()), Cf, Cc, True)
+    assert float((dwt.cpu() - wt.grad).abs().max()) <= 2e-4 * float(wt.grad.abs().max()) + 1e-4
+    assert float((dbt.cpu() - bt.grad).abs().max()) <= 2e-4 * float(bt.grad.abs().max()) + 2e-3
+
+
+@pytest.mark.parametrize('Ct,Cf,H,T,B', [(64, 128, 31, 256, 2), (32, 32, 5, 200, 3), (64, 100, 31, 128, 1)])
+def test_tensor_core_weight_gradient_tall_kernel_layers(Ct, Cf, H, T, B):
+    """tt_conv_wgrad_lat against torch autograd: Encoder.convlat (Conv2d (Cf, Ct, H, 1) over the full height) and Decoder.convin
+    (ConvTranspose2d (Cf + 1, Ct, H, 1) with the indicator channel: its weight row and the bias are row sums of the output gradient)."""
+    from timbre_trap_b200.framework import packing as P, train as TR
+    g = torch.Generator().manual_seed(Ct + H)
+    tall = torch.randn((B, Ct, H, T), generator=g).to(torch.bfloat16).float()
+    flat = (torch.randn((B, Cf, 1, T), generator=g) * 0.1).to(torch.bfloat16).float()
+    fpad = (Cf + 15) // 16 * 16
+    flat8 = TR.P.to_c8(torch.nn.functional.pad(flat, (0, 0, 0, 0, 0, fpad - Cf)).cuda())
+    tall8 = P.to_c8(tall.cuda())
+    # convlat: y = conv(tall, w (Cf, Ct, H, 1)); flat plays dL/dy
+    w = torch.zeros((Cf, Ct, H, 1), requires_grad=True)
+    bias = torch.zeros(Cf, requires_grad=True)
+    (F.conv2d(tall, w, bias) * flat).sum().backward()
+    dw = torch.zeros((Cf, Ct, H, 1), device='cuda')
+    db = torch.zeros(Cf, device='cuda')
+    TR._wgrad_lat(tall8, flat8, Ct, Cf, dw, db, None)
+    assert float((dw.cpu() - w.grad).abs().max()) <= 2e-4 * float(w.grad.abs().max()) + 1e-4
+    assert float((db.cpu() - bias.grad).abs().max()) <= 2e-4 * float(bias.grad.abs().max()) + 1e-4
+    # decoder convin: y = convT(cat(flat, indicator), wt (Cf + 1, Ct, H, 1)); tall plays dL/dy
+    wt = torch.zeros((Cf + 1, Ct, H, 1), requires_grad=True)
+    bt = torch.zeros(Ct, requires_grad=True)
+    full = torch.cat((flat, torch.ones_like(flat[:, :1])), dim=1)
+    (F.conv_transpose2d(full, wt, bt) * tall).sum().backward()
+    dwt = torch.zeros((Cf + 1, Ct, H, 1), device='cuda')
+    rows = torch.zeros((Ct, H), device='cuda')
+    TR._wgrad_lat(tall8, flat8, Ct, Cf, dwt, None, rows)
+    dwt[Cf, :, :, 0] = rows
+    assert float((dwt.cpu() - wt.grad).abs().max()) <= 2e-4 * float(wt.grad.abs().max()) + 2e-3
+    assert float((rows.sum(1).cpu() - bt.grad).abs().max()) <= 2e-4 * float(bt.grad.abs().max()) + 2e-3

@@ -33,16 +33,17 @@ SIGNATURES = {
     'tt_chunk_crossfade': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'tt_res_block_rs': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     'tt_set_strip_rows': (c_int, [c_int]),
-    'tt_conv_down_strip': (c_int, [c_void_p] * 3 + [c_int] * 6 + [c_void_p]),
-    'tt_conv_up_strip': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
+    'tt_conv_down_strip': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
+    'tt_conv_up_strip': (c_int, [c_void_p] * 3 + [c_int] * 8 + [c_void_p]),
     'tt_conv_same': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
     'tt_conv_lat': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
-    'tt_deconv_in': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
+    'tt_deconv_in': (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     'tt_conv_in': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'tt_conv_out': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'tt_conv_out_crossfade': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 3),
     'tt_add_scaled_bf16': (c_int, [c_void_p] * 4 + [c_int64, c_void_p]),
     'tt_widen_pairs': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    'tt_pairs_to_c8': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'tt_channel0_activation': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'tt_resample_mono': (c_int, [c_void_p, c_int, c_int64, c_void_p, c_int, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     'tt_rasterise_pitches': (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
@@ -55,6 +56,9 @@ SIGNATURES = {
     'tt_conv_bwd_weight_f32': (c_int, [c_void_p] * 4 + [c_int] * 13 + [c_void_p]),
     'tt_wgrad_scratch_floats': (c_int64, [c_int, c_int, c_int]),
     'tt_conv_wgrad_same': (c_int, [c_void_p] * 4 + [c_int] * 9 + [c_void_p, c_void_p]),
+    'tt_conv_wgrad_updown': (c_int, [c_void_p] * 4 + [c_int] * 9 + [c_void_p, c_void_p]),
+    'tt_wgrad_lat_scratch_floats': (c_int64, [c_int, c_int, c_int]),
+    'tt_conv_wgrad_lat': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p, c_void_p]),
     'tt_elu_bwd_bf16': (c_int, [c_void_p] * 3 + [c_int64, c_void_p]),
     'tt_res_out_bwd_bf16': (c_int, [c_void_p] * 4 + [c_int64, c_void_p]),
     'tt_p4_to_c8': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),

@@ -304,7 +304,7 @@ extern "C" int tt_conv_same(const void* x, void* y, const void* w, const float* 
 // its own weight slice W[:, :, h]; the indicator channel (modules.py:139-142) is folded into a per-row bias table.
 //   lat (B, Clat/8, 1, T, 8) -> y (B, C0/8, H0, T, 8);  w packed [H0][Clat/8][C0][8];  bias [H0][C0]
 extern "C" int tt_deconv_in(const void* lat, void* y, const void* w, const float* bias, int B, int Clat, int C0, int H0, int T,
-                            void* stream) {
+                            int act_elu, void* stream) {
     TT_REQUIRE(lat && y && w && bias, "null argument");
     TT_REQUIRE(Clat % 16 == 0 && Clat <= 256 && (C0 == 16 || C0 == 32 || C0 == 64 || C0 == 128), "deconv_in: unsupported sizes");
     if (B <= 0 || T <= 0) return TT_OK;
@@ -314,7 +314,7 @@ extern "C" int tt_deconv_in(const void* lat, void* y, const void* w, const float
     p.groups = H0;
     p.R = 4;
     p.sh = 0; p.row_lo = 0; p.in_rows = 1; p.padT = 0;
-    p.out_mode = 0; p.act = 1;
+    p.out_mode = 0; p.act = act_elu;
     const uint32_t plane = kTileT * 16;
     int m = 0;
     for (int q = 0; q < CG / 2; ++q) { p.tap_off[m] = 2 * q * plane; p.tap_lbo[m] = plane; ++m; }
@@ -749,7 +749,7 @@ __global__ void __launch_bounds__(128) conv_out_xfade_p4_kernel(const uint2* __r
 
 // Encoder.convin, fp32 interleaved (B, H, T, 2) -> packed4 (B, H, T, 4) bf16, + ELU
 __global__ void __launch_bounds__(128) conv_in_p4_kernel(const float2* __restrict__ x, uint2* __restrict__ y, const float* __restrict__ w /* [C0][2][3][3] */,
-                                                         const float* __restrict__ bias, int C0, int H, int T, int rows) {
+                                                         const float* __restrict__ bias, int C0, int H, int T, int rows, int act) {
     __shared__ __align__(16) float2 sw[3][3][2][2];  // [ky][kx][re/im][channel pair] -> (w for channel 2p, 2p+1)
     __shared__ float2 sb[2];
     for (int i = threadIdx.x; i < 36; i += 128) {
@@ -807,7 +807,11 @@ __global__ void __launch_bounds__(128) conv_in_p4_kernel(const float2* __restric
             float r[16];
 #pragma unroll
             for (int f = 0; f < 4; ++f) {
-                r[4 * f] = elu(A[f][0].x); r[4 * f + 1] = elu(A[f][0].y); r[4 * f + 2] = elu(A[f][1].x); r[4 * f + 3] = elu(A[f][1].y);
+                r[4 * f] = A[f][0].x; r[4 * f + 1] = A[f][0].y; r[4 * f + 2] = A[f][1].x; r[4 * f + 3] = A[f][1].y;
+            }
+            if (act) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) r[e] = elu(r[e]);
             }
             uint4* dst = reinterpret_cast<uint4*>(yb + (size_t)ho * T);
             dst[0] = pack8(r);
@@ -861,6 +865,8 @@ extern "C" int tt_conv_lat(const void* x, void* lat, const void* w, const float*
     return TT_OK;
 }
 
+// packed4: 0 = C8 planar output, 1 = packed 4-channel output, 2 = packed 4-channel output WITHOUT the ELU (the data gradient of
+// Decoder.convout in the loss step: a 2 -> 4 channel 3x3 conv of the fp32 coefficient gradient with transposed, flipped weights)
 extern "C" int tt_conv_in(const float* coeffs, void* y, const float* w, const float* bias, int B, int C0, int H, int T, int packed4,
                           void* stream) {
     TT_REQUIRE(coeffs && y && w && bias, "null argument");
@@ -872,7 +878,7 @@ extern "C" int tt_conv_in(const float* coeffs, void* y, const float* w, const fl
     if (packed4) {
         const int rows = walk_rows(B, H, T);
         conv_in_p4_kernel<<<dim3((T / 4 + 127) / 128, (H + rows - 1) / rows, B), 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (uint2*)y, w, bias, C0,
-                                                                                                            H, T, rows);
+                                                                                                            H, T, rows, packed4 != 2);
     } else if (C0 <= 4) conv_in_kernel<4><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T, packed4);
     else conv_in_kernel<8><<<grid, 128, 0, (cudaStream_t)stream>>>((const float2*)coeffs, (__nv_bfloat16*)y, w, bias, C0, H, T, 0);
     tt_count_launches(1);

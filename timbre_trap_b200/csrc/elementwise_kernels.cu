@@ -50,6 +50,17 @@ __global__ void channel0_activation_kernel(const float2* __restrict__ pairs, lon
     }
 }
 
+// fp32 interleaved pairs (coefficients or their gradient, (B, F, T, 2)) -> C8 planar bf16 with one channel group (B, 1, F, T, 8),
+// channels 2..7 zero: the layout the tensor-core weight-gradient kernel reads
+__global__ void pairs_to_c8_kernel(const float2* __restrict__ pairs, long long n, uint4* __restrict__ c8) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float2 v = ld_stream(pairs + i);
+        __nv_bfloat162 h = __floats2bfloat162_rn(v.x, v.y);
+        c8[i] = make_uint4(*reinterpret_cast<uint32_t*>(&h), 0u, 0u, 0u);
+    }
+}
+
 }  // namespace tt
 
 using namespace tt;
@@ -80,6 +91,15 @@ extern "C" int tt_channel0_activation(const float* pairs, int64_t n, int mode, f
     TT_REQUIRE(mode >= 0 && mode <= 3, "channel0_activation: mode must be 0..3");
     if (n <= 0) return TT_OK;
     channel0_activation_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float2*)pairs, n, mode, out);
+    tt_count_launches(1);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
+extern "C" int tt_pairs_to_c8(const float* pairs, int64_t n, void* c8, void* stream) {
+    TT_REQUIRE(pairs && c8, "null argument");
+    if (n <= 0) return TT_OK;
+    pairs_to_c8_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float2*)pairs, n, (uint4*)c8);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;

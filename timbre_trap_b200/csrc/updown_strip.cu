@@ -32,6 +32,7 @@ struct UpDownParams {
     int CGout;             // channel groups of one output row
     int groups;            // row groups in total (DOWN: Hout, UP: ceil(Hout / 2))
     int groups_per_strip;
+    int act;               // 1: ELU on the output (the model's layers); 0: linear (the same kernels as data-gradient convolutions)
 };
 
 template <int CGIN, int N>
@@ -179,10 +180,14 @@ __global__ void __launch_bounds__(kUdThreads, (N <= 32 && !UP) ? 2 : 1) updown_s
                     if constexpr (UP) { ho = 2 * grp + (c >= N / 2 ? 1 : 0); cg = (c % (N / 2)) >> 3; }
                     else { ho = grp; cg = c >> 3; }
                     uint4 o;
-                    o.x = pack2(elu_f(v[k]), elu_f(v[k + 1]));
-                    o.y = pack2(elu_f(v[k + 2]), elu_f(v[k + 3]));
-                    o.z = pack2(elu_f(v[k + 4]), elu_f(v[k + 5]));
-                    o.w = pack2(elu_f(v[k + 6]), elu_f(v[k + 7]));
+                    if (p.act) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) v[k + e] = elu_f(v[k + e]);
+                    }
+                    o.x = pack2(v[k], v[k + 1]);
+                    o.y = pack2(v[k + 2], v[k + 3]);
+                    o.z = pack2(v[k + 4], v[k + 5]);
+                    o.w = pack2(v[k + 6], v[k + 7]);
                     if constexpr (P4 && !UP) {
                         // pair j -> frames 2 (t0 + j) + (c >> 3) of the 8-channel output (p.T counts pairs)
                         if (t_ok && ho < p.Hout)
@@ -243,7 +248,7 @@ static int strip_groups(int B, int T, int groups) {
 using namespace tt;
 
 extern "C" int tt_conv_down_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int T, int packed4_in,
-                                  void* stream) {
+                                  int act_elu, void* stream) {
     TT_REQUIRE(x && y && w, "null argument");
     TT_REQUIRE(!packed4_in || (Cin == 8 && Cout == 8 && T % 2 == 0), "packed input: 4 -> 8 channels only, even frame count");
     if (packed4_in) T /= 2;                 // the kernel works on frame pairs
@@ -252,7 +257,7 @@ extern "C" int tt_conv_down_strip(const void* x, void* y, const void* w, int B, 
     TT_REQUIRE(Hout >= 1, "conv_down: input too short");
     UpDownParams p;
     p.y = (__nv_bfloat16*)y; p.w = (const __nv_bfloat16*)w;
-    p.B = B; p.Hin = Hin; p.Hout = Hout; p.T = T; p.CGout = Cout / 8; p.groups = Hout;
+    p.B = B; p.Hin = Hin; p.Hout = Hout; p.T = T; p.CGout = Cout / 8; p.groups = Hout; p.act = act_elu;
     p.groups_per_strip = strip_groups(B, T, p.groups);
     cudaStream_t s = (cudaStream_t)stream;
     if (packed4_in) return launch_updown<1, 16, 16, false, true>(x, p, s);
@@ -265,13 +270,13 @@ extern "C" int tt_conv_down_strip(const void* x, void* y, const void* w, int B, 
 }
 
 extern "C" int tt_conv_up_strip(const void* x, void* y, const void* w, int B, int Cin, int Cout, int Hin, int out_pad, int T,
-                                int packed4_out, void* stream) {
+                                int packed4_out, int act_elu, void* stream) {
     TT_REQUIRE(x && y && w, "null argument");
     TT_REQUIRE(!packed4_out || (Cin == 8 && Cout == 8), "packed output: 8 -> 4 channels only");
     if (B <= 0 || T <= 0 || Hin <= 0) return TT_OK;
     UpDownParams p;
     p.y = (__nv_bfloat16*)y; p.w = (const __nv_bfloat16*)w;
-    p.B = B; p.Hin = Hin; p.Hout = 2 * Hin + 2 + out_pad; p.T = T; p.CGout = Cout / 8; p.groups = (p.Hout + 1) / 2;
+    p.B = B; p.Hin = Hin; p.Hout = 2 * Hin + 2 + out_pad; p.T = T; p.CGout = Cout / 8; p.groups = (p.Hout + 1) / 2; p.act = act_elu;
     p.groups_per_strip = strip_groups(B, T, p.groups);
     cudaStream_t s = (cudaStream_t)stream;
     if (Cin == 64 && Cout == 32) return launch_updown<8, 64, 64, true>(x, p, s);

@@ -21,49 +21,64 @@
 
 namespace tt {
 
-constexpr int kWgThreads = 128;        // warp 0: TMA producer + epilogue, warp 1: MMA issuer, warps 2-3: epilogue helpers (idle in the loop)
-constexpr int kWgZSlots = 3;           // dZ row ring
+constexpr int kWgThreads = 128;        // warp 0: TMA producer, warp 1: MMA issuer; after the row loop warps 0-1 drain the accumulators
+constexpr int kWgZSlots = 3;           // A-side row ring
 constexpr int kWgMaxTaps = 10;         // 9 conv taps + the bias "tap"
+constexpr int kWgMaxM = 64;            // A-side channels a CTA of the row-walking geometries writes out (TMEM lanes 0..63)
 
 struct WgradParams {
-    float* partial;                    // (n_ctas, kWgMaxTaps, 32, NPAD) fp32
-    int B, H, T;
-    int CGi, CGo;
-    int d;                             // dilation (= halo in pixels)
+    float* partial;                    // (n_ctas, kWgMaxTaps, kWgMaxM, NPAD) fp32
+    int B, T;
+    int Hz, Hx;                        // rows of the A-side (dZ) and B-side (X) tensors
+    int CGi, CGo;                      // channel groups of the B side (X) and the A side (dZ)
+    int d;                             // dilation of the 3x3 geometry
     int rows_per_strip;
+    int z_slots;                       // A-side ring depth (<= kWgZSlots)
+    int tap_group;                     // 0: blockIdx.y walks strips of A-side rows; > 0: the A side has ONE row and blockIdx.y selects a
+                                       // group of `tap_group` consecutive B-side rows = vertical taps (the (31,1) layers)
 };
 
-// shared memory plan (bytes): [barriers 1 KB][ones 4 KB][dZ ring][X ring]; the A operand reads 16 channel groups = 32 KB from its slot, the
-// B operand NPAD/8 groups: both stay inside the allocation because the X ring follows and the allocation is padded (see wgrad_smem)
-template <int NPAD, int KS>
-__global__ void __launch_bounds__(kWgThreads, 1) wgrad_same_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
-                                                                   const WgradParams p) {
-    constexpr int TAPS = KS * KS;
-    constexpr uint32_t ncols = (TAPS + 1) * NPAD <= 32 ? 32 : ((TAPS + 1) * NPAD <= 64 ? 64 : ((TAPS + 1) * NPAD <= 128 ? 128 : ((TAPS + 1) * NPAD <= 256 ? 256 : 512)));
+// Geometry (compile time): KH x KW taps; the B-side row of tap ky for A-side row q is  q * RS + ky * DH + row0  with
+//   3x3 'same' (KH = KW = 3, RS = 1):  DH = d, row0 = -d, horizontal tap offsets (kx - 1) d, column halo d
+//   1x1        (KH = KW = 1, RS = 1):  row0 = 0
+//   (4,1) stride (2,1) (KH = 4, KW = 1, RS = 2):  DH = 1, row0 = 0  (EncoderBlock.sconv; DecoderBlock.tconv with the two sides swapped)
+// shared memory plan (bytes): [barriers 1 KB][ones 4 KB][A ring][B ring]; the A operand reads 16 channel groups = 32 KB from its slot, the
+// B operand NPAD/8 groups: both stay inside the allocation because the B ring follows and the allocation is padded (see wgrad_smem)
+template <int NPAD, int KH, int KW, int RS, int MW>
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
+                                                              const WgradParams p) {
+    constexpr int TAPS = KH * KW;
+    constexpr uint32_t need = (TAPS + 1) * NPAD;
+    constexpr uint32_t ncols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
+    static_assert(need <= 512, "TMEM columns");
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int d = KS == 3 ? p.d : 0;
+    const int d = KW == 3 ? p.d : 0;                  // column halo / horizontal tap step
+    const int DH = KH == 3 ? p.d : 1;                 // vertical tap step in B-side rows
+    const int span = (KH - 1) * DH;                   // B-side rows an A-side row reaches beyond its first one
     const int TW = kStripTileT + 2 * d;
-    const int xring = KS == 3 ? 2 * d + 3 : 2;
+    const int xring = span + 1 + 2 * RS;
     const uint32_t z_slot = (uint32_t)p.CGo * kStripTileT * 16u;
     const uint32_t x_plane = (uint32_t)TW * 16u;
     const uint32_t x_slot = ((uint32_t)p.CGi * x_plane + 127u) & ~127u;
     uint64_t* z_full = reinterpret_cast<uint64_t*>(smem);            // [kWgZSlots]
     uint64_t* z_empty = z_full + kWgZSlots;                           // [kWgZSlots]
-    uint64_t* x_full = z_empty + kWgZSlots;                           // [xring <= 9]
+    uint64_t* x_full = z_empty + kWgZSlots;                           // [xring <= 16]
     uint64_t* x_empty = x_full + 16;                                  // [xring]
     uint64_t* done = x_empty + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 512);
     uint8_t* sOnes = smem + 1024;                                      // [2 groups][128 px][8] bf16 ones (group 1 only pads N to 16)
     uint8_t* sZ = smem + 1024 + 4096;
-    uint8_t* sX = sZ + kWgZSlots * z_slot;
+    uint8_t* sX = sZ + p.z_slots * z_slot;
+    const int zslots = p.z_slots;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int t0 = blockIdx.x * kStripTileT;
-    const int h0 = blockIdx.y * p.rows_per_strip;
-    const int h1 = min(p.H, h0 + p.rows_per_strip);
+    const int h0 = p.tap_group ? 0 : blockIdx.y * p.rows_per_strip;
+    const int h1 = p.tap_group ? p.Hz : min(p.Hz, h0 + p.rows_per_strip);
     const int b = blockIdx.z;
-    const int n_rows = h1 - h0;                    // dZ rows of this strip
-    const int n_xrows = n_rows + 2 * d;            // X rows h0 - d .. h1 - 1 + d
+    const int n_rows = h1 - h0;                         // A-side rows of this strip
+    const int n_xrows = (n_rows - 1) * RS + span + 1;   // B-side rows, relative index 0 <-> image row x_row0
+    const int x_row0 = p.tap_group ? blockIdx.y * p.tap_group : h0 * RS - (KH == 3 ? d : 0);
 
     if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
     if (tid == 32) {
@@ -80,19 +95,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_same_kernel(const __grid_
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0 && lane == 0) {
-        // ================= producer: X rows run d ahead of the dZ rows =================
-        int xr = 0;                                                    // next X row (relative index 0 .. n_xrows-1 <-> image row h0 - d + xr)
+        // ================= producer: the B-side rows run ahead of the A-side rows =================
+        int xr = 0;                                                    // next B-side row (relative)
         auto load_x = [&]() {
             const int slot = xr % xring;
             if (xr >= xring) umma::mbar_wait(&x_empty[slot], (uint32_t)((xr / xring - 1) & 1));
             mbar_expect_tx(&x_full[slot], (uint32_t)p.CGi * x_plane);
-            tma_load_5d(sX + (size_t)slot * x_slot, &tmap_x, &x_full[slot], 0, t0 - d, h0 - d + xr, 0, b);
+            tma_load_5d(sX + (size_t)slot * x_slot, &tmap_x, &x_full[slot], 0, t0 - d, x_row0 + xr, 0, b);
             ++xr;
         };
         for (int r = 0; r < n_rows; ++r) {
-            while (xr < n_xrows && xr <= r + 2 * d + 1) load_x();      // rows r .. r + 2d (+1 prefetch) relative = image rows h0+r-d .. h0+r+d
-            const int slot = r % kWgZSlots;
-            if (r >= kWgZSlots) umma::mbar_wait(&z_empty[slot], (uint32_t)((r / kWgZSlots - 1) & 1));
+            while (xr < n_xrows && xr <= r * RS + span + RS) load_x();      // the rows of A-side row r, plus those of row r + 1
+            const int slot = r % zslots;
+            if (r >= zslots) umma::mbar_wait(&z_empty[slot], (uint32_t)((r / zslots - 1) & 1));
             mbar_expect_tx(&z_full[slot], z_slot);
             tma_load_5d(sZ + (size_t)slot * z_slot, &tmap_z, &z_full[slot], 0, t0, h0 + r, 0, b);
         }
@@ -102,23 +117,24 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_same_kernel(const __grid_
         const uint32_t z0 = umma::smem_u32(sZ), x0 = umma::smem_u32(sX), ones0 = umma::smem_u32(sOnes);
         bool first = true;                                             // the very first MMA of every accumulator overwrites
         for (int r = 0; r < n_rows; ++r) {
-            const int zs = r % kWgZSlots;
-            umma::mbar_wait(&z_full[zs], (uint32_t)((r / kWgZSlots) & 1));
-            // X rows r .. r + 2d (relative); the newest one (and, at the start, all of them) may still be in flight
-            for (int xr = (r == 0 ? 0 : r + 2 * d); xr <= r + 2 * d; ++xr) umma::mbar_wait(&x_full[xr % xring], (uint32_t)((xr / xring) & 1));
+            const int zs = r % zslots;
+            umma::mbar_wait(&z_full[zs], (uint32_t)((r / zslots) & 1));
+            // B-side rows r RS .. r RS + span; those beyond what row r - 1 already waited for may still be in flight
+            for (int xr = (r == 0 ? 0 : (r - 1) * RS + span + 1); xr <= r * RS + span; ++xr)
+                umma::mbar_wait(&x_full[xr % xring], (uint32_t)((xr / xring) & 1));
             umma::fence_after_sync();
             const uint32_t za = z0 + (uint32_t)zs * z_slot;
 #pragma unroll 1
             for (int s = 0; s < kStripTileT / 16; ++s) {
                 const uint64_t da = umma::make_desc(za + (uint32_t)s * 256u, 128u, (uint32_t)kStripTileT * 16u);
 #pragma unroll
-                for (int ky = 0; ky < KS; ++ky) {
-                    const int xr = r + ky * d;                         // relative X row of this vertical tap
+                for (int ky = 0; ky < KH; ++ky) {
+                    const int xr = r * RS + ky * DH;                   // relative B-side row of this vertical tap
                     const uint32_t xa = x0 + (uint32_t)(xr % xring) * x_slot;
 #pragma unroll
-                    for (int kx = 0; kx < KS; ++kx) {
+                    for (int kx = 0; kx < KW; ++kx) {
                         const uint64_t db = umma::make_desc(xa + (uint32_t)(kx * d) * 16u + (uint32_t)s * 256u, 128u, x_plane);
-                        umma::mma_bf16(tmem + (uint32_t)((ky * KS + kx) * NPAD), da, db, idesc, !(first && s == 0));
+                        umma::mma_bf16(tmem + (uint32_t)((ky * KW + kx) * NPAD), da, db, idesc, !(first && s == 0));
                     }
                 }
                 const uint64_t dones = umma::make_desc(ones0 + (uint32_t)s * 256u, 128u, (uint32_t)kStripTileT * 16u);
@@ -126,26 +142,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_same_kernel(const __grid_
             }
             first = false;
             umma::commit(&z_empty[zs]);
-            // X row r (relative) is not needed by later rows
-            umma::commit(&x_empty[r % xring]);
+            // the first RS B-side rows of this A-side row are not needed by later rows
+#pragma unroll
+            for (int k = 0; k < RS; ++k) umma::commit(&x_empty[(r * RS + k) % xring]);
         }
         umma::commit(done);
     }
     __syncwarp();
-    // ================= epilogue: accumulators -> partial buffer (lanes 0..31 = output channels; NPAD columns per tap) =================
-    if (warp == 0) {
+    // ================= epilogue: accumulators -> partial buffer (TMEM lane = A-side channel; NPAD columns per tap) =================
+    if (warp < MW) {
+        constexpr int MROWS = MW * 32;
         umma::mbar_wait_warp(done, 0);
         umma::fence_after_sync();
         const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-        float* dst = p.partial + (cta * kWgMaxTaps * 32 + lane) * NPAD;
+        float* dst = p.partial + (cta * kWgMaxTaps * MROWS + warp * 32 + lane) * NPAD;
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
         for (int tap = 0; tap <= TAPS; ++tap) {
 #pragma unroll
             for (int c0 = 0; c0 < NPAD; c0 += 16) {
                 float v[16];
-                umma::tmem_ld16(tmem + (uint32_t)(tap * NPAD + c0), v);
+                umma::tmem_ld16(lane_addr + (uint32_t)(tap * NPAD + c0), v);
                 umma::tmem_ld_wait();
-                float4* o = reinterpret_cast<float4*>(dst + (size_t)tap * 32 * NPAD + c0);
+                float4* o = reinterpret_cast<float4*>(dst + (size_t)tap * MROWS * NPAD + c0);
                 o[0] = make_float4(v[0], v[1], v[2], v[3]);
                 o[1] = make_float4(v[4], v[5], v[6], v[7]);
                 o[2] = make_float4(v[8], v[9], v[10], v[11]);
@@ -158,25 +177,122 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_same_kernel(const __grid_
     if (warp == 0) umma::tmem_dealloc(tmem, ncols);
 }
 
-// dW (co, ci, KS, KS) and db (co) += fixed-order sums of the per-CTA partials
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, int npad, int ks, int co, int ci, float* __restrict__ dw,
+// dW (m, n, taps) and db (m) += fixed-order sums of the per-CTA partials (m = A-side channel, n = B-side channel: (co, ci, kh, kw) for a
+// regular conv, (ci, co, kh, kw) - the ConvTranspose2d weight layout - when the two sides are swapped)
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, int npad, int taps, int m_real, int n_real, float* __restrict__ dw,
                                     float* __restrict__ db) {
-    const int taps = ks * ks;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;              // over (tap' in [0, taps], co, ci)
-    const int total = (taps + 1) * co * ci;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;              // over (tap' in [0, taps], m, n)
+    const int total = (taps + 1) * m_real * n_real;
     if (i >= total) return;
-    const int tap = i / (co * ci), rem = i - tap * co * ci;
-    const int o = rem / ci, c = rem - o * ci;
-    if (tap == taps && c != 0) return;
-    const float* src = partial + ((size_t)tap * 32 + o) * npad + (tap == taps ? 0 : c);
-    const size_t stride = (size_t)kWgMaxTaps * 32 * npad;
+    const int tap = i / (m_real * n_real), rem = i - tap * m_real * n_real;
+    const int o = rem / n_real, c = rem - o * n_real;
+    if (tap == taps && (c != 0 || db == nullptr)) return;
+    const float* src = partial + ((size_t)tap * kWgMaxM + o) * npad + (tap == taps ? 0 : c);
+    const size_t stride = (size_t)kWgMaxTaps * kWgMaxM * npad;
     float acc = 0.f;
     for (int k = 0; k < n_ctas; ++k) acc += src[(size_t)k * stride];
-    if (tap == taps) {
-        if (db) db[o] += acc;
-    } else {
-        dw[((size_t)o * ci + c) * taps + tap] += acc;                 // (co, ci, ky, kx): tap = ky * ks + kx
+    if (tap == taps) db[o] += acc;
+    else dw[((size_t)o * n_real + c) * taps + tap] += acc;
+}
+
+// the (31,1) layers: CTA (x, group, b) holds taps group * G .. group * G + G - 1 of all 128 A-side channels; dw (m, n, taps) += fixed-order sums
+__global__ void wgrad_reduce_groups_kernel(const float* __restrict__ partial, int nx, int n_groups, int nb, int G, int npad, int taps, int m_real,
+                                           int n_real, float* __restrict__ dw, float* __restrict__ db) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;              // over (kh in [0, taps], m, n); kh == taps: the bias "tap"
+    const int total = (taps + 1) * m_real * n_real;
+    if (i >= total) return;
+    const int kh = i / (m_real * n_real), rem = i - kh * m_real * n_real;
+    const int o = rem / n_real, c = rem - o * n_real;
+    if (kh == taps && (c != 0 || db == nullptr)) return;
+    const int group = kh == taps ? 0 : kh / G, tl = kh == taps ? G : kh - group * G;
+    const size_t cta_stride = (size_t)kWgMaxTaps * 128 * npad;
+    const float* src = partial + ((size_t)tl * 128 + o) * npad + (kh == taps ? 0 : c);
+    float acc = 0.f;
+    for (int b = 0; b < nb; ++b)
+        for (int x = 0; x < nx; ++x) acc += src[(((size_t)b * n_groups + group) * nx + x) * cta_stride];
+    if (kh == taps) db[o] += acc;
+    else dw[((size_t)o * n_real + c) * taps + kh] += acc;
+}
+
+// out[c][h] += sum over (b, t) of a C8 planar tensor (B, CG, H, T, 8): two stages, fixed order (the indicator row of Decoder.convin's
+// weight gradient and that layer's bias gradient)
+__global__ void __launch_bounds__(256) row_channel_sum_c8_kernel(const uint4* __restrict__ x, int CG, int H, int T, float* __restrict__ partial) {
+    // grid (H, CG, B)
+    const uint4* row = x + (((size_t)blockIdx.z * CG + blockIdx.y) * H + blockIdx.x) * T;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < T; i += 256) {
+        const uint4 v = __ldcs(row + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(h[k]);
+            acc[2 * k] += f.x;
+            acc[2 * k + 1] += f.y;
+        }
     }
+    __shared__ float red[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        partial[(((size_t)blockIdx.z * CG + blockIdx.y) * H + blockIdx.x) * 8 + threadIdx.x] = v;
+    }
+}
+__global__ void row_channel_sum_finish_kernel(const float* __restrict__ partial, int B, int CG, int H, int c_real, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;              // over (c, h)
+    if (i >= c_real * H) return;
+    const int c = i / H, h = i - c * H;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc += partial[(((size_t)b * CG + (c >> 3)) * H + h) * 8 + (c & 7)];
+    out[i] += acc;
+}
+
+// db[c] += sum over pixels of a C8 planar tensor (B, CG, H, T, 8): per-CTA partials, fixed-order second stage (the transposed layers'
+// bias gradient: their weight-gradient GEMM has the layer INPUT on its A side)
+__global__ void __launch_bounds__(256) channel_sum_c8_partial_kernel(const uint4* __restrict__ x, int CG, long long hw, float* __restrict__ partial) {
+    // grid (chunks, CG, B); thread-strided over the pixels of one (b, cg) plane
+    const uint4* plane = x + ((size_t)blockIdx.z * CG + blockIdx.y) * hw;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 v = __ldcs(plane + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = __bfloat1622float2(h[k]);
+            acc[2 * k] += f.x;
+            acc[2 * k + 1] += f.y;
+        }
+    }
+    __shared__ float red[8][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5][k] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        partial[(((size_t)blockIdx.z * CG + blockIdx.y) * gridDim.x + blockIdx.x) * 8 + threadIdx.x] = v;
+    }
+}
+__global__ void channel_sum_c8_finish_kernel(const float* __restrict__ partial, int B, int CG, int chunks, int c_real, float* __restrict__ db) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_real) return;
+    const int cg = c >> 3, k = c & 7;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b)
+        for (int i = 0; i < chunks; ++i) acc += partial[(((size_t)b * CG + cg) * chunks + i) * 8 + k];
+    db[c] += acc;
 }
 
 // ---- element-wise pieces of the backward pass on bf16 tensors of ANY common layout -------------------------------------------------
@@ -237,37 +353,42 @@ __global__ void c8_to_p4_kernel(const uint4* __restrict__ c8, uint2* __restrict_
     }
 }
 
-static size_t wgrad_smem(int CGi, int CGo, int d, int ks) {
-    const int dd = ks == 3 ? d : 0;
-    const size_t TW = kStripTileT + 2 * dd;
+static size_t wgrad_smem(int CGi, int CGo, int halo, int xring, int zslots) {
+    const size_t TW = kStripTileT + 2 * halo;
     const size_t z_slot = (size_t)CGo * kStripTileT * 16;
     const size_t x_slot = ((size_t)CGi * TW * 16 + 127) & ~(size_t)127;
-    const size_t xring = ks == 3 ? 2 * dd + 3 : 2;
-    size_t s = 1024 + 4096 + kWgZSlots * z_slot + xring * x_slot + 4 * TW * 16;   // + the padded N groups read past the last X slot
-    // the A operand spans 16 channel groups (32 KB) from the start of a dZ slot, the ones operand 2 groups: keep both inside
-    s = std::max(s, (size_t)1024 + 4096 + (kWgZSlots - 1) * z_slot + 16 * (size_t)kStripTileT * 16 + 1024);
+    size_t s = 1024 + 4096 + zslots * z_slot + xring * x_slot + 8 * TW * 16;   // + the padded N groups read past the last B slot
+    // the A operand spans 16 channel groups (32 KB) from the start of an A slot, the ones operand NPAD/8 groups: keep both inside
+    s = std::max(s, (size_t)1024 + 4096 + (zslots - 1) * z_slot + 16 * (size_t)kStripTileT * 16 + 1024);
     return s;
 }
 
-template <int NPAD, int KS>
+template <int NPAD, int KH, int KW, int RS, int MW>
 static int launch_wgrad(const void* x, const void* dz, const WgradParams& p, dim3 grid, cudaStream_t stream) {
-    const size_t smem = wgrad_smem(p.CGi, p.CGo, p.d, KS);
+    const int halo = KW == 3 ? p.d : 0;
+    const int xring = (KH - 1) * (KH == 3 ? p.d : 1) + 1 + 2 * RS;
+    TT_REQUIRE(xring <= 16, "wgrad: ring of %d rows", xring);
+    const size_t smem = wgrad_smem(p.CGi, p.CGo, halo, xring, p.z_slots);
     TT_REQUIRE(smem <= 227 * 1024, "wgrad: %zu bytes of shared memory", smem);
     static size_t configured = 0;
     if (smem > configured) {
-        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad_same_kernel<NPAD, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel<NPAD, KH, KW, RS, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    const int dd = KS == 3 ? p.d : 0;
     CUtensorMap mx, mz;
-    int rc = make_row_map(&mx, x, p.B, p.CGi, p.H, p.T, kStripTileT + 2 * dd);
+    int rc = make_row_map(&mx, x, p.B, p.CGi, p.Hx, p.T, kStripTileT + 2 * halo);
     if (rc) return rc;
-    rc = make_row_map(&mz, dz, p.B, p.CGo, p.H, p.T, kStripTileT);
+    rc = make_row_map(&mz, dz, p.B, p.CGo, p.Hz, p.T, kStripTileT);
     if (rc) return rc;
-    wgrad_same_kernel<NPAD, KS><<<grid, kWgThreads, smem, stream>>>(mx, mz, p);
+    wgrad_kernel<NPAD, KH, KW, RS, MW><<<grid, kWgThreads, smem, stream>>>(mx, mz, p);
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;
+}
+
+static long long wgrad_strips(int B, int Hz, int T) {
+    const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
+    return std::max<long long>(1, std::min<long long>((2 * 148 + tiles - 1) / tiles, Hz));
 }
 
 }  // namespace tt
@@ -275,10 +396,31 @@ static int launch_wgrad(const void* x, const void* dz, const WgradParams& p, dim
 using namespace tt;
 
 extern "C" int64_t tt_wgrad_scratch_floats(int B, int H, int T) {
-    // upper bound over the strip splits tt_conv_wgrad_same chooses
+    // upper bound over the strip splits the weight-gradient entry points choose (H = rows of the A-side tensor)
     const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
-    const long long strips = std::max<long long>(1, std::min<long long>((2 * 148 + tiles - 1) / tiles, H));
-    return tiles * (strips + 1) * kWgMaxTaps * 32 * 32;
+    return tiles * (wgrad_strips(B, H, T) + 1) * kWgMaxTaps * kWgMaxM * 32;
+}
+
+// common launch: A side `a` (channels Ca, rows Ha), B side `bsrc` (channels Cb, rows Hb)
+template <int KH, int KW, int RS>
+static int wgrad_any(const void* bsrc, const void* a, float* dw, float* db, int B, int Cb, int Ca, int cb_real, int ca_real, int Hb, int Ha, int T,
+                     int dilation, float* scratch, cudaStream_t stream) {
+    WgradParams p;
+    p.partial = scratch;
+    p.B = B; p.T = T; p.Hz = Ha; p.Hx = Hb; p.CGi = Cb / 8; p.CGo = Ca / 8; p.d = dilation;
+    p.z_slots = kWgZSlots; p.tap_group = 0;
+    const long long strips = wgrad_strips(B, Ha, T);
+    p.rows_per_strip = (int)((Ha + strips - 1) / strips);
+    dim3 grid((T + kStripTileT - 1) / kStripTileT, (Ha + p.rows_per_strip - 1) / p.rows_per_strip, B);
+    const int n_ctas = (int)(grid.x * grid.y * grid.z);
+    const int npad = Cb >= 32 ? 32 : 16;
+    const int rc = npad == 32 ? launch_wgrad<32, KH, KW, RS, 2>(bsrc, a, p, grid, stream) : launch_wgrad<16, KH, KW, RS, 2>(bsrc, a, p, grid, stream);
+    if (rc) return rc;
+    const int total = (KH * KW + 1) * ca_real * cb_real;
+    wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, stream>>>(scratch, n_ctas, npad, KH * KW, ca_real, cb_real, dw, db);
+    tt_count_launches(1);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
 }
 
 extern "C" int tt_conv_wgrad_same(const void* x, const void* dz, float* dw, float* db, int B, int Cin, int Cout, int cin_real, int cout_real,
@@ -289,22 +431,64 @@ extern "C" int tt_conv_wgrad_same(const void* x, const void* dz, float* dw, floa
     TT_REQUIRE((k == 3 && dilation >= 1 && dilation <= 3) || k == 1, "wgrad: 3x3 (dilation 1..3) or 1x1");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
+    if (k == 3) return wgrad_any<3, 3, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, dilation, scratch, stream);
+    return wgrad_any<1, 1, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, 1, scratch, stream);
+}
+
+extern "C" int tt_conv_wgrad_updown(const void* fine, const void* coarse, float* dw, float* db, int B, int Cfine, int Ccoarse, int cfine_real,
+                                    int ccoarse_real, int Hfine, int Hcoarse, int T, int transposed, float* scratch, void* stream_) {
+    TT_REQUIRE(fine && coarse && dw && scratch, "null argument");
+    TT_REQUIRE(Cfine % 8 == 0 && Ccoarse % 8 == 0 && Cfine >= 8 && Ccoarse >= 8 && Cfine <= 32 && Ccoarse <= 64,
+               "wgrad_updown: fine side up to 32 channels, coarse side up to 64 (padded)");
+    TT_REQUIRE(Hfine >= 2 * Hcoarse + 2, "wgrad_updown: the fine tensor must hold rows 2q .. 2q+3 of every coarse row q");
+    if (B <= 0 || T <= 0 || Hcoarse <= 0) return TT_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // the coarse tensor (sconv: the output gradient; tconv: the layer input) is the A side, the fine one (rows 2q + kh) the B side
+    const int rc = wgrad_any<4, 1, 2>(fine, coarse, dw, transposed ? nullptr : db, B, Cfine, Ccoarse, cfine_real, ccoarse_real, Hfine, Hcoarse, T, 1,
+                                      scratch, stream);
+    if (rc || !transposed || !db) return rc;
+    // ConvTranspose2d bias: sum of the FINE tensor (the output gradient) over all pixels
+    const int CG = Cfine / 8, chunks = 64;
+    const long long hw = (long long)Hfine * T;
+    channel_sum_c8_partial_kernel<<<dim3(chunks, CG, B), 256, 0, stream>>>((const uint4*)fine, CG, hw, scratch);
+    channel_sum_c8_finish_kernel<<<1, 64, 0, stream>>>(scratch, B, CG, chunks, cfine_real, db);
+    tt_count_launches(2);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
+constexpr int kLatTapGroup = 7;       // vertical taps per CTA of the (H, 1)-kernel layers: (7 + 1 bias) x 64 accumulator columns = all of TMEM
+
+extern "C" int64_t tt_wgrad_lat_scratch_floats(int B, int H, int T) {
+    const long long nx = (T + kStripTileT - 1) / kStripTileT, groups = (H + kLatTapGroup - 1) / kLatTapGroup;
+    return std::max<long long>(nx * groups * B * kWgMaxTaps * 128 * 64, (long long)B * 8 * H * 8);
+}
+
+extern "C" int tt_conv_wgrad_lat(const void* tall, const void* flat, float* dw, float* db, float* tall_row_sums, int B, int Ctall, int Cflat,
+                                 int ctall_real, int cflat_real, int H, int T, float* scratch, void* stream_) {
+    TT_REQUIRE(tall && flat && dw && scratch, "null argument");
+    TT_REQUIRE(Ctall % 8 == 0 && Cflat % 8 == 0 && Ctall >= 8 && Ctall <= 64 && Cflat >= 8 && Cflat <= 128,
+               "wgrad_lat: up to 64 tall-side and 128 flat-side (padded) channels (got %d, %d)", Ctall, Cflat);
+    TT_REQUIRE(ctall_real >= 1 && ctall_real <= Ctall && cflat_real >= 1 && cflat_real <= Cflat && H >= 1, "wgrad_lat: bad sizes");
+    if (B <= 0 || T <= 0) return TT_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
     WgradParams p;
     p.partial = scratch;
-    p.B = B; p.H = H; p.T = T; p.CGi = Cin / 8; p.CGo = Cout / 8; p.d = dilation;
-    const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
-    const long long strips = std::max<long long>(1, std::min<long long>((2 * 148 + tiles - 1) / tiles, H));
-    p.rows_per_strip = (int)((H + strips - 1) / strips);
-    dim3 grid((T + kStripTileT - 1) / kStripTileT, (H + p.rows_per_strip - 1) / p.rows_per_strip, B);
-    const int n_ctas = (int)(grid.x * grid.y * grid.z);
-    const int npad = Cin == 32 ? 32 : 16;
-    int rc;
-    if (k == 3) rc = npad == 32 ? launch_wgrad<32, 3>(x, dz, p, grid, stream) : launch_wgrad<16, 3>(x, dz, p, grid, stream);
-    else rc = npad == 32 ? launch_wgrad<32, 1>(x, dz, p, grid, stream) : launch_wgrad<16, 1>(x, dz, p, grid, stream);
+    p.B = B; p.T = T; p.Hz = 1; p.Hx = H; p.CGi = Ctall / 8; p.CGo = Cflat / 8; p.d = 1;
+    p.rows_per_strip = 1; p.z_slots = 1; p.tap_group = kLatTapGroup;
+    const int groups = (H + kLatTapGroup - 1) / kLatTapGroup;
+    dim3 grid((T + kStripTileT - 1) / kStripTileT, groups, B);
+    const int rc = launch_wgrad<64, kLatTapGroup, 1, 1, 4>(tall, flat, p, grid, stream);
     if (rc) return rc;
-    const int total = (k * k + 1) * cout_real * cin_real;
-    wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, stream>>>(scratch, n_ctas, npad, k, cout_real, cin_real, dw, db);
+    const int total = (H + 1) * cflat_real * ctall_real;
+    wgrad_reduce_groups_kernel<<<(total + 127) / 128, 128, 0, stream>>>(scratch, (int)grid.x, groups, B, kLatTapGroup, 64, H, cflat_real, ctall_real, dw, db);
     tt_count_launches(1);
+    if (tall_row_sums) {
+        // (ctall_real, H) += sum over (b, t) of the tall tensor (after the reduction above has consumed the scratch: same stream)
+        row_channel_sum_c8_kernel<<<dim3(H, Ctall / 8, B), 256, 0, stream>>>((const uint4*)tall, Ctall / 8, H, T, scratch);
+        row_channel_sum_finish_kernel<<<(ctall_real * H + 127) / 128, 128, 0, stream>>>(scratch, B, Ctall / 8, H, ctall_real, tall_row_sums);
+        tt_count_launches(2);
+    }
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }

@@ -34,12 +34,12 @@ def conv_lat(x, w, b, latent_pad):
     return y
 
 
-def deconv_in(lat, w, bias_table, c0_pad, h0):
+def deconv_in(lat, w, bias_table, c0_pad, h0, act=True):
     _check_c8(lat, 'latents')
     B, CG, _, T, _ = lat.shape
     y = torch.empty((B, c0_pad // 8, h0, T, 8), dtype=torch.bfloat16, device=lat.device)
     with torch.cuda.device(lat.device):
-        _lib.check(_lib.lib().tt_deconv_in(_p(lat), _p(y), _p(w), _p(bias_table), B, CG * 8, c0_pad, h0, T, _s(lat)))
+        _lib.check(_lib.lib().tt_deconv_in(_p(lat), _p(y), _p(w), _p(bias_table), B, CG * 8, c0_pad, h0, T, int(act), _s(lat)))
     return y
 
 
@@ -96,7 +96,7 @@ def res_block_rs(x, w1, w2, bias, c_real, dilation, out=None, fold=False):
     return y
 
 
-def conv_down_strip(x, w, cout_pad):
+def conv_down_strip(x, w, cout_pad, act=True):
     """C8 planar input, or the packed 4-channel layout (B, H, T, 4) with weights from packing.pack_down_pairs (4 -> 8 channels)."""
     packed4 = x.dim() == 4
     if packed4:
@@ -109,17 +109,17 @@ def conv_down_strip(x, w, cout_pad):
         cin = CG * 8
     y = torch.empty((B, cout_pad // 8, (H - 4) // 2 + 1, T, 8), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_conv_down_strip(_p(x), _p(y), _p(w), B, cin, cout_pad, H, T, int(packed4), _s(x)))
+        _lib.check(_lib.lib().tt_conv_down_strip(_p(x), _p(y), _p(w), B, cin, cout_pad, H, T, int(packed4), int(act), _s(x)))
     return y
 
 
-def conv_up_strip(x, w, cout_pad, out_pad, packed4_out=False):
+def conv_up_strip(x, w, cout_pad, out_pad, packed4_out=False, act=True):
     _check_c8(x)
     B, CG, H, T, _ = x.shape
     Hout = 2 * H + 2 + out_pad
     y = torch.empty((B, Hout, T, 4) if packed4_out else (B, cout_pad // 8, Hout, T, 8), dtype=torch.bfloat16, device=x.device)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_conv_up_strip(_p(x), _p(y), _p(w), B, CG * 8, cout_pad, H, out_pad, T, int(packed4_out), _s(x)))
+        _lib.check(_lib.lib().tt_conv_up_strip(_p(x), _p(y), _p(w), B, CG * 8, cout_pad, H, out_pad, T, int(packed4_out), int(act), _s(x)))
     return y
 
 

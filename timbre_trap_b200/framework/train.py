@@ -281,6 +281,188 @@ class _ResFn(torch.autograd.Function):
         return gx, dw1, db1, dw2, db2, None, None, None
 
 
+def _wgrad_updown(fine8, coarse8, cfine, ccoarse, transposed):
+    """Weight / bias gradients of a (4,1) stride-(2,1) layer from C8 planar bf16 tensors (tt_conv_wgrad_updown, tensor cores):
+    sconv: (fine = layer input, coarse = dz) -> dW (ccoarse, cfine, 4, 1), db (ccoarse); tconv (transposed): (fine = dz, coarse = layer
+    input) -> dW (ccoarse, cfine, 4, 1) in the ConvTranspose2d layout, db (cfine)."""
+    B, CGf, Hf, T, _ = fine8.shape
+    Hc = coarse8.size(2)
+    lib = _lib.lib()
+    n = int(lib.tt_wgrad_scratch_floats(B, Hc, T))
+    key = (fine8.device, n)
+    if key not in _WGRAD_SCRATCH:
+        _WGRAD_SCRATCH.clear()
+        _WGRAD_SCRATCH[key] = torch.empty(n, dtype=torch.float32, device=fine8.device)
+    dw = torch.zeros((ccoarse, cfine, 4, 1), dtype=torch.float32, device=fine8.device)
+    db = torch.zeros(cfine if transposed else ccoarse, dtype=torch.float32, device=fine8.device)
+    _lib.check(lib.tt_conv_wgrad_updown(_p(fine8), _p(coarse8), _p(dw), _p(db), B, CGf * 8, coarse8.size(1) * 8, cfine, ccoarse, Hf, Hc, T,
+                                        int(transposed), _p(_WGRAD_SCRATCH[key]), _s(fine8)))
+    return dw, db
+
+
+class _DownFn(torch.autograd.Function):
+    """EncoderBlock.sconv + ELU (modules.py:626-629).  Backward in the inference layouts: ELU derivative (element-wise), weight gradient
+    (tensor-core GEMM over the pixel axis), data gradient = the transposed-conv forward kernel without activation on W seen as a
+    ConvTranspose2d weight (in = Cout, out = Cin)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, run, cin, cout):
+        y = run(x)
+        ctx.save_for_backward(x, y, weight)
+        ctx.meta = (cin, cout)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, weight = ctx.saved_tensors
+        cin, cout = ctx.meta
+        dz = _ew('tt_elu_bwd_bf16', gy.contiguous(), y)
+        x8 = _as_c8(x)
+        dw, db = _wgrad_updown(x8, dz, cin, cout, False)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            hin, hout = x8.size(2), dz.size(2)
+            wt = P.pack_up_strip(weight.detach().float(), torch.zeros(cin, device=weight.device))
+            gx = ops.conv_up_strip(dz, wt, P.pad8(cin), hin - 2 * hout - 2, packed4_out=x.dim() == 4, act=False)
+        return gx, dw, db, None, None, None
+
+
+class _UpFn(torch.autograd.Function):
+    """DecoderBlock.tconv + ELU (modules.py:685-688).  Backward: data gradient = the strided-conv forward kernel without activation on
+    W^T seen as a Conv2d weight (out = Cin, in = Cout)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, run, cin, cout):
+        y = run(x)
+        ctx.save_for_backward(x, y, weight)
+        ctx.meta = (cin, cout)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, y, weight = ctx.saved_tensors
+        cin, cout = ctx.meta
+        dz = _ew('tt_elu_bwd_bf16', gy.contiguous(), y)                          # layout of y (packed 4-channel for the last stage)
+        dw, db = _wgrad_updown(_as_c8(dz), x, cout, cin, True)
+        wd = weight.detach().float().contiguous()       # ConvTranspose2d (cin, cout, 4, 1) read as a Conv2d weight (out = cin, in = cout)
+        zero = torch.zeros(cin, device=weight.device)
+        if dz.dim() == 4:
+            gx = ops.conv_down_strip(dz, P.pack_down_pairs(wd, zero), P.pad8(cin), act=False)
+        else:
+            gx = ops.conv_down_strip(dz, P.pack_down_strip(wd, zero), P.pad8(cin), act=False)
+        return gx, dw, db, None, None, None
+
+
+_LAT_SCRATCH = {}
+
+
+def _wgrad_lat(tall8, flat8, ctall, cflat, dw, db, row_sums):
+    """tt_conv_wgrad_lat: accumulates into dw (cflat.., ctall, H, 1) [first cflat rows], db (cflat) and row_sums (ctall, H) (either may be None)."""
+    B, CGt, H, T, _ = tall8.shape
+    lib = _lib.lib()
+    n = int(lib.tt_wgrad_lat_scratch_floats(B, H, T))
+    key = (tall8.device, n)
+    if key not in _LAT_SCRATCH:
+        _LAT_SCRATCH.clear()
+        _LAT_SCRATCH[key] = torch.empty(n, dtype=torch.float32, device=tall8.device)
+    _lib.check(lib.tt_conv_wgrad_lat(_p(tall8), _p(flat8), _p(dw), _p(db), _p(row_sums), B, CGt * 8, flat8.size(1) * 8, ctall, cflat, H, T,
+                                     _p(_LAT_SCRATCH[key]), _s(tall8)))
+
+
+def _lat_tc_ok(c_tall, c_flat_pad):
+    """The tensor-core kernels of the two (H, 1)-kernel layers take up to 64 embedding / 128 latent channels (the base model's sizes)."""
+    return P.pad8(c_tall) in (16, 32, 64) and c_flat_pad <= 128
+
+
+class _LatFn(torch.autograd.Function):
+    """Encoder.convlat (modules.py:446, no activation).  Backward in the inference layouts: weight gradient = tap-grouped tensor-core GEMM
+    over (b, t); data gradient = the Decoder.convin forward kernel (a (H, 1) transposed conv) without activation on the same weights."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, run, c4, d, d_pad):
+        y = run(x)
+        ctx.save_for_backward(x, weight)
+        ctx.meta = (c4, d, d_pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        c4, d, d_pad = ctx.meta
+        gy = gy.contiguous()
+        dw = torch.zeros(weight.shape, dtype=torch.float32, device=x.device)
+        db = torch.zeros(d, dtype=torch.float32, device=x.device)
+        _wgrad_lat(x, gy, c4, d, dw, db, None)
+        # gx[ci, h, t] = sum_co W[co, ci, h] gy[co, t]: ConvTranspose2d with weight (in = co, out = ci, H, 1)
+        w, table = P.pack_deconv_in_film(weight.detach().float(), torch.zeros(c4, device=x.device), torch.ones(d, device=x.device),
+                                         torch.zeros(d, device=x.device), d_pad)
+        gx = ops.deconv_in(gy, w, table, P.pad8(c4), x.size(2), act=False)
+        return gx, dw, db, None, None, None, None
+
+
+def _pairs_to_c8(pairs):
+    """fp32 interleaved (B, F, T, 2) -> C8 planar bf16 (B, 1, F, T, 8) (tt_pairs_to_c8)."""
+    pairs = pairs.contiguous()
+    B, F_, T, _ = pairs.shape
+    out = torch.empty((B, 1, F_, T, 8), dtype=torch.bfloat16, device=pairs.device)
+    _lib.check(_lib.lib().tt_pairs_to_c8(_p(pairs), B * F_ * T, _p(out), _s(pairs)))
+    return out
+
+
+def _edge_tc_ok(x_like, c):
+    """The native backward of the first / last 3x3 conv needs the packed 4-channel stage layout (model_complexity 1 and 2)."""
+    return x_like.dim() == 4 and c <= 4
+
+
+class _InFn(torch.autograd.Function):
+    """Encoder.convin + ELU (modules.py:430-433) with a packed 4-channel output.  Backward: ELU derivative on the packed tensor; weight
+    gradient on the tensor cores (both operands re-laid out to C8 planar bf16 by one-pass kernels); data gradient (only the consistency
+    pass asks for it) = the Decoder.convout forward kernel on transposed, flipped weights."""
+
+    @staticmethod
+    def forward(ctx, coeffs, weight, bias, run, c0):
+        y = run(coeffs)
+        ctx.save_for_backward(coeffs, y, weight)
+        ctx.c0 = c0
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        coeffs, y, weight = ctx.saved_tensors
+        c0 = ctx.c0
+        dz = _ew('tt_elu_bwd_bf16', gy.contiguous(), y)
+        dw, db = _wgrad_same(_pairs_to_c8(coeffs), _as_c8(dz), 2, c0, 3, 1)
+        gx = None
+        if ctx.needs_input_grad[0]:
+            wt = weight.detach().float().transpose(0, 1).flip(2, 3).contiguous()          # (2, c0, 3, 3)
+            gx = ops.conv_out(dz, wt, torch.zeros(2, device=dz.device), c0)
+        return gx, dw, db, None, None
+
+
+class _OutFn(torch.autograd.Function):
+    """Decoder.convout (modules.py:543, no activation) on a packed 4-channel input.  Backward: weight gradient on the tensor cores;
+    data gradient = the Encoder.convin forward kernel without ELU on transposed, flipped weights."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, run, c):
+        y = run(x)
+        ctx.save_for_backward(x, weight)
+        ctx.c = c
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, weight = ctx.saved_tensors
+        c = ctx.c
+        gy = gy.contiguous()
+        dw, db = _wgrad_same(_as_c8(x), _pairs_to_c8(gy), c, 2, 3, 1)
+        wt = weight.detach().float().transpose(0, 1).flip(2, 3).contiguous()              # (c, 2, 3, 3)
+        B, F_, T, _ = gy.shape
+        gx = torch.empty((B, F_, T, 4), dtype=torch.bfloat16, device=gy.device)
+        _lib.check(_lib.lib().tt_conv_in(_p(gy), _p(gx), _p(wt), _p(torch.zeros(c, device=gy.device)), B, c, F_, T, 2, _s(gy)))
+        return gx, dw, db, None, None
+
+
 class _ActivationsFn(torch.autograd.Function):
     """TimbreTrap.to_activations (modules.py:271-289) on interleaved coefficients (B, F, T, 2) -> (B, F, T)."""
 
@@ -344,8 +526,11 @@ def _encoder(enc, coeffs):
     ch = enc.channels
     w_in, b_in, w_lat, b_lat = enc._packed()
     ci = enc.convin[0]
-    x = _ConvFn.apply(coeffs, ci.weight, ci.bias, lambda t: ops.conv_in(t, w_in, b_in, ch[0], packed4=enc.packed4),
-                      _geom(3, 3, ph=1, pw=1), 2, ch[0], True)
+    if enc.packed4:
+        x = _InFn.apply(coeffs, ci.weight, ci.bias, lambda t: ops.conv_in(t, w_in, b_in, ch[0], packed4=True), ch[0])
+    else:
+        x = _ConvFn.apply(coeffs, ci.weight, ci.bias, lambda t: ops.conv_in(t, w_in, b_in, ch[0], packed4=enc.packed4),
+                          _geom(3, 3, ph=1, pw=1), 2, ch[0], True)
     for i, blk in enumerate((enc.block1, enc.block2, enc.block3, enc.block4)):
         for rb in (blk.block1, blk.block2, blk.block3):
             x = _res(rb, x)
@@ -355,8 +540,10 @@ def _encoder(enc, coeffs):
             pack = P.pack_down_pairs if blk.packed4 else P.pack_down_strip
             (w,) = blk._cache.get((blk.sconv[0].weight, blk.sconv[0].bias), lambda: (pack(blk.sconv[0].weight, blk.sconv[0].bias),))
             return ops.conv_down_strip(t, w, P.pad8(blk.out_channels))
-        x = _ConvFn.apply(x, sc.weight, sc.bias, run_down, _geom(4, 1, sh=2), ch[i], ch[i + 1], True)
+        x = _DownFn.apply(x, sc.weight, sc.bias, run_down, ch[i], ch[i + 1])
     cl = enc.convlat
+    if _lat_tc_ok(ch[4], enc.latent_pad):
+        return _LatFn.apply(x, cl.weight, cl.bias, lambda t: ops.conv_lat(t, w_lat, b_lat, enc.latent_pad), ch[4], enc.latent_size, enc.latent_pad)
     return _ConvFn.apply(x, cl.weight, cl.bias, lambda t: ops.conv_lat(t, w_lat, b_lat, enc.latent_pad),
                          _geom(cl.weight.size(2), 1), ch[4], enc.latent_size, False)
 
@@ -379,6 +566,19 @@ class _IndicatorFn(torch.autograd.Function):
     def backward(ctx, gy):
         lat, y, weight = ctx.saved_tensors
         flag, d, c0 = ctx.meta
+        if _lat_tc_ok(c0, lat.size(1) * 8):
+            # inference layouts end to end: ELU derivative, tap-grouped tensor-core weight gradient (rows 0 .. D-1; the indicator row and
+            # the bias are row sums of dz), data gradient = the Encoder.convlat forward kernel on the first D weight rows
+            dz = _ew('tt_elu_bwd_bf16', gy.contiguous(), y)
+            h0 = y.size(2)
+            dw = torch.zeros(weight.shape, dtype=torch.float32, device=lat.device)
+            rows = torch.zeros((c0, h0), dtype=torch.float32, device=lat.device)
+            _wgrad_lat(dz, lat, c0, d, dw, None, rows)
+            dw[d, :, :, 0] = flag * rows
+            db = rows.sum(dim=1)
+            d_pad = lat.size(1) * 8
+            glat = ops.conv_lat(dz, P.pack_lat(weight.detach().float()[:d], d_pad), torch.zeros(d_pad, device=lat.device), d_pad)
+            return glat, dw, db, None, None, None, None
         geom = _geom(weight.size(2), 1)
         ln = _nchw(lat, d)                                                       # (B, D, 1, T)
         full = torch.cat((ln, torch.full_like(ln[:, :1], flag)), dim=1)          # (B, D+1, 1, T)
@@ -403,10 +603,12 @@ def _decoder(dec, lat, reconstruct):
         def run_up(t, blk=blk):
             (w,) = blk._cache.get((blk.tconv[0].weight, blk.tconv[0].bias), lambda: (P.pack_up_strip(blk.tconv[0].weight, blk.tconv[0].bias),))
             return ops.conv_up_strip(t, w, P.pad8(blk.out_channels), blk.out_pad, packed4_out=blk.packed4)
-        x = _ConvTFn.apply(x, tc.weight, tc.bias, run_up, _geom(4, 1, sh=2), ch[i], ch[i + 1])
+        x = _UpFn.apply(x, tc.weight, tc.bias, run_up, ch[i], ch[i + 1])
         for rb in (blk.block1, blk.block2, blk.block3):
             x = _res(rb, x)
     co = dec.convout
+    if dec.packed4:
+        return _OutFn.apply(x, co.weight, co.bias, lambda t: ops.conv_out(t, w_out, b_out, ch[4]), ch[4])
     return _ConvFn.apply(x, co.weight, co.bias, lambda t: ops.conv_out(t, w_out, b_out, ch[4]), _geom(3, 3, ph=1, pw=1), ch[4], 2, False)
 
 
