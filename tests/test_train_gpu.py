@@ -150,7 +150,7 @@ def test_training_reduces_the_loss():
 
 
 @pytest.mark.parametrize('C,H,T,k,d,B', [(4, 23, 256, 3, 1, 2), (8, 17, 384, 3, 2, 1), (16, 33, 200, 3, 3, 2), (32, 9, 128, 3, 1, 3), (32, 40, 512, 1, 1, 1),
-                                           (3, 11, 136, 1, 1, 2), (16, 300, 128, 3, 2, 1)])
+                                           (3, 11, 136, 1, 1, 2), (16, 300, 128, 3, 2, 1), (8, 20, 256, 3, 3, 1), (2, 35, 640, 3, 3, 2)])
 def test_tensor_core_weight_gradient(C, H, T, k, d, B):
     """tt_conv_wgrad_same (MN-major tcgen05 GEMM over the pixel axis, deterministic two-stage reduction) against torch autograd on the
     same bf16-rounded operands; products of bf16 values are exact in fp32, so only the summation order differs."""

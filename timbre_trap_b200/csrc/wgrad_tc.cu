@@ -44,10 +44,14 @@ struct WgradParams {
 //   (4,1) stride (2,1) (KH = 4, KW = 1, RS = 2):  DH = 1, row0 = 0  (EncoderBlock.sconv; DecoderBlock.tconv with the two sides swapped)
 // shared memory plan (bytes): [barriers 1 KB][ones 4 KB][A ring][B ring]; the A operand reads 16 channel groups = 32 KB from its slot, the
 // B operand NPAD/8 groups: both stay inside the allocation because the B ring follows and the allocation is padded (see wgrad_smem)
-template <int NPAD, int KH, int KW, int RS, int MW>
+// KXN (3x3 with ONE B-side channel group, i.e. C <= 8 - the two largest stages): the three horizontal taps are the N-GROUPS of one
+// MMA - the B descriptor's group stride is the tap step d * 16 bytes instead of the plane stride - so a K step costs 3 + 1 MMAs
+// instead of 9 + 1; accumulator columns of vertical tap ky: [kx][8 channels] (+ one unused group), NPAD = 32.
+template <int NPAD, int KH, int KW, int RS, int MW, bool KXN = false>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
                                                               const WgradParams p) {
-    constexpr int TAPS = KH * KW;
+    static_assert(!KXN || (KH == 3 && KW == 3 && NPAD == 32), "KXN is the 3x3 single-group form");
+    constexpr int TAPS = KXN ? KH : KH * KW;
     constexpr uint32_t need = (TAPS + 1) * NPAD;
     constexpr uint32_t ncols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
     static_assert(need <= 512, "TMEM columns");
@@ -131,10 +135,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                 for (int ky = 0; ky < KH; ++ky) {
                     const int xr = r * RS + ky * DH;                   // relative B-side row of this vertical tap
                     const uint32_t xa = x0 + (uint32_t)(xr % xring) * x_slot;
+                    if constexpr (KXN) {
+                        const uint64_t db = umma::make_desc(xa + (uint32_t)s * 256u, 128u, (uint32_t)d * 16u);
+                        umma::mma_bf16(tmem + (uint32_t)(ky * NPAD), da, db, idesc, !(first && s == 0));
+                    } else {
 #pragma unroll
-                    for (int kx = 0; kx < KW; ++kx) {
-                        const uint64_t db = umma::make_desc(xa + (uint32_t)(kx * d) * 16u + (uint32_t)s * 256u, 128u, x_plane);
-                        umma::mma_bf16(tmem + (uint32_t)((ky * KW + kx) * NPAD), da, db, idesc, !(first && s == 0));
+                        for (int kx = 0; kx < KW; ++kx) {
+                            const uint64_t db = umma::make_desc(xa + (uint32_t)(kx * d) * 16u + (uint32_t)s * 256u, 128u, x_plane);
+                            umma::mma_bf16(tmem + (uint32_t)((ky * KW + kx) * NPAD), da, db, idesc, !(first && s == 0));
+                        }
                     }
                 }
                 const uint64_t dones = umma::make_desc(ones0 + (uint32_t)s * 256u, 128u, (uint32_t)kStripTileT * 16u);
@@ -179,15 +188,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
 // dW (m, n, taps) and db (m) += fixed-order sums of the per-CTA partials (m = A-side channel, n = B-side channel: (co, ci, kh, kw) for a
 // regular conv, (ci, co, kh, kw) - the ConvTranspose2d weight layout - when the two sides are swapped)
+// kxn: the partials hold 3 vertical taps of [kx][8 channels] columns (see KXN above); taps stays 9 for the output layout
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, int npad, int taps, int m_real, int n_real, float* __restrict__ dw,
-                                    float* __restrict__ db) {
+                                    float* __restrict__ db, int kxn) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;              // over (tap' in [0, taps], m, n)
     const int total = (taps + 1) * m_real * n_real;
     if (i >= total) return;
     const int tap = i / (m_real * n_real), rem = i - tap * m_real * n_real;
     const int o = rem / n_real, c = rem - o * n_real;
     if (tap == taps && (c != 0 || db == nullptr)) return;
-    const float* src = partial + ((size_t)tap * kWgMaxM + o) * npad + (tap == taps ? 0 : c);
+    const int ptap = kxn ? (tap == taps ? 3 : tap / 3) : tap;         // accumulator block inside a CTA's partial
+    const int pcol = tap == taps ? 0 : (kxn ? (tap % 3) * 8 + c : c);
+    const float* src = partial + ((size_t)ptap * kWgMaxM + o) * npad + pcol;
     const size_t stride = (size_t)kWgMaxTaps * kWgMaxM * npad;
     float acc = 0.f;
     for (int k = 0; k < n_ctas; ++k) acc += src[(size_t)k * stride];
@@ -363,7 +375,7 @@ static size_t wgrad_smem(int CGi, int CGo, int halo, int xring, int zslots) {
     return s;
 }
 
-template <int NPAD, int KH, int KW, int RS, int MW>
+template <int NPAD, int KH, int KW, int RS, int MW, bool KXN = false>
 static int launch_wgrad(const void* x, const void* dz, const WgradParams& p, dim3 grid, cudaStream_t stream) {
     const int halo = KW == 3 ? p.d : 0;
     const int xring = (KH - 1) * (KH == 3 ? p.d : 1) + 1 + 2 * RS;
@@ -372,7 +384,7 @@ static int launch_wgrad(const void* x, const void* dz, const WgradParams& p, dim
     TT_REQUIRE(smem <= 227 * 1024, "wgrad: %zu bytes of shared memory", smem);
     static size_t configured = 0;
     if (smem > configured) {
-        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel<NPAD, KH, KW, RS, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad_kernel<NPAD, KH, KW, RS, MW, KXN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     CUtensorMap mx, mz;
@@ -380,7 +392,7 @@ static int launch_wgrad(const void* x, const void* dz, const WgradParams& p, dim
     if (rc) return rc;
     rc = make_row_map(&mz, dz, p.B, p.CGo, p.Hz, p.T, kStripTileT);
     if (rc) return rc;
-    wgrad_kernel<NPAD, KH, KW, RS, MW><<<grid, kWgThreads, smem, stream>>>(mx, mz, p);
+    wgrad_kernel<NPAD, KH, KW, RS, MW, KXN><<<grid, kWgThreads, smem, stream>>>(mx, mz, p);
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;
@@ -413,11 +425,20 @@ static int wgrad_any(const void* bsrc, const void* a, float* dw, float* db, int 
     p.rows_per_strip = (int)((Ha + strips - 1) / strips);
     dim3 grid((T + kStripTileT - 1) / kStripTileT, (Ha + p.rows_per_strip - 1) / p.rows_per_strip, B);
     const int n_ctas = (int)(grid.x * grid.y * grid.z);
-    const int npad = Cb >= 32 ? 32 : 16;
-    const int rc = npad == 32 ? launch_wgrad<32, KH, KW, RS, 2>(bsrc, a, p, grid, stream) : launch_wgrad<16, KH, KW, RS, 2>(bsrc, a, p, grid, stream);
+    int npad = Cb >= 32 ? 32 : 16;
+    int rc, kxn = 0;
+    if constexpr (KH == 3 && KW == 3) {
+        if (Cb == 8) { kxn = 1; npad = 32; }
+    }
+    if (kxn) {
+        if constexpr (KH == 3 && KW == 3) rc = launch_wgrad<32, KH, KW, RS, 2, true>(bsrc, a, p, grid, stream);
+        else rc = TT_ERR_INVALID;
+    } else {
+        rc = npad == 32 ? launch_wgrad<32, KH, KW, RS, 2>(bsrc, a, p, grid, stream) : launch_wgrad<16, KH, KW, RS, 2>(bsrc, a, p, grid, stream);
+    }
     if (rc) return rc;
     const int total = (KH * KW + 1) * ca_real * cb_real;
-    wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, stream>>>(scratch, n_ctas, npad, KH * KW, ca_real, cb_real, dw, db);
+    wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, stream>>>(scratch, n_ctas, npad, KH * KW, ca_real, cb_real, dw, db, kxn);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;

@@ -230,6 +230,20 @@ def _to_layout_of(c8, ref):
 
 
 _WGRAD_SCRATCH = {}
+_BW_PACKS = {'epoch': -1}
+
+
+def _bw_pack(weight, tag, build):
+    """Packed (kernel-layout) weights of the backward pass, built once per optimisation step per layer: the same layer runs backward
+    two to four times per step (two encoder, four decoder passes), and every pack is a handful of tiny launches."""
+    if _BW_PACKS['epoch'] != _PackedCache.epoch:
+        _BW_PACKS.clear()
+        _BW_PACKS['epoch'] = _PackedCache.epoch
+    key = (weight.data_ptr(), weight._version, tag)
+    if key not in _BW_PACKS:
+        with torch.no_grad():
+            _BW_PACKS[key] = build()
+    return _BW_PACKS[key]
 
 
 def _wgrad_same(x8, dz8, cin, cout, k, d):
@@ -264,17 +278,19 @@ class _ResFn(torch.autograd.Function):
     def backward(ctx, gy):
         x, y, w1, b1, w2 = ctx.saved_tensors
         c, d = ctx.meta
-        w1f, w2f = w1.detach().float(), w2.detach().float()
         n = max(16, P.pad8(c))
+        w1_fwd, b1_pad = _bw_pack(w1, 'res3x3', lambda: (P.pack_res3x3(w1.detach().float()), P.pad_vec(b1, n)))
+        w2_t = _bw_pack(w2, 'res1x1T', lambda: P.pack_res1x1(w2.detach().float().transpose(0, 1).contiguous()))
+        w1_t = _bw_pack(w1, 'res3x3T', lambda: P.pack_res3x3(w1.detach().float().transpose(0, 1).flip(2, 3).contiguous()))
         gy = gy.contiguous()
         dz2 = _as_c8(_ew('tt_res_out_bwd_bf16', gy, y, x))                       # gy * ELU'(z2), activated 1x1 output = y - x
         x8 = _as_c8(x)
-        a1 = ops.conv_same(x8, P.pack_res3x3(w1f), P.pad_vec(b1, n), 3, d, act=True)    # the inner activation, as the forward staged it
+        a1 = ops.conv_same(x8, w1_fwd, b1_pad, 3, d, act=True)                   # the inner activation, as the forward staged it
         dw2, db2 = _wgrad_same(a1, dz2, c, c, 1, 1)
-        da1 = ops.conv_same(dz2, P.pack_res1x1(w2f.transpose(0, 1).contiguous()), None, 1, 1)
+        da1 = ops.conv_same(dz2, w2_t, None, 1, 1)
         dz1 = _ew('tt_elu_bwd_bf16', da1, a1)
         dw1, db1 = _wgrad_same(x8, dz1, c, c, 3, d)
-        gx8 = ops.conv_same(dz1, P.pack_res3x3(w1f.transpose(0, 1).flip(2, 3).contiguous()), None, 3, d)
+        gx8 = ops.conv_same(dz1, w1_t, None, 3, d)
         gx = _to_layout_of(gx8, x)
         one = torch.ones((), dtype=torch.float32, device=gx.device)
         _lib.check(_lib.lib().tt_add_scaled_bf16(_p(gy), _p(gx), _p(one.reshape(1)), _p(gx), gx.numel(), _s(gx)))     # gx = gy + gx
@@ -322,7 +338,7 @@ class _DownFn(torch.autograd.Function):
         gx = None
         if ctx.needs_input_grad[0]:
             hin, hout = x8.size(2), dz.size(2)
-            wt = P.pack_up_strip(weight.detach().float(), torch.zeros(cin, device=weight.device))
+            wt = _bw_pack(weight, 'downT', lambda: P.pack_up_strip(weight.detach().float(), torch.zeros(cin, device=weight.device)))
             gx = ops.conv_up_strip(dz, wt, P.pad8(cin), hin - 2 * hout - 2, packed4_out=x.dim() == 4, act=False)
         return gx, dw, db, None, None, None
 
@@ -344,12 +360,10 @@ class _UpFn(torch.autograd.Function):
         cin, cout = ctx.meta
         dz = _ew('tt_elu_bwd_bf16', gy.contiguous(), y)                          # layout of y (packed 4-channel for the last stage)
         dw, db = _wgrad_updown(_as_c8(dz), x, cout, cin, True)
-        wd = weight.detach().float().contiguous()       # ConvTranspose2d (cin, cout, 4, 1) read as a Conv2d weight (out = cin, in = cout)
-        zero = torch.zeros(cin, device=weight.device)
-        if dz.dim() == 4:
-            gx = ops.conv_down_strip(dz, P.pack_down_pairs(wd, zero), P.pad8(cin), act=False)
-        else:
-            gx = ops.conv_down_strip(dz, P.pack_down_strip(wd, zero), P.pad8(cin), act=False)
+        # ConvTranspose2d (cin, cout, 4, 1) read as a Conv2d weight (out = cin, in = cout)
+        pack = P.pack_down_pairs if dz.dim() == 4 else P.pack_down_strip
+        wd = _bw_pack(weight, 'upT', lambda: pack(weight.detach().float().contiguous(), torch.zeros(cin, device=weight.device)))
+        gx = ops.conv_down_strip(dz, wd, P.pad8(cin), act=False)
         return gx, dw, db, None, None, None
 
 
@@ -394,8 +408,8 @@ class _LatFn(torch.autograd.Function):
         db = torch.zeros(d, dtype=torch.float32, device=x.device)
         _wgrad_lat(x, gy, c4, d, dw, db, None)
         # gx[ci, h, t] = sum_co W[co, ci, h] gy[co, t]: ConvTranspose2d with weight (in = co, out = ci, H, 1)
-        w, table = P.pack_deconv_in_film(weight.detach().float(), torch.zeros(c4, device=x.device), torch.ones(d, device=x.device),
-                                         torch.zeros(d, device=x.device), d_pad)
+        w, table = _bw_pack(weight, 'latT', lambda: P.pack_deconv_in_film(weight.detach().float(), torch.zeros(c4, device=x.device),
+                                                                          torch.ones(d, device=x.device), torch.zeros(d, device=x.device), d_pad))
         gx = ops.deconv_in(gy, w, table, P.pad8(c4), x.size(2), act=False)
         return gx, dw, db, None, None, None, None
 
@@ -434,8 +448,9 @@ class _InFn(torch.autograd.Function):
         dw, db = _wgrad_same(_pairs_to_c8(coeffs), _as_c8(dz), 2, c0, 3, 1)
         gx = None
         if ctx.needs_input_grad[0]:
-            wt = weight.detach().float().transpose(0, 1).flip(2, 3).contiguous()          # (2, c0, 3, 3)
-            gx = ops.conv_out(dz, wt, torch.zeros(2, device=dz.device), c0)
+            wt, zb = _bw_pack(weight, 'inT', lambda: (weight.detach().float().transpose(0, 1).flip(2, 3).contiguous(),      # (2, c0, 3, 3)
+                                                      torch.zeros(2, device=dz.device)))
+            gx = ops.conv_out(dz, wt, zb, c0)
         return gx, dw, db, None, None
 
 
@@ -456,10 +471,11 @@ class _OutFn(torch.autograd.Function):
         c = ctx.c
         gy = gy.contiguous()
         dw, db = _wgrad_same(_as_c8(x), _pairs_to_c8(gy), c, 2, 3, 1)
-        wt = weight.detach().float().transpose(0, 1).flip(2, 3).contiguous()              # (c, 2, 3, 3)
+        wt, zb = _bw_pack(weight, 'outT', lambda: (weight.detach().float().transpose(0, 1).flip(2, 3).contiguous(),         # (c, 2, 3, 3)
+                                                   torch.zeros(c, device=gy.device)))
         B, F_, T, _ = gy.shape
         gx = torch.empty((B, F_, T, 4), dtype=torch.bfloat16, device=gy.device)
-        _lib.check(_lib.lib().tt_conv_in(_p(gy), _p(gx), _p(wt), _p(torch.zeros(c, device=gy.device)), B, c, F_, T, 2, _s(gy)))
+        _lib.check(_lib.lib().tt_conv_in(_p(gy), _p(gx), _p(wt), _p(zb), B, c, F_, T, 2, _s(gy)))
         return gx, dw, db, None, None
 
 
@@ -577,7 +593,8 @@ class _IndicatorFn(torch.autograd.Function):
             dw[d, :, :, 0] = flag * rows
             db = rows.sum(dim=1)
             d_pad = lat.size(1) * 8
-            glat = ops.conv_lat(dz, P.pack_lat(weight.detach().float()[:d], d_pad), torch.zeros(d_pad, device=lat.device), d_pad)
+            wl, zl = _bw_pack(weight, 'decinT', lambda: (P.pack_lat(weight.detach().float()[:d], d_pad), torch.zeros(d_pad, device=lat.device)))
+            glat = ops.conv_lat(dz, wl, zl, d_pad)
             return glat, dw, db, None, None, None, None
         geom = _geom(weight.size(2), 1)
         ln = _nchw(lat, d)                                                       # (B, D, 1, T)
