@@ -360,19 +360,26 @@ def run_ours(args, rank, world, local_rank):
         clip = ((torch.rand((1, 1, 1200 * L), generator=gh) * 2 - 1) * 0.5).to(device)      # every rank holds the clip
         for _ in range(1):
             model.transcribe_sharded(clip, group=group)
-            model.reconstruct_sharded(clip, group=group)
+            model.transcribe_and_reconstruct_sharded(clip, group=group)
         barrier()
-        a.record()
         n_hour = 2
+        a.record()
         for _ in range(n_hour):
             h_act = model.transcribe_sharded(clip, group=group)
-            h_wav = model.reconstruct_sharded(clip, group=group)
+        b.record()
+        barrier()
+        h_ms_t = max_over_ranks(a.elapsed_time(b)) / n_hour
+        a.record()
+        for _ in range(n_hour):
+            h_act, h_wav = model.transcribe_and_reconstruct_sharded(clip, group=group)
         b.record()
         barrier()
         h_ms = max_over_ranks(a.elapsed_time(b)) / n_hour
-        hour = dict(workload='BASELINE.json configs[4]: transcribe_sharded + reconstruct_sharded of one 3600 s clip (2401 chunks), contiguous '
-                             'block ranges per rank with half-block halos, all_gather of the frames, one scalar MAX all-reduce',
-                    ms=h_ms, audio_s_per_s=3600.0 / (h_ms * 1e-3), activations=list(h_act.shape), audio_out=list(h_wav.shape))
+        hour = dict(workload='BASELINE.json configs[4]: one 3600 s clip (1200 blocks -> 2401 overlapped chunks) sharded by contiguous block ranges '
+                             'over the ranks with half-block halos, all_gather of the frames (and one scalar MAX all-reduce for the audio)',
+                    transcribe_ms=h_ms_t, transcribe_audio_s_per_s=3600.0 / (h_ms_t * 1e-3),
+                    transcribe_and_reconstruct_ms=h_ms, transcribe_and_reconstruct_audio_s_per_s=3600.0 / (h_ms * 1e-3),
+                    activations=list(h_act.shape), audio_out=list(h_wav.shape))
         del clip, h_act, h_wav
         torch.cuda.empty_cache()
 

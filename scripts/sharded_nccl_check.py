@@ -28,6 +28,8 @@ act = model.transcribe(audio)
 wav = model.reconstruct(audio)
 act_s = model.transcribe_sharded(audio)                 # group=None -> WORLD: sharded by rank AND gathered
 wav_s = model.reconstruct_sharded(audio)
+act_b, wav_b = model.transcribe_and_reconstruct_sharded(audio)
+assert torch.equal(act_b, act_s) and torch.equal(wav_b, wav_s)
 torch.cuda.synchronize()
 res = dict(rank=rank, world=world, n_blocks=n_blocks, act_shape=list(act_s.shape), wav_shape=list(wav_s.shape),
            act_equal=bool(torch.equal(act_s, act)), act_max_diff=float((act_s - act).abs().max()),

@@ -220,6 +220,11 @@ def test_sharded_long_clip_equals_unsharded():
     whole = model.reconstruct(audio)
     stitched = torch.cat([w / top for w, _ in peaks], dim=-1)
     assert float((stitched - whole).abs().max()) <= 2e-6
+    # the shared-encoder pair: same activations; with one rank (= the whole clip) the audio equals reconstruct()
+    both = [model.transcribe_and_reconstruct_sharded(audio, rank=r, world=world, gather=False) for r in range(world)]
+    assert torch.equal(torch.cat([a for a, _ in both], dim=-1), act)
+    a1, w1 = model.transcribe_and_reconstruct_sharded(audio, rank=0, world=1)
+    assert torch.equal(a1, act) and torch.equal(w1, whole)
     # more ranks than blocks: empty shards are legal
     tiny = tonal_clip(L, SMALL['sample_rate'], seed=5).cuda()
     parts = [model.transcribe_sharded(tiny, rank=r, world=2, gather=False) for r in range(2)]

@@ -707,6 +707,24 @@ class TimbreTrap(nn.Module):
                 dist.all_reduce(torch.zeros(1, device=audio.device), op=dist.ReduceOp.MAX, group=group)
         return _gather_frames(local, -1, L, audio, L, group, world) if gather else local
 
+    def transcribe_and_reconstruct_sharded(self, audio, group=None, rank=None, world=None, gather=True):
+        """Both results for a clip every rank holds from ONE encoder pass per rank (transcribe_sharded + reconstruct_sharded run two)."""
+        group, rank, world = _resolve_group(group, rank, world)
+        sub, b0, b1 = self.shard_audio(audio, rank, world)
+        M, F, L = self.sliCQ.max_window_length, self.sliCQ.n_bins, self.sliCQ.block_length
+        if b1 > b0:
+            act, rec = self._chunked(sub, True, True, prepadded=True)
+            wav = self._decode_shared_peak(rec.permute(0, 3, 1, 2), group)
+        else:
+            act = torch.empty((audio.size(0), F, 0), dtype=torch.float32, device=audio.device)
+            wav = torch.empty((audio.size(0), 1, 0), dtype=torch.float32, device=audio.device)
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(torch.zeros(1, device=audio.device), op=dist.ReduceOp.MAX, group=group)
+        if not gather:
+            return act, wav
+        return _gather_frames(act, -1, M, audio, L, group, world), _gather_frames(wav, -1, L, audio, L, group, world)
+
     def forward(self, audio, consistency=False):
         """modules.py:338-393 (inference semantics; the training step with gradients is framework.train_step)."""
         with torch.no_grad():
