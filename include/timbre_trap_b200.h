@@ -49,6 +49,9 @@ int tt_cqt_plan_create(tt_cqt_plan** plan, int block_length, int n_bins, int max
                        const float* win_packed, const float* dual_packed, int n_taps,
                        int max_blocks_per_launch);
 int tt_cqt_plan_destroy(tt_cqt_plan* plan);
+/* Number of internal streams ("lanes", 1..4, default 2) consecutive groups of `max_blocks_per_launch` blocks rotate over: the FFT
+ * front end of one group overlaps the HBM-bound per-bin kernel of another.  Results do not depend on it. */
+int tt_cqt_plan_set_lanes(tt_cqt_plan* plan, int n_lanes);
 /* bytes of device scratch held by the plan */
 int64_t tt_cqt_plan_scratch_bytes(const tt_cqt_plan* plan);
 
@@ -186,6 +189,10 @@ int tt_conv_out_crossfade(const void* x, const float* window, const float* w, co
 /* out = x + (*scale) * e on bf16 tensors of one layout, n elements (multiple of 8): the decoder's skip connection with the learnable
  * weight of TimbreTrap.apply_skip_connections read from device memory; out may alias x */
 int tt_add_scaled_bf16(const void* x, const void* e, const float* scale, void* out, int64_t n, void* stream);
+/* *out = sum of a[i] * b[i] over two bf16 tensors of one layout (gradient of a skip connection's scalar weight in the loss step);
+ * deterministic two-stage reduction through `scratch` (tt_dot_scratch_floats() floats) */
+int tt_dot_scratch_floats(void);
+int tt_dot_bf16(const void* a, const void* b, int64_t n, float* out, float* scratch, void* stream);
 /* (x) -> interleaved (x, 0): a one-channel feature map (TimbreTrapMag / MagDB encoder input, modules.py:927-950, 1019-1031) in the
  * two-channel layout tt_conv_in reads */
 int tt_widen_pairs(const float* x, int64_t n, float* out, void* stream);

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, 'timbre_trap_b200', 'libtimbretrap_b200.so')
 text = subprocess.run(['cuobjdump', '-sass', so], capture_output=True, text=True, check=True).stdout
 names = subprocess.run(['c++filt'], input='\n'.join(re.findall(r'Function : (\S+)', text)), capture_output=True, text=True).stdout.split('\n')
-OPS = ('UTCHMMA', 'UTMALDG', 'LDTM', 'STTM', 'UTCBAR', 'SYNCS', 'HMMA', 'LDGSTS', 'FFMA2', 'RED', 'ATOM')
+OPS = ('UTCHMMA', 'UTMALDG', 'LDTM', 'STTM', 'UTCBAR', 'SYNCS', 'HMMA', 'LDGSTS', 'FFMA2', 'FADD2', 'REDG', 'ATOMG')
 rows, cur, i = [], None, -1
 for line in text.split('\n'):
     m = re.search(r'Function : (\S+)', line)

@@ -64,11 +64,13 @@ def test_transposed_roles(Cin, Cout, KH, sh, op, H):
     assert torch.allclose(TR._channel_sum(gyc).cpu(), gy.sum(dim=(0, 2, 3)), atol=1e-3, rtol=1e-4)
 
 
-def _setup():
+def _setup(skip=False):
     from oracle import model_ref as R
     from timbre_trap_b200.framework import TimbreTrap
-    model = TimbreTrap(latent_size=None, model_complexity=1, **SMALL)
+    model = TimbreTrap(latent_size=None, model_complexity=1, skip_connections=skip, **SMALL)
     sd = R.init_state_dict(model.sliCQ.n_bins, None, 1, seed=3)
+    if skip:
+        sd['skip_weights'] = torch.tensor([0.9, 1.1, 0.8, 1.2, 0.7])
     model.load_state_dict(sd)
     model = model.cuda()
     c = R.CQTRef(SMALL['n_octaves'], SMALL['bins_per_octave'], SMALL['sample_rate'], SMALL['secs_per_block'])
@@ -94,9 +96,10 @@ def _oracle_grads(R, sd, c, audio, gt):
     return {k: v.grad for k, v in sd.items()}, losses, float(total.detach())
 
 
-def test_step_gradients_match_oracle_autograd():
+@pytest.mark.parametrize('skip', [False, True])
+def test_step_gradients_match_oracle_autograd(skip):
     from timbre_trap_b200.framework.train import TrainStep
-    R, model, sd, c, audio, gt = _setup()
+    R, model, sd, c, audio, gt = _setup(skip)
     want, want_losses, want_total = _oracle_grads(R, sd, c, audio, gt)
     ts = TrainStep(model)
     out = ts.losses(audio.cuda(), gt.cuda())

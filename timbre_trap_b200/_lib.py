@@ -25,6 +25,7 @@ SIGNATURES = {
     'tt_cqt_plan_create': (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int32_p, c_int32_p, c_int32_p,
                                    c_int32_p, c_float_p, c_float_p, c_int, c_int]),
     'tt_cqt_plan_destroy': (c_int, [c_void_p]),
+    'tt_cqt_plan_set_lanes': (c_int, [c_void_p, c_int]),
     'tt_cqt_plan_scratch_bytes': (c_int64, [c_void_p]),
     'tt_cqt_forward': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'tt_cqt_inverse': (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]),
@@ -42,6 +43,8 @@ SIGNATURES = {
     'tt_conv_out': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'tt_conv_out_crossfade': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p] * 3),
     'tt_add_scaled_bf16': (c_int, [c_void_p] * 4 + [c_int64, c_void_p]),
+    'tt_dot_scratch_floats': (c_int, []),
+    'tt_dot_bf16': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     'tt_widen_pairs': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'tt_pairs_to_c8': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'tt_channel0_activation': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),

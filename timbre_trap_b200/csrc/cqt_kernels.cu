@@ -83,6 +83,7 @@ cols_fwd_kernel(const float* __restrict__ audio, float2* __restrict__ T, FftSpec
 
     for (int i = tid; i < N1; i += kFftThreads) tw[i] = tw_n1[i];
     float* buf_f = reinterpret_cast<float*>(buf_a);
+#pragma unroll 8
     for (int i = tid; i < N1 * G; i += kFftThreads) {
         const int n1 = i / G, g = i - n1 * G;
         const int n2 = n2_0 + g;
@@ -93,6 +94,7 @@ cols_fwd_kernel(const float* __restrict__ audio, float2* __restrict__ T, FftSpec
     const float2* Z = run_passes<-1>(spec, buf_a, buf_b, tw, G / 2, tid, kFftThreads);
 
     float2* Tb = T + (size_t)blockIdx.y * K1 * N2;
+#pragma unroll 4
     for (int i = tid; i < K1 * G; i += kFftThreads) {
         const int k1 = i / G, g = i - k1 * G;
         const int n2 = n2_0 + g;
@@ -128,6 +130,7 @@ rows_fwd_kernel(const float2* __restrict__ T, float2* __restrict__ S, FftSpec sp
     const float2* Tb = T + ((size_t)blockIdx.y * K1 + k1_0) * N2;
 
     for (int i = tid; i < N2; i += kFftThreads) tw[i] = tw_n2[i];
+#pragma unroll 8
     for (int i = tid; i < rows * N2; i += kFftThreads) buf_a[i] = Tb[i];
     __syncthreads();
     const float2* X = run_passes<-1>(spec, buf_a, buf_b, tw, rows, tid, kFftThreads);
@@ -580,6 +583,8 @@ __global__ void crossfade_kernel(const float2* __restrict__ chunks, const float*
 // =============================================================================================
 using namespace tt;
 
+constexpr int kMaxLanes = 4;
+
 struct tt_cqt_plan {
     int L, F, M, n_taps;
     int N1, N2, K1, SP;
@@ -592,9 +597,10 @@ struct tt_cqt_plan {
     // scratch
     // two scratch sets + two internal streams: consecutive groups of blocks run on alternating lanes, so the FFT front end of
     // group g+1 overlaps the HBM-bound per-bin kernel of group g
-    float2 *d_T[2], *d_S[2];
-    cudaStream_t lane[2];
-    cudaEvent_t ev_start, ev_done[2];
+    float2 *d_T[kMaxLanes], *d_S[kMaxLanes];
+    cudaStream_t lane[kMaxLanes];
+    cudaEvent_t ev_start, ev_done[kMaxLanes];
+    int n_lanes;                   // lanes in use (consecutive groups of blocks rotate over them)
     int64_t scratch_bytes;
 };
 
@@ -702,14 +708,15 @@ extern "C" int tt_cqt_plan_create(tt_cqt_plan** out, int block_length, int n_bin
 
     const size_t t_bytes = (size_t)p->max_blocks * p->K1 * p->N2 * sizeof(float2);
     const size_t s_bytes = (size_t)p->max_blocks * p->SP * sizeof(float2);
-    for (int i = 0; i < 2; ++i) {
+    p->n_lanes = 2;
+    for (int i = 0; i < kMaxLanes; ++i) {
         TT_CUDA_CHECK(cudaMalloc((void**)&p->d_T[i], t_bytes));
         TT_CUDA_CHECK(cudaMalloc((void**)&p->d_S[i], s_bytes));
         TT_CUDA_CHECK(cudaStreamCreateWithFlags(&p->lane[i], cudaStreamNonBlocking));
         TT_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_done[i], cudaEventDisableTiming));
     }
     TT_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_start, cudaEventDisableTiming));
-    p->scratch_bytes = (int64_t)(2 * (t_bytes + s_bytes));
+    p->scratch_bytes = (int64_t)(kMaxLanes * (t_bytes + s_bytes));
 
     TT_REQUIRE(cols_smem(p) <= 200 * 1024 && rows_smem(p) <= 200 * 1024, "block_length %d needs too much shared memory", L);
     TT_CUDA_CHECK(cudaFuncSetAttribute(cols_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cols_smem(p)));
@@ -732,7 +739,7 @@ extern "C" int tt_cqt_plan_destroy(tt_cqt_plan* p) {
     cudaFree(p->d_start); cudaFree(p->d_length); cudaFree(p->d_first); cudaFree(p->d_offset);
     cudaFree(p->d_win); cudaFree(p->d_dual);
     cudaFree(p->d_tw_n1); cudaFree(p->d_tw_n2); cudaFree(p->d_tw_L); cudaFree(p->d_tw_m_inv); cudaFree(p->d_tw_m_fwd);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxLanes; ++i) {
         cudaFree(p->d_T[i]); cudaFree(p->d_S[i]);
         if (p->lane[i]) cudaStreamDestroy(p->lane[i]);
         if (p->ev_done[i]) cudaEventDestroy(p->ev_done[i]);
@@ -743,6 +750,12 @@ extern "C" int tt_cqt_plan_destroy(tt_cqt_plan* p) {
 }
 
 extern "C" int64_t tt_cqt_plan_scratch_bytes(const tt_cqt_plan* p) { return p ? p->scratch_bytes : 0; }
+
+extern "C" int tt_cqt_plan_set_lanes(tt_cqt_plan* p, int n_lanes) {
+    TT_REQUIRE(p && n_lanes >= 1 && n_lanes <= kMaxLanes, "lanes must be in [1, %d]", kMaxLanes);
+    p->n_lanes = n_lanes;
+    return TT_OK;
+}
 
 static BinTables bin_tables(const tt_cqt_plan* p) {
     BinTables t;
@@ -759,14 +772,14 @@ extern "C" int tt_cqt_forward(tt_cqt_plan* p, const float* audio, int batch, int
     const BinTables tab = bin_tables(p);
     if (total == 0) return TT_OK;
     const int n_groups = (int)((total + p->max_blocks - 1) / p->max_blocks);
-    const int n_lanes = n_groups > 1 ? 2 : 1;
+    const int n_lanes = std::min(n_groups, p->n_lanes);
     TT_CUDA_CHECK(cudaEventRecord(p->ev_start, user));
     for (int i = 0; i < n_lanes; ++i) TT_CUDA_CHECK(cudaStreamWaitEvent(p->lane[i], p->ev_start, 0));
     int g = 0;
     for (long long b0 = 0; b0 < total; b0 += p->max_blocks, ++g) {
         const int nb = (int)std::min<long long>(p->max_blocks, total - b0);
-        cudaStream_t stream = p->lane[g & 1];
-        float2 *T = p->d_T[g & 1], *S = p->d_S[g & 1];
+        cudaStream_t stream = p->lane[g % n_lanes];
+        float2 *T = p->d_T[g % n_lanes], *S = p->d_S[g % n_lanes];
         dim3 g1((p->N2 + kColsPerCta - 1) / kColsPerCta, nb);
         cols_fwd_kernel<<<g1, kFftThreads, cols_smem(p), stream>>>(audio + (size_t)b0 * p->L, T, p->spec_n1, p->N2,
                                                                     p->K1, p->L, p->d_tw_n1, p->d_tw_L);
@@ -813,14 +826,14 @@ extern "C" int tt_cqt_inverse(tt_cqt_plan* p, const float* coeffs, int batch, in
     TT_CUDA_CHECK(cudaMemsetAsync(peak, 0, sizeof(float), user));
     if (total == 0) return TT_OK;
     const int n_groups = (int)((total + p->max_blocks - 1) / p->max_blocks);
-    const int n_lanes = n_groups > 1 ? 2 : 1;
+    const int n_lanes = std::min(n_groups, p->n_lanes);
     TT_CUDA_CHECK(cudaEventRecord(p->ev_start, user));
     for (int i = 0; i < n_lanes; ++i) TT_CUDA_CHECK(cudaStreamWaitEvent(p->lane[i], p->ev_start, 0));
     int g = 0;
     for (long long b0 = 0; b0 < total; b0 += p->max_blocks, ++g) {
         const int nb = (int)std::min<long long>(p->max_blocks, total - b0);
-        cudaStream_t stream = p->lane[g & 1];
-        float2 *T = p->d_T[g & 1], *S = p->d_S[g & 1];
+        cudaStream_t stream = p->lane[g % n_lanes];
+        float2 *T = p->d_T[g % n_lanes], *S = p->d_S[g % n_lanes];
         TT_CUDA_CHECK(cudaMemsetAsync(S, 0, (size_t)nb * p->SP * sizeof(float2), stream));
         if (p->M == 1024) {
             const long long warps = (long long)nb * p->F;

@@ -61,6 +61,39 @@ __global__ void pairs_to_c8_kernel(const float2* __restrict__ pairs, long long n
     }
 }
 
+// sum of a[i] * b[i] over two bf16 tensors of one layout (the gradient of a skip connection's scalar weight): per-CTA partials in fp32,
+// fixed-order finish in fp64 (bit-reproducible)
+__global__ void __launch_bounds__(256) dot_bf16_partial_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, long long n8,
+                                                               float* __restrict__ partial) {
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 av = __ldcs(a + i), bv = __ldcs(b + i);
+        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&av);
+        const __nv_bfloat162* bh = reinterpret_cast<const __nv_bfloat162*>(&bv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 fa = __bfloat1622float2(ah[k]), fb = __bfloat1622float2(bh[k]);
+            acc = fmaf(fa.x, fb.x, acc);
+            acc = fmaf(fa.y, fb.y, acc);
+        }
+    }
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = 0.f;
+        for (int w = 0; w < 8; ++w) v += red[w];
+        partial[blockIdx.x] = v;
+    }
+}
+__global__ void dot_finish_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) acc += (double)partial[i];
+    *out = (float)acc;
+}
+
 }  // namespace tt
 
 using namespace tt;
@@ -101,6 +134,24 @@ extern "C" int tt_pairs_to_c8(const float* pairs, int64_t n, void* c8, void* str
     if (n <= 0) return TT_OK;
     pairs_to_c8_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>((const float2*)pairs, n, (uint4*)c8);
     tt_count_launches(1);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
+extern "C" int tt_dot_scratch_floats(void) { return 148 * 8; }
+
+extern "C" int tt_dot_bf16(const void* a, const void* b, int64_t n, float* out, float* scratch, void* stream) {
+    TT_REQUIRE(a && b && out && scratch, "null argument");
+    TT_REQUIRE(n % 8 == 0, "dot_bf16: element count must be a multiple of 8");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n <= 0) {
+        TT_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(float), s));
+        return TT_OK;
+    }
+    const int blocks = (int)std::min<long long>((n / 8 + 255) / 256, 148 * 8);
+    dot_bf16_partial_kernel<<<blocks, 256, 0, s>>>((const uint4*)a, (const uint4*)b, n / 8, scratch);
+    dot_finish_kernel<<<1, 1, 0, s>>>(scratch, blocks, out);
+    tt_count_launches(2);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }

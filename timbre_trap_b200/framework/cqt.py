@@ -39,7 +39,7 @@ def _f32(a):
 class _Plan:
     """Owns one tt_cqt_plan (device tables + scratch) on one device."""
 
-    def __init__(self, bank, device, max_blocks):
+    def __init__(self, bank, device, max_blocks, lanes):
         self.device = device
         self.handle = ctypes.c_void_p()
         with torch.cuda.device(device):
@@ -47,6 +47,7 @@ class _Plan:
                 ctypes.byref(self.handle), bank.block_length, bank.n_bins, bank.max_window_length,
                 _i32(bank.start), _i32(bank.length), _i32(bank.first), _i32(bank.offset),
                 _f32(bank.win), _f32(bank.dual), bank.n_taps, max_blocks))
+            _lib.check(_lib.lib().tt_cqt_plan_set_lanes(self.handle, lanes))
 
     def __del__(self):
         try:
@@ -63,6 +64,8 @@ class CQT(torch.nn.Module):
 
     # blocks per kernel group: bounds the plan's scratch (two complex half-spectra per block)
     BLOCKS_PER_LAUNCH = 64
+    # internal streams the groups rotate over (front-end FFT kernels of one group overlap the per-bin kernel of another)
+    LANES = 2
 
     def __init__(self, n_octaves, bins_per_octave, sample_rate, secs_per_block):
         """Same signature as the reference (cqtwrapper.py:15-48)."""
@@ -82,7 +85,7 @@ class CQT(torch.nn.Module):
     def _plan(self, device):
         key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
         if key not in self._plans:
-            self._plans[key] = _Plan(self._bank, device, self.BLOCKS_PER_LAUNCH)
+            self._plans[key] = _Plan(self._bank, device, self.BLOCKS_PER_LAUNCH, self.LANES)
         return self._plans[key]
 
     # the buffers cqt_pytorch.CQT registers, as reference checkpoints carry them under `sliCQ.`

@@ -479,6 +479,31 @@ class _OutFn(torch.autograd.Function):
         return gx, dw, db, None, None
 
 
+class _SkipAddFn(torch.autograd.Function):
+    """Decoder skip connection (modules.py:568-589) with TimbreTrap.apply_skip_connections' learnable weight (:110-112):
+    out = x + w * e on two bf16 tensors of one layout, one pass; gradients: x <- g, e <- w * g (one pass), w <- <g, e> (deterministic)."""
+
+    @staticmethod
+    def forward(ctx, x, e, w):
+        scale = w.detach().float().reshape(1)
+        out = torch.empty_like(x)
+        _lib.check(_lib.lib().tt_add_scaled_bf16(_p(x), _p(e), _p(scale), _p(out), x.numel(), _s(x)))
+        ctx.save_for_backward(e, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        e, scale = ctx.saved_tensors
+        g = g.contiguous()
+        lib = _lib.lib()
+        ge = torch.empty_like(g)
+        _lib.check(lib.tt_add_scaled_bf16(_p(g), _p(g), _p(scale - 1.0), _p(ge), g.numel(), _s(g)))        # g + (w - 1) g = w g
+        gw = torch.empty((), dtype=torch.float32, device=g.device)
+        scratch = torch.empty(int(lib.tt_dot_scratch_floats()), dtype=torch.float32, device=g.device)
+        _lib.check(lib.tt_dot_bf16(_p(g), _p(e), g.numel(), _p(gw), _p(scratch), _s(g)))
+        return g, ge, gw
+
+
 class _ActivationsFn(torch.autograd.Function):
     """TimbreTrap.to_activations (modules.py:271-289) on interleaved coefficients (B, F, T, 2) -> (B, F, T)."""
 
@@ -539,6 +564,7 @@ def _res(blk, x):
 
 
 def _encoder(enc, coeffs):
+    """-> (latents C8, [the five embeddings in their internal layouts])"""
     ch = enc.channels
     w_in, b_in, w_lat, b_lat = enc._packed()
     ci = enc.convin[0]
@@ -547,6 +573,7 @@ def _encoder(enc, coeffs):
     else:
         x = _ConvFn.apply(coeffs, ci.weight, ci.bias, lambda t: ops.conv_in(t, w_in, b_in, ch[0], packed4=enc.packed4),
                           _geom(3, 3, ph=1, pw=1), 2, ch[0], True)
+    emb = [x]
     for i, blk in enumerate((enc.block1, enc.block2, enc.block3, enc.block4)):
         for rb in (blk.block1, blk.block2, blk.block3):
             x = _res(rb, x)
@@ -557,11 +584,12 @@ def _encoder(enc, coeffs):
             (w,) = blk._cache.get((blk.sconv[0].weight, blk.sconv[0].bias), lambda: (pack(blk.sconv[0].weight, blk.sconv[0].bias),))
             return ops.conv_down_strip(t, w, P.pad8(blk.out_channels))
         x = _DownFn.apply(x, sc.weight, sc.bias, run_down, ch[i], ch[i + 1])
+        emb.append(x)
     cl = enc.convlat
     if _lat_tc_ok(ch[4], enc.latent_pad):
-        return _LatFn.apply(x, cl.weight, cl.bias, lambda t: ops.conv_lat(t, w_lat, b_lat, enc.latent_pad), ch[4], enc.latent_size, enc.latent_pad)
+        return _LatFn.apply(x, cl.weight, cl.bias, lambda t: ops.conv_lat(t, w_lat, b_lat, enc.latent_pad), ch[4], enc.latent_size, enc.latent_pad), emb
     return _ConvFn.apply(x, cl.weight, cl.bias, lambda t: ops.conv_lat(t, w_lat, b_lat, enc.latent_pad),
-                         _geom(cl.weight.size(2), 1), ch[4], enc.latent_size, False)
+                         _geom(cl.weight.size(2), 1), ch[4], enc.latent_size, False), emb
 
 
 class _IndicatorFn(torch.autograd.Function):
@@ -607,7 +635,8 @@ class _IndicatorFn(torch.autograd.Function):
         return _like(gfull[:, :d].contiguous(), lat), dw, db, None, None, None, None
 
 
-def _decoder(dec, lat, reconstruct):
+def _decoder(dec, lat, reconstruct, skips=None):
+    """skips: None or [(weight 0-dim tensor, embedding)] * 5 in encoder order (modules.py:568-589)"""
     ch = dec.channels
     w_in, tables, w_out, b_out = dec._packed()
     ci = dec.convin[0]
@@ -615,6 +644,8 @@ def _decoder(dec, lat, reconstruct):
     x = _IndicatorFn.apply(lat, ci.weight, ci.bias, lambda t: ops.deconv_in(t, w_in[sw], tables[sw], P.pad8(ch[0]), dec.embedding_size),
                            1.0 if reconstruct else 0.0, dec.latent_size, ch[0])
     for i, blk in enumerate((dec.block1, dec.block2, dec.block3, dec.block4)):
+        if skips is not None:
+            x = _SkipAddFn.apply(x, skips[-1 - i][1], skips[-1 - i][0])
         tc = blk.tconv[0]
 
         def run_up(t, blk=blk):
@@ -623,6 +654,8 @@ def _decoder(dec, lat, reconstruct):
         x = _UpFn.apply(x, tc.weight, tc.bias, run_up, ch[i], ch[i + 1])
         for rb in (blk.block1, blk.block2, blk.block3):
             x = _res(rb, x)
+    if skips is not None:
+        x = _SkipAddFn.apply(x, skips[0][1], skips[0][0])
     co = dec.convout
     if dec.packed4:
         return _OutFn.apply(x, co.weight, co.bias, lambda t: ops.conv_out(t, w_out, b_out, ch[4]), ch[4])
@@ -650,14 +683,15 @@ def allreduce_mean_gradients(params, group, flat=None):
 
 class TrainStep:
     """
-    One optimisation step of experiments/train.py:393-500 for the base TimbreTrap (no skip connections):
+    One optimisation step of experiments/train.py:393-500 for TimbreTrap (with or without skip connections):
     losses as in compute_step_losses, backward, optional NCCL all-reduce of one flat gradient bucket (mean over ranks),
     clip_grad_norm_(max_norm) and AdamW (torch defaults: betas (0.9, 0.999), eps 1e-8, weight_decay 1e-2; train.py:334).
     """
 
     def __init__(self, model, lr=1e-3, max_norm=10.0, multipliers=None, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None):
-        if model.skip_weights is not None:
-            raise NotImplementedError('TrainStep covers the base model (skip_connections=False, experiments/train.py:161)')
+        if getattr(model, 'HEAD_MODE', None) is not None or hasattr(model, 'film_layer'):
+            raise NotImplementedError('TrainStep covers TimbreTrap with or without skip connections (experiments/train.py:155-161); '
+                                      'the FiLM / magnitude variants run forward only')
         self.model = model
         self.params = [p for p in model.parameters()]
         self.lr, self.max_norm, self.betas, self.eps, self.wd = lr, max_norm, betas, eps, weight_decay
@@ -690,17 +724,23 @@ class TrainStep:
         model = self.model
         with torch.no_grad():
             coeffs = model.sliCQ.encode_interleaved(audio)
-        lat = _encoder(model.encoder, coeffs)
-        rec = _decoder(model.decoder, lat, True)
-        trn = _decoder(model.decoder, lat, False)
+        def skips_of(emb):
+            if model.skip_weights is None:
+                return None
+            return [(model.skip_weights[i], e) for i, e in enumerate(emb)]
+        lat, emb = _encoder(model.encoder, coeffs)
+        sk = skips_of(emb)
+        rec = _decoder(model.decoder, lat, True, sk)
+        trn = _decoder(model.decoder, lat, False, sk)
         act = _ActivationsFn.apply(trn)
         n = ground_truth.size(0)
         out = dict(reconstruction=_SqDiffFn.apply(rec, coeffs), transcription=_TrnLossFn.apply(act[:n].contiguous(), ground_truth.float().contiguous()))
         total = self.mult['reconstruction'] * out['reconstruction']
         if self.mult['consistency']:
-            lat_t = _encoder(model.encoder, trn)
-            trn_rec = _decoder(model.decoder, lat_t, True)
-            trn_scr = _decoder(model.decoder, lat_t, False)
+            lat_t, emb_t = _encoder(model.encoder, trn)
+            sk_t = skips_of(emb_t)
+            trn_rec = _decoder(model.decoder, lat_t, True, sk_t)
+            trn_scr = _decoder(model.decoder, lat_t, False, sk_t)
             tgt = trn[:n].contiguous()
             out['consistency_spectral'] = _SqDiffFn.apply(trn_rec[:n].contiguous(), tgt)
             out['consistency_score'] = _SqDiffFn.apply(trn_scr[:n].contiguous(), tgt)
