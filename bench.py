@@ -332,11 +332,11 @@ def run_ours(args, rank, world, local_rank):
         t_gt = synthetic_targets(tb, 3 * M, seed=300 + rank).to(device)
         tmodel = TimbreTrap(SR, N_OCT, BPO, SECS, latent_size=LATENT, model_complexity=COMPLEXITY).to(device)
         ts = TrainStep(tmodel, group=group)
-        for _ in range(2):
+        for _ in range(3):
             res = ts.step(t_audio, t_gt)
         barrier()
         a.record()
-        n_train = 3
+        n_train = 5
         for _ in range(n_train):
             res = ts.step(t_audio, t_gt)
         b.record()
@@ -407,7 +407,7 @@ def run_ours(args, rank, world, local_rank):
             del x, y
         ms_4, bytes_4 = per_instance[(4, 1)]
         traffic = None
-        tpath = os.path.join(ROOT, 'profiles', 'r01_res_rs_c4_traffic.json')
+        tpath = os.path.join(ROOT, 'profiles', 'r02_res_rs_c4_traffic.json')
         if os.path.exists(tpath):
             t = json.load(open(tpath))
             traffic = t['dram_bytes_per_launch'] * (n_chunks / t['chunks'])

@@ -22,7 +22,7 @@
 namespace tt {
 
 constexpr int kWgThreads = 128;        // warp 0: TMA producer, warp 1: MMA issuer; after the row loop warps 0-1 drain the accumulators
-constexpr int kWgZSlots = 3;           // A-side row ring
+constexpr int kWgZSlots = 8;           // A-side row ring (upper bound; the launch picks the depth that fits)
 constexpr int kWgMaxTaps = 10;         // 9 conv taps + the bias "tap"
 constexpr int kWgMaxM = 64;            // A-side channels a CTA of the row-walking geometries writes out (TMEM lanes 0..63)
 
@@ -34,6 +34,7 @@ struct WgradParams {
     int d;                             // dilation of the 3x3 geometry
     int rows_per_strip;
     int z_slots;                       // A-side ring depth (<= kWgZSlots)
+    int xring;                         // B-side ring depth (<= 16): the rows one A-side row reaches + the prefetch distance
     int tap_group;                     // 0: blockIdx.y walks strips of A-side rows; > 0: the A side has ONE row and blockIdx.y selects a
                                        // group of `tap_group` consecutive B-side rows = vertical taps (the (31,1) layers)
 };
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     const int DH = KH == 3 ? p.d : 1;                 // vertical tap step in B-side rows
     const int span = (KH - 1) * DH;                   // B-side rows an A-side row reaches beyond its first one
     const int TW = kStripTileT + 2 * d;
-    const int xring = span + 1 + 2 * RS;
+    const int xring = p.xring;
     const uint32_t z_slot = (uint32_t)p.CGo * kStripTileT * 16u;
     const uint32_t x_plane = (uint32_t)TW * 16u;
     const uint32_t x_slot = ((uint32_t)p.CGi * x_plane + 127u) & ~127u;
@@ -109,7 +110,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             ++xr;
         };
         for (int r = 0; r < n_rows; ++r) {
-            while (xr < n_xrows && xr <= r * RS + span + RS) load_x();      // the rows of A-side row r, plus those of row r + 1
+            // as far ahead as the ring allows without waiting for a release that needs THIS iteration's A-side row (deadlock): the
+            // slot of row xr is freed by A-side row (xr - xring) / RS, which must lie before r
+            while (xr < n_xrows && xr <= r * RS + xring - RS - 1) load_x();
             const int slot = r % zslots;
             if (r >= zslots) umma::mbar_wait(&z_empty[slot], (uint32_t)((r / zslots - 1) & 1));
             mbar_expect_tx(&z_full[slot], z_slot);
@@ -128,26 +131,32 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                 umma::mbar_wait(&x_full[xr % xring], (uint32_t)((xr / xring) & 1));
             umma::fence_after_sync();
             const uint32_t za = z0 + (uint32_t)zs * z_slot;
-#pragma unroll 1
+            // Descriptors: the high word (group stride, version bit) is constant per operand kind, the low word is (address >> 4) with
+            // the k-group stride 128 B in bits 16-29; a K step of 16 pixels advances the address field by 256 B >> 4 = 16.  Everything
+            // below is 32-bit adds in the one issuing thread (its instruction stream, not the tensor pipe, bounds this kernel).
+            constexpr uint32_t lbo_field = (128u >> 4) << 16;
+            const uint32_t hi_a = ((uint32_t)(kStripTileT * 16) >> 4) | (1u << 14);
+            const uint32_t hi_b = ((KXN ? (uint32_t)d * 16u : x_plane) >> 4) | (1u << 14);
+            const uint32_t lo_a = ((za >> 4) & 0x3FFFu) | lbo_field, lo_ones = ((ones0 >> 4) & 0x3FFFu) | lbo_field;
+            uint32_t lo_b[KH];
+#pragma unroll
+            for (int ky = 0; ky < KH; ++ky) lo_b[ky] = (((x0 + (uint32_t)((r * RS + ky * DH) % xring) * x_slot) >> 4) & 0x3FFFu) | lbo_field;
+            auto d64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+#pragma unroll
             for (int s = 0; s < kStripTileT / 16; ++s) {
-                const uint64_t da = umma::make_desc(za + (uint32_t)s * 256u, 128u, (uint32_t)kStripTileT * 16u);
+                const bool acc = !(first && s == 0);
+                const uint64_t da = d64(hi_a, lo_a + (uint32_t)s * 16u);
 #pragma unroll
                 for (int ky = 0; ky < KH; ++ky) {
-                    const int xr = r * RS + ky * DH;                   // relative B-side row of this vertical tap
-                    const uint32_t xa = x0 + (uint32_t)(xr % xring) * x_slot;
                     if constexpr (KXN) {
-                        const uint64_t db = umma::make_desc(xa + (uint32_t)s * 256u, 128u, (uint32_t)d * 16u);
-                        umma::mma_bf16(tmem + (uint32_t)(ky * NPAD), da, db, idesc, !(first && s == 0));
+                        umma::mma_bf16(tmem + (uint32_t)(ky * NPAD), da, d64(hi_b, lo_b[ky] + (uint32_t)s * 16u), idesc, acc);
                     } else {
 #pragma unroll
-                        for (int kx = 0; kx < KW; ++kx) {
-                            const uint64_t db = umma::make_desc(xa + (uint32_t)(kx * d) * 16u + (uint32_t)s * 256u, 128u, x_plane);
-                            umma::mma_bf16(tmem + (uint32_t)((ky * KW + kx) * NPAD), da, db, idesc, !(first && s == 0));
-                        }
+                        for (int kx = 0; kx < KW; ++kx)
+                            umma::mma_bf16(tmem + (uint32_t)((ky * KW + kx) * NPAD), da, d64(hi_b, lo_b[ky] + (uint32_t)(kx * d) + (uint32_t)s * 16u), idesc, acc);
                     }
                 }
-                const uint64_t dones = umma::make_desc(ones0 + (uint32_t)s * 256u, 128u, (uint32_t)kStripTileT * 16u);
-                umma::mma_bf16(tmem + (uint32_t)(TAPS * NPAD), da, dones, idesc, !(first && s == 0));
+                umma::mma_bf16(tmem + (uint32_t)(TAPS * NPAD), da, d64(hi_a, lo_ones + (uint32_t)s * 16u), idesc, acc);
             }
             first = false;
             umma::commit(&z_empty[zs]);
@@ -188,10 +197,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
 // dW (m, n, taps) and db (m) += fixed-order sums of the per-CTA partials (m = A-side channel, n = B-side channel: (co, ci, kh, kw) for a
 // regular conv, (ci, co, kh, kw) - the ConvTranspose2d weight layout - when the two sides are swapped)
-// kxn: the partials hold 3 vertical taps of [kx][8 channels] columns (see KXN above); taps stays 9 for the output layout
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, int npad, int taps, int m_real, int n_real, float* __restrict__ dw,
-                                    float* __restrict__ db, int kxn) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;              // over (tap' in [0, taps], m, n)
+// kxn: the partials hold 3 vertical taps of [kx][8 channels] columns (see KXN above); taps stays 9 for the output layout.
+// One WARP per output element: the lanes stride over the CTAs' partials, then a shuffle tree - a fixed order, so still bit-reproducible.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int n_ctas, int npad, int taps, int m_real, int n_real,
+                                                           float* __restrict__ dw, float* __restrict__ db, int kxn) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // over (tap' in [0, taps], m, n)
+    const int lane = threadIdx.x & 31;
     const int total = (taps + 1) * m_real * n_real;
     if (i >= total) return;
     const int tap = i / (m_real * n_real), rem = i - tap * m_real * n_real;
@@ -202,9 +213,13 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int n_cta
     const float* src = partial + ((size_t)ptap * kWgMaxM + o) * npad + pcol;
     const size_t stride = (size_t)kWgMaxTaps * kWgMaxM * npad;
     float acc = 0.f;
-    for (int k = 0; k < n_ctas; ++k) acc += src[(size_t)k * stride];
-    if (tap == taps) db[o] += acc;
-    else dw[((size_t)o * n_real + c) * taps + tap] += acc;
+    for (int k = lane; k < n_ctas; k += 32) acc += src[(size_t)k * stride];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+        if (tap == taps) db[o] += acc;
+        else dw[((size_t)o * n_real + c) * taps + tap] += acc;
+    }
 }
 
 // the (31,1) layers: CTA (x, group, b) holds taps group * G .. group * G + G - 1 of all 128 A-side channels; dw (m, n, taps) += fixed-order sums
@@ -378,8 +393,8 @@ static size_t wgrad_smem(int CGi, int CGo, int halo, int xring, int zslots) {
 template <int NPAD, int KH, int KW, int RS, int MW, bool KXN = false>
 static int launch_wgrad(const void* x, const void* dz, const WgradParams& p, dim3 grid, cudaStream_t stream) {
     const int halo = KW == 3 ? p.d : 0;
-    const int xring = (KH - 1) * (KH == 3 ? p.d : 1) + 1 + 2 * RS;
-    TT_REQUIRE(xring <= 16, "wgrad: ring of %d rows", xring);
+    const int xring = p.xring;
+    TT_REQUIRE(xring <= 16 && xring >= (KH - 1) * (KH == 3 ? p.d : 1) + 1 + 2 * RS, "wgrad: ring of %d rows", xring);
     const size_t smem = wgrad_smem(p.CGi, p.CGo, halo, xring, p.z_slots);
     TT_REQUIRE(smem <= 227 * 1024, "wgrad: %zu bytes of shared memory", smem);
     static size_t configured = 0;
@@ -399,8 +414,10 @@ static int launch_wgrad(const void* x, const void* dz, const WgradParams& p, dim
 }
 
 static long long wgrad_strips(int B, int Hz, int T) {
+    // about six CTAs per SM in total (several are co-resident: the accumulators of a CTA take 128-512 TMEM columns): evens out
+    // the load over the 148 SMs at the price of more partial buffers for the reduction
     const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
-    return std::max<long long>(1, std::min<long long>((2 * 148 + tiles - 1) / tiles, Hz));
+    return std::max<long long>(1, std::min<long long>((6 * 148 + tiles - 1) / tiles, std::max(1, Hz / 8)));
 }
 
 }  // namespace tt
@@ -420,7 +437,17 @@ static int wgrad_any(const void* bsrc, const void* a, float* dw, float* db, int 
     WgradParams p;
     p.partial = scratch;
     p.B = B; p.T = T; p.Hz = Ha; p.Hx = Hb; p.CGi = Cb / 8; p.CGo = Ca / 8; p.d = dilation;
-    p.z_slots = kWgZSlots; p.tap_group = 0;
+    p.tap_group = 0;
+    // ring depths: the loads are 2-16 KB rows with ~1 us latency each, so the prefetch distance - not bandwidth - sets the pace;
+    // take up to 8 A-side rows and up to 8 row-steps of B-side rows ahead, within ~170 KB of shared memory
+    {
+        const int span = (KH - 1) * (KH == 3 ? dilation : 1);
+        const size_t z_slot = (size_t)(Ca / 8) * kStripTileT * 16, x_slot = (size_t)(Cb / 8) * (kStripTileT + 2 * (KW == 3 ? dilation : 0)) * 16 + 128;
+        p.z_slots = (int)std::max<size_t>(3, std::min<size_t>(kWgZSlots, (48 * 1024) / z_slot));
+        int pf = 8;
+        while (pf > 2 && (span + 1 + pf * RS > 16 || (span + 1 + pf * RS) * x_slot > 120 * 1024)) --pf;
+        p.xring = span + 1 + pf * RS;
+    }
     const long long strips = wgrad_strips(B, Ha, T);
     p.rows_per_strip = (int)((Ha + strips - 1) / strips);
     dim3 grid((T + kStripTileT - 1) / kStripTileT, (Ha + p.rows_per_strip - 1) / p.rows_per_strip, B);
@@ -438,7 +465,7 @@ static int wgrad_any(const void* bsrc, const void* a, float* dw, float* db, int 
     }
     if (rc) return rc;
     const int total = (KH * KW + 1) * ca_real * cb_real;
-    wgrad_reduce_kernel<<<(total + 127) / 128, 128, 0, stream>>>(scratch, n_ctas, npad, KH * KW, ca_real, cb_real, dw, db, kxn);
+    wgrad_reduce_kernel<<<(total + 7) / 8, 256, 0, stream>>>(scratch, n_ctas, npad, KH * KW, ca_real, cb_real, dw, db, kxn);
     tt_count_launches(1);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
@@ -496,7 +523,7 @@ extern "C" int tt_conv_wgrad_lat(const void* tall, const void* flat, float* dw, 
     WgradParams p;
     p.partial = scratch;
     p.B = B; p.T = T; p.Hz = 1; p.Hx = H; p.CGi = Ctall / 8; p.CGo = Cflat / 8; p.d = 1;
-    p.rows_per_strip = 1; p.z_slots = 1; p.tap_group = kLatTapGroup;
+    p.rows_per_strip = 1; p.z_slots = 1; p.tap_group = kLatTapGroup; p.xring = kLatTapGroup + 2;
     const int groups = (H + kLatTapGroup - 1) / kLatTapGroup;
     dim3 grid((T + kStripTileT - 1) / kStripTileT, groups, B);
     const int rc = launch_wgrad<64, kLatTapGroup, 1, 1, 4>(tall, flat, p, grid, stream);
