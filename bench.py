@@ -86,108 +86,21 @@ def synthetic_audio(n_blocks, seed, device='cpu', pin=False):
     return x.to(device) if device != 'cpu' else x
 
 
-# ---------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference path (model.transcribe(audio); model.reconstruct(audio), modules.py:292-336)
-# ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_step(state, n_blocks):
-    from oracle import model_ref as R
-    sd, cqt = state
-    audio = synthetic_audio(n_blocks, seed=0)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        R.transcribe_ref(audio, sd, cqt)
-        R.reconstruct_ref(audio, sd, cqt)
-    return time.perf_counter() - t0
-
-
-def cpu_state():
-    from oracle import model_ref as R
-    import numpy as np
-    torch.set_num_threads(os.cpu_count() or 1)
-    return R.init_state_dict(F, LATENT, COMPLEXITY, seed=0), R.CQTRef(N_OCT, BPO, SR, SECS, dtype=np.complex64)
-
-
-WORKLOAD = ('BASELINE.json configs[2]: transcribe+reconstruct, 256 x 3 s blocks per GPU, base model '
-            '(9 oct x 60 bpo, 22.05 kHz, latent 128, complexity 2), random init')
-
-
-CPU_BLOCKS = 8        # blocks per CPU step: the reference's chunk loop runs the whole batch through each chunk position
-
-
-def median(xs):
-    xs = sorted(xs)
-    return xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2])
-
-
-def run_reference(args, rank):
-    if rank != 0:
-        return
-    state = cpu_state()
-    n_blocks = CPU_BLOCKS                     # bounded sample of the 256-block batch: 8 blocks per step, all host threads
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference_step(state, n_blocks)
-    times = [cpu_reference_step(state, n_blocks) for _ in range(args.steps)]
-    per_step = median(times)                  # BASELINE.md section 4: median of >= 5 runs after one warm-up
-    value = n_blocks * SECS / per_step
-    cores = torch.get_num_threads()
-    line = dict(metric=METRIC, value=value, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=per_step * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
-                config=dict(workload=WORKLOAD, sample=f'bounded sample of that workload: a batch of {n_blocks} x 3 s blocks per step on the host '
-                                                      'CPU (the reference\'s sequential chunk loop over the batch), median step time'),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='port',
-                                  sample=f'{args.steps} steps x {n_blocks} block(s) of 3 s; oracle/model_ref.py + oracle/nsgt_ref.py (the reference is '
-                                         'pure Python with an un-vendored CQT dependency; /root/reference is absent on the GPU box)'),
-                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
-
-
-# ---------------------------------------------------------------------------------------------------------------
-# GPU arm
-# ---------------------------------------------------------------------------------------------------------------
-def time_kernel(fn, iters, warm=3):
-    for _ in range(warm):
-        fn()
-    torch.cuda.synchronize()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(iters):
-        fn()
-    b.record()
-    torch.cuda.synchronize()
-    return a.elapsed_time(b) / iters          # ms
-
-
-def synthetic_targets(n_items, n_frames, seed):
-    """Multi-pitch targets in the manner of PitchDataset.multi_pitch_to_activations (datasets/PitchDataset.py:233-307): exact 1.0
-    at a few bins per frame held for >= 50 frames, Gaussian-blurred neighbours (sigma = 1 bin), clipped to [0, 1]."""
-    import numpy as np
-    rng = np.random.default_rng(seed)
-    gt = np.zeros((n_items, F, n_frames), dtype=np.float32)
-    blur = np.exp(-0.5 * np.arange(-3, 4) ** 2)
-    for b in range(n_items):
-        t = 0
-        while t < n_frames:
-            hold = int(rng.integers(50, 400))
-            for k in rng.integers(30, F - 30, size=int(rng.integers(1, 7))):
-                for o, g in zip(range(-3, 4), blur):
-                    gt[b, k + o, t:t + hold] = np.maximum(gt[b, k + o, t:t + hold], g)
-            t += hold
-    return torch.from_numpy(gt)
-
-
-class EagerGpuReference:
+class TorchReference:
     """
-    DIAGNOSTIC ANCHOR ONLY (what the reference's own code does when it is given a GPU): the oracle's functional
-    restatement of the reference model (oracle/model_ref.py: F.conv2d / F.conv_transpose2d / F.elu = cuDNN + ATen) under bf16
-    autocast, with the NSGT as torch.fft calls (cuFFT) on the oracle's tables, run as the reference runs it - model.transcribe(audio)
-    then model.reconstruct(audio), each a sequential loop over the chunk positions with the whole batch per iteration
-    (modules.py:247-263).  Never on the product path; bench.py only.
+    The reference's own code path restated with library calls only, on any torch device: the oracle's functional model
+    (oracle/model_ref.py: F.conv2d / F.conv_transpose2d / F.elu) with the NSGT as torch.fft calls on the oracle's tables (what
+    cqt_pytorch does), run as the reference runs it - model.transcribe(audio) then model.reconstruct(audio), each a sequential loop
+    over the chunk positions with the whole batch per iteration (modules.py:247-263).
+      device cpu  (fp32, all host threads): the CPU arm - `--impl reference` and `cpu_baseline`
+      device cuda (bf16 autocast: cuFFT + cuDNN + ATen): `gpu_eager_baseline`, a DIAGNOSTIC ANCHOR
+    Never on the product path; bench.py only.
     """
 
     def __init__(self, device):
         from oracle import model_ref as R
         self.R = R
-        self.device = device
+        self.device = torch.device(device)
         cq = R.CQTRef(N_OCT, BPO, SR, SECS)
         t = cq.nsgt.tables
         self.block_length, self.max_window_length, self.n_bins = cq.block_length, cq.max_window_length, cq.n_bins
@@ -230,7 +143,7 @@ class EagerGpuReference:
         R, hop, Mw = self.R, self.block_length // 2, self.max_window_length
         window = R.hann_sym(Mw).to(self.device)
         outs = []
-        with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+        with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16, enabled=self.device.type == 'cuda'):
             for transcribe in (True, False):
                 x = torch.nn.functional.pad(self.pad_to_block_length(audio), [hop, hop])
                 n_chunks = (x.size(-1) - hop) // hop
@@ -241,6 +154,89 @@ class EagerGpuReference:
                 out = out[..., Mw // 2: -Mw // 2]
                 outs.append(torch.tanh(self.to_magnitude(out)) if transcribe else self.decode(out))
         return outs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path (model.transcribe(audio); model.reconstruct(audio), modules.py:292-336)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(state, n_blocks):
+    audio = synthetic_audio(n_blocks, seed=0)
+    t0 = time.perf_counter()
+    state.step(audio)
+    return time.perf_counter() - t0
+
+
+def cpu_state():
+    torch.set_num_threads(os.cpu_count() or 1)
+    return TorchReference('cpu')
+
+
+WORKLOAD = ('BASELINE.json configs[2]: transcribe+reconstruct, 256 x 3 s blocks per GPU, base model '
+            '(9 oct x 60 bpo, 22.05 kHz, latent 128, complexity 2), random init')
+
+
+CPU_BLOCKS = 8        # blocks per CPU step: the reference's chunk loop runs the whole batch through each chunk position
+
+
+def median(xs):
+    xs = sorted(xs)
+    return xs[len(xs) // 2] if len(xs) % 2 else 0.5 * (xs[len(xs) // 2 - 1] + xs[len(xs) // 2])
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    state = cpu_state()
+    n_blocks = CPU_BLOCKS                     # bounded sample of the 256-block batch: 8 blocks per step, all host threads
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_step(state, n_blocks)
+    times = [cpu_reference_step(state, n_blocks) for _ in range(args.steps)]
+    per_step = median(times)                  # BASELINE.md section 4: median of >= 5 runs after one warm-up
+    value = n_blocks * SECS / per_step
+    cores = torch.get_num_threads()
+    line = dict(metric=METRIC, value=value, unit=UNIT, impl='reference', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=per_step * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+                config=dict(workload=WORKLOAD, sample=f'bounded sample of that workload: a batch of {n_blocks} x 3 s blocks per step on the host '
+                                                      'CPU (the reference\'s sequential chunk loop over the batch), median step time'),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='port',
+                                  sample=f'{args.steps} steps x {n_blocks} block(s) of 3 s; oracle/model_ref.py convs + a torch.fft NSGT on the oracle tables (the '
+                                         'reference is pure Python with an un-vendored CQT dependency; /root/reference is absent on the GPU box)'),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------
+def time_kernel(fn, iters, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters          # ms
+
+
+def synthetic_targets(n_items, n_frames, seed):
+    """Multi-pitch targets in the manner of PitchDataset.multi_pitch_to_activations (datasets/PitchDataset.py:233-307): exact 1.0
+    at a few bins per frame held for >= 50 frames, Gaussian-blurred neighbours (sigma = 1 bin), clipped to [0, 1]."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    gt = np.zeros((n_items, F, n_frames), dtype=np.float32)
+    blur = np.exp(-0.5 * np.arange(-3, 4) ** 2)
+    for b in range(n_items):
+        t = 0
+        while t < n_frames:
+            hold = int(rng.integers(50, 400))
+            for k in rng.integers(30, F - 30, size=int(rng.integers(1, 7))):
+                for o, g in zip(range(-3, 4), blur):
+                    gt[b, k + o, t:t + hold] = np.maximum(gt[b, k + o, t:t + hold], g)
+            t += hold
+    return torch.from_numpy(gt)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -447,7 +443,7 @@ def run_ours(args, rank, world, local_rank):
         eager = None
         if world == 1 and not args.no_eager:
             try:
-                ref = EagerGpuReference(device)
+                ref = TorchReference(device)
                 ref.step(dev_audio[:8])
                 torch.cuda.synchronize()
                 ms_e = time_kernel(lambda: ref.step(dev_audio), iters=2, warm=1)
@@ -471,7 +467,7 @@ def run_ours(args, rank, world, local_rank):
             v = CPU_BLOCKS * SECS / median(times)
             cpu = dict(value=v, unit=UNIT, cores=torch.get_num_threads(), kind='port',
                        sample=f'median of {len(times)} x (transcribe + reconstruct of a batch of {CPU_BLOCKS} x 3 s blocks, sequential 3-chunk '
-                              'loops over the batch) with oracle/model_ref.py + oracle/nsgt_ref.py')
+                              'loops over the batch): oracle/model_ref.py convs + a torch.fft NSGT on the oracle tables, fp32, all host threads')
 
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
                     higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16 convs (fp32 accumulate), fp32 CQT',
