@@ -202,3 +202,35 @@ def test_rejects_cpu_and_ragged_inputs():
         cqt(torch.zeros(1, 1, ref.block_length + 1).cuda())
     empty = cqt(torch.zeros(0, 1, ref.block_length).cuda())
     assert empty.shape == (0, 2, ref.n_bins, ref.max_window_length)
+
+
+def test_full_size_config_properties():
+    """BASELINE.json configs[1] at its full size (1024 x 3 s blocks, 4.5 GB of coefficients): size-independent properties - every
+    block's rows equal the transform of that block alone (bit-exact: blocks are independent), the energy identity of the frame holds
+    for the whole batch, and the round trip returns the covered band of the input."""
+    from timbre_trap_b200.framework import CQT
+    cqt = CQT(*BASE)
+    L, M = cqt.block_length, cqt.max_window_length
+    g = torch.Generator(device='cuda').manual_seed(11)
+    x = torch.rand((1024, 1, L), device='cuda', generator=g) * 2 - 1
+    c = cqt(x)
+    assert c.shape == (1024, 2, 540, M)
+    for i in (0, 63, 64, 511, 1023):                                   # group boundaries of the plan (64 blocks per launch group) included
+        assert torch.equal(cqt(x[i:i + 1])[0], c[i]), i
+    two = cqt(x[100:102].reshape(1, 1, 2 * L))                           # two consecutive blocks of ONE item = the same rows, concatenated on time
+    assert torch.equal(two[0, :, :, :M], c[100]) and torch.equal(two[0, :, :, M:], c[101])
+    b = cqt._bank
+    diag = np.zeros(L // 2 + 1)
+    for k in range(b.n_bins):
+        diag[b.start[k]: b.start[k] + b.length[k]] += b.win[b.offset[k]: b.offset[k + 1]].astype(np.float64) ** 2
+    D = torch.from_numpy(diag).cuda()
+    sel = slice(0, 1024, 37)
+    X = torch.fft.rfft(x[sel, 0].double(), dim=-1)
+    energy = (c[sel].double() ** 2).sum(dim=(1, 2, 3))
+    want = (X.abs() ** 2 * D).sum(-1) / M
+    assert float(((energy - want).abs() / want).max()) < 1e-4
+    raw, peak = cqt.decode_raw(c)
+    ideal = torch.fft.irfft(X * (D > 0), n=L, dim=-1) / 2
+    emax, el2 = rel_err(raw[sel, 0].cpu().numpy(), ideal.cpu().numpy())
+    assert emax < TOL and el2 < TOL, (emax, el2)
+    assert abs(float(peak) - float(raw.abs().max())) <= 1e-6 * float(peak)

@@ -282,3 +282,21 @@ def test_reconstruct_end_to_end_vs_oracle(cfg, latent, complexity, n_blocks):
     print(f'reconstruct end to end ({cfg["sample_rate"]} Hz): well-conditioned band before normalise {banded:.1f} dB; '
           f'final audio full band {full:.1f} dB (floor {floor:.1f})')
     assert full >= floor, (full, floor)
+
+
+def test_full_size_batch_equals_single_items():
+    """BASELINE.json configs[2] at its full size (256 x 3 s blocks -> 768 chunks, base model): every item of the batch equals the same
+    clip run alone - activations bit for bit, audio up to the batch-global peak the reference normalises by (cqtwrapper.py:209-211)."""
+    model, sd, c = _build(BASE, 128, 2, False, seed=0)
+    g = torch.Generator(device='cuda').manual_seed(3)
+    audio = torch.rand((256, 1, c.block_length), device='cuda', generator=g) * 2 - 1
+    audio[7] *= 0.05                                                      # a quiet item: its own peak differs from the batch's
+    act, wav = model.transcribe_and_reconstruct(audio)
+    assert act.shape == (256, 540, 1024) and wav.shape == (256, 1, c.block_length)
+    assert abs(float(wav.abs().max()) - 1.0) < 1e-5
+    for i in (0, 7, 85, 255):                                             # sub-batch boundaries (256 chunks per kernel batch) included
+        a1, w1 = model.transcribe_and_reconstruct(audio[i:i + 1])
+        assert torch.equal(a1[0], act[i]), i
+        scale = (w1[0] * wav[i]).sum() / (wav[i] * wav[i]).sum()          # ratio of the two peaks
+        assert float((w1[0] - scale * wav[i]).abs().max()) <= 2e-5, i
+    assert torch.equal(model.transcribe(audio[:3]), act[:3])
