@@ -48,6 +48,7 @@ constexpr int kRsEpiWarps = 16;
 // warps: 16 epilogue + TMA producer + scout + 3x3 issuer + 1x1 issuer (the last four use one thread each)
 constexpr int kRsThreads = (kRsEpiWarps + 4) * 32;
 constexpr int kRsSlots = 16;       // TMEM accumulator slots (3x3 rings + 1x1 slots)
+constexpr int kRsCmdSlots = 32;    // >= the deepest input-row ring: the scout can never be further ahead of the issuer than that
 
 struct ResRsParams {
     __nv_bfloat16* y;
@@ -95,7 +96,8 @@ struct RsPlan {
     static constexpr int kRingBase = kMid + A2 * kMidSlot;
     static constexpr int kSlotBytes = (CG * TW * 16 + 127) / 128 * 128;
     static constexpr int kZero = kRingBase + kRing * kSlotBytes;
-    static constexpr int kTotal = kZero + 2048;
+    static constexpr int kCmd = kZero + 2048;                        // per-row issue commands, written by the scout (kRsCmdSlots x 32 bytes)
+    static constexpr int kTotal = kCmd + kRsCmdSlots * 32;
     static_assert(SR >= 3 && D * SR + A2 <= kRsSlots, "TMEM slot plan");
 };
 
@@ -199,9 +201,36 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
         // =================================== producer ===================================
         if (lane == 0) {
             constexpr uint32_t bytes = (uint32_t)CG * TW * 16u;
+            // The producer also does ALL of the 3x3 issuer's per-row index arithmetic (ring positions, wrap-around split, descriptor words)
+            // and leaves it as a 32-byte command in shared memory before it starts the row's load: the issuer is the pacing thread of the
+            // kernel (~830 cycles per row, of which ~300 were this arithmetic) and now only reads the command and issues.  The producer is
+            // never more than kRing rows ahead of the issuer (ring_free), so kRsCmdSlots >= kRing entries suffice; the command is ordered
+            // before the issuer's read through arrive.expect_tx (release) -> the scout's barrier wait -> its release store of rows_ready.
+            constexpr uint32_t idesc1 = umma::make_idesc_bf16(128, NC), idesc2 = umma::make_idesc_bf16(128, 2 * NC), idesc3 = umma::make_idesc_bf16(128, N3);
+            const uint32_t ring0 = umma::smem_u32(sRing);
+            const uint32_t b_base = desc_lo(umma::smem_u32(sW1), N3 * 16u);
+            uint4* cmds = reinterpret_cast<uint4*>(smem + S_::kCmd);
             for (int ri = ri_first; ri <= ri_last; ++ri) {
                 const int idx = ri - ri_first, slot = idx % kRing;
+                // target blocks j = 0, 1, 2 <-> output rows ri - D, ri, ri + D (vertical taps ky = 2, 1, 0)
+                const int j0 = ri >= D ? 0 : (ri >= 0 ? 1 : 2);
+                const int j1 = ri + D < n_out ? 2 : (ri < n_out ? 1 : 0);
+                const int res = (ri + D) % D;                            // residue class of the three targets
+                const int q1 = (ri + D) / D - 1;                         // ring sequence number of output row ri
+                const int pa = (q1 - 1 + j0) % SR;
+                const int na = min(j1 - j0 + 1, SR - pa), nb = (j1 - j0 + 1) - na;
+                uint4 c0, c1;
+                c0.x = ring0 + (uint32_t)slot * slot_bytes;                                           // the input row in the ring
+                c0.y = tmem + (uint32_t)((res * SR + pa) * NC);                                       // first run of target slots
+                c0.z = na <= 0 ? 0u : (na == 3 ? idesc3 : (na == 2 ? idesc2 : idesc1));               // (0 = nothing to issue)
+                c0.w = b_base + (uint32_t)(j0 * NC);
+                c1.x = tmem + (uint32_t)((res * SR) * NC);                                            // the run after the ring's wrap-around
+                c1.y = nb <= 0 ? 0u : (nb == 3 ? idesc3 : (nb == 2 ? idesc2 : idesc1));
+                c1.z = b_base + (uint32_t)((j0 + na) * NC);
+                c1.w = ri - D >= 0 ? umma::smem_u32(&acc1_full[slot_of(ri - D)]) : 0u;                // barrier of the row this one completes
                 if (idx >= kRing) umma::mbar_wait(&ring_free[slot], (uint32_t)((idx / kRing - 1) & 1));
+                cmds[2 * (idx % kRsCmdSlots)] = c0;
+                cmds[2 * (idx % kRsCmdSlots) + 1] = c1;
                 mbar_expect_tx(&ring_full[slot], bytes);
                 tma_load_5d(sRing + (size_t)slot * slot_bytes, &tmap_x, &ring_full[slot], 0, t0 - halo, h_start + ri, 0, b);
             }
@@ -230,11 +259,10 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
         // (measured: running the loop warp-uniformly with one elected lane issuing is not faster - the cost is the tcgen05 hand-off)
         if (lane == 0) {
             constexpr bool issuer = true;
-            constexpr uint32_t idesc1 = umma::make_idesc_bf16(128, NC), idesc2 = umma::make_idesc_bf16(128, 2 * NC), idesc3 = umma::make_idesc_bf16(128, N3);
-            const uint32_t ring0 = umma::smem_u32(sRing), zero0 = umma::smem_u32(sZero), w1_0 = umma::smem_u32(sW1);
+            const uint32_t zero0 = umma::smem_u32(sZero);
             constexpr uint32_t plane = (uint32_t)TW * 16u;
             constexpr uint32_t b_step = (2u * N3 * 16u) >> 4;             // two K groups per MMA
-            const uint32_t b_base = desc_lo(w1_0, N3 * 16u);
+            const uint4* cmds = reinterpret_cast<const uint4*>(smem + S_::kCmd);
             uint32_t ready = 0;
             TT_PROF(long long t_wait = 0, t_mma = 0, t_commit = 0, tp = clock64();)
             for (int ri = ri_first; ri <= ri_last; ++ri) {
@@ -242,19 +270,10 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
                 while (ready <= (uint32_t)idx)
                     asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(ready) : "r"(umma::smem_u32(rows_ready)) : "memory");
                 umma::fence_after_sync();
+                const uint4 c0 = cmds[2 * (idx % kRsCmdSlots)], c1 = cmds[2 * (idx % kRsCmdSlots) + 1];
                 TT_PROF(t_wait += clock64() - tp; tp = clock64();)
-                // target blocks j = 0, 1, 2 <-> output rows ri - D, ri, ri + D (vertical taps ky = 2, 1, 0)
-                const int j0 = ri >= D ? 0 : (ri >= 0 ? 1 : 2);
-                const int j1 = ri + D < n_out ? 2 : (ri < n_out ? 1 : 0);
-                const int res = (ri + D) % D;                            // residue class of the three targets
-                const int q1 = (ri + D) / D - 1;                         // ring sequence number of output row ri
-                const int pa = (q1 - 1 + j0) % SR;
-                const int na = min(j1 - j0 + 1, SR - pa), nb = (j1 - j0 + 1) - na;
-                const uint32_t row = ring0 + (uint32_t)(idx % kRing) * slot_bytes;
-                auto issue = [&](int pos, int jb, int nblk) {
-                    const uint32_t acc = tmem + (uint32_t)((res * SR + pos) * NC);
-                    const uint32_t idesc = nblk == 3 ? idesc3 : (nblk == 2 ? idesc2 : idesc1);
-                    uint32_t b_lo = b_base + (uint32_t)(jb * NC);         // + jb * NC rows of 16 bytes, in 16-byte units
+                const uint32_t row = c0.x;
+                auto issue = [&](uint32_t acc, uint32_t idesc, uint32_t b_lo) {
                     if constexpr (CG == 1) {
                         // kG K groups at column offsets g * kColStep, consumed as pairs (g, g+1); the unpaired last group meets a zero
                         // operand (never an arbitrary neighbour: stale shared memory times zero could be NaN)
@@ -278,10 +297,10 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
                         }
                     }
                 };
-                if (na > 0) issue(pa, j0, na);
-                if (nb > 0) issue(0, j0 + na, nb);
+                if (c0.z) issue(c0.y, c0.z, c0.w);
+                if (c1.y) issue(c1.x, c1.y, c1.z);
                 TT_PROF(t_mma += clock64() - tp; tp = clock64();)
-                if (ri - D >= 0) umma::commit(&acc1_full[slot_of(ri - D)]);
+                if (c1.w) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c1.w) : "memory");
                 if (ri == ri_last)
                     for (int it = max(0, ri_last - D + 1); it < n_out; ++it) umma::commit(&acc1_full[slot_of(it)]);
                 TT_PROF(t_commit += clock64() - tp; tp = clock64();)
