@@ -233,6 +233,15 @@ _WGRAD_SCRATCH = {}
 _BW_PACKS = {'epoch': -1}
 
 
+def _scratch(pool, device, n):
+    """One growing fp32 scratch buffer per device (the weight-gradient partials): reused by every layer, reallocated only to grow."""
+    buf = pool.get(device)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(n, dtype=torch.float32, device=device)
+        pool[device] = buf
+    return buf
+
+
 def _bw_pack(weight, tag, build):
     """Packed (kernel-layout) weights of the backward pass, built once per optimisation step per layer: the same layer runs backward
     two to four times per step (two encoder, four decoder passes), and every pack is a handful of tiny launches."""
@@ -250,15 +259,11 @@ def _wgrad_same(x8, dz8, cin, cout, k, d):
     """(dW (cout, cin, k, k), db (cout)) fp32 of a 'same' conv from C8 planar bf16 x and dz (tt_conv_wgrad_same, tensor cores)."""
     B, CGi, H, T, _ = x8.shape
     lib = _lib.lib()
-    n = int(lib.tt_wgrad_scratch_floats(B, H, T))
-    key = (x8.device, n)
-    if key not in _WGRAD_SCRATCH:
-        _WGRAD_SCRATCH.clear()
-        _WGRAD_SCRATCH[key] = torch.empty(n, dtype=torch.float32, device=x8.device)
+    scratch = _scratch(_WGRAD_SCRATCH, x8.device, int(lib.tt_wgrad_scratch_floats(B, H, T)))
     dw = torch.zeros((cout, cin, k, k), dtype=torch.float32, device=x8.device)
     db = torch.zeros(cout, dtype=torch.float32, device=x8.device)
     _lib.check(lib.tt_conv_wgrad_same(_p(x8), _p(dz8), _p(dw), _p(db), B, CGi * 8, dz8.size(1) * 8, cin, cout, H, T, k, d,
-                                      _p(_WGRAD_SCRATCH[key]), _s(x8)))
+                                      _p(scratch), _s(x8)))
     return dw, db
 
 
@@ -304,15 +309,11 @@ def _wgrad_updown(fine8, coarse8, cfine, ccoarse, transposed):
     B, CGf, Hf, T, _ = fine8.shape
     Hc = coarse8.size(2)
     lib = _lib.lib()
-    n = int(lib.tt_wgrad_scratch_floats(B, Hc, T))
-    key = (fine8.device, n)
-    if key not in _WGRAD_SCRATCH:
-        _WGRAD_SCRATCH.clear()
-        _WGRAD_SCRATCH[key] = torch.empty(n, dtype=torch.float32, device=fine8.device)
+    scratch = _scratch(_WGRAD_SCRATCH, fine8.device, int(lib.tt_wgrad_scratch_floats(B, Hc, T)))
     dw = torch.zeros((ccoarse, cfine, 4, 1), dtype=torch.float32, device=fine8.device)
     db = torch.zeros(cfine if transposed else ccoarse, dtype=torch.float32, device=fine8.device)
     _lib.check(lib.tt_conv_wgrad_updown(_p(fine8), _p(coarse8), _p(dw), _p(db), B, CGf * 8, coarse8.size(1) * 8, cfine, ccoarse, Hf, Hc, T,
-                                        int(transposed), _p(_WGRAD_SCRATCH[key]), _s(fine8)))
+                                        int(transposed), _p(scratch), _s(fine8)))
     return dw, db
 
 
@@ -374,13 +375,9 @@ def _wgrad_lat(tall8, flat8, ctall, cflat, dw, db, row_sums):
     """tt_conv_wgrad_lat: accumulates into dw (cflat.., ctall, H, 1) [first cflat rows], db (cflat) and row_sums (ctall, H) (either may be None)."""
     B, CGt, H, T, _ = tall8.shape
     lib = _lib.lib()
-    n = int(lib.tt_wgrad_lat_scratch_floats(B, H, T))
-    key = (tall8.device, n)
-    if key not in _LAT_SCRATCH:
-        _LAT_SCRATCH.clear()
-        _LAT_SCRATCH[key] = torch.empty(n, dtype=torch.float32, device=tall8.device)
+    scratch = _scratch(_LAT_SCRATCH, tall8.device, int(lib.tt_wgrad_lat_scratch_floats(B, H, T)))
     _lib.check(lib.tt_conv_wgrad_lat(_p(tall8), _p(flat8), _p(dw), _p(db), _p(row_sums), B, CGt * 8, flat8.size(1) * 8, ctall, cflat, H, T,
-                                     _p(_LAT_SCRATCH[key]), _s(tall8)))
+                                     _p(scratch), _s(tall8)))
 
 
 def _lat_tc_ok(c_tall, c_flat_pad):
