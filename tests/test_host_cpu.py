@@ -190,14 +190,34 @@ def _emulate_rs(x_rows, w1p, bias, d, shifts, step, halo, NC):
     return acc
 
 
+def _emulate_rs_fold(x_rows, w1p, bias, d, mmas, NC):
+    """The folded-row schedule of csrc/res_rs.cu (RsPlan::fold_s / fold_adj): MMA (s, adj) multiplies the first 16-byte half of GEMM
+    row t + s and the second half of row t + s - adj with the K groups (mma, half) of w1p."""
+    H, Tr, K = x_rows.shape
+    assert K == 16
+    halo = 1 + max(abs(s_) + a for s_, a in mmas)
+    w = w1p.float().reshape(len(mmas), 2, 3, NC, 8)                              # [mma][half][j][n][k]
+    xp = torch.nn.functional.pad(x_rows, (0, 0, halo, halo))
+    acc = bias[0].float().view(1, 1, NC).repeat(H, Tr, 1)
+    for r in range(H):
+        for m, (s_, adj) in enumerate(mmas):
+            first = xp[r, halo + s_: halo + s_ + Tr, :8]
+            second = xp[r, halo + s_ - adj: halo + s_ - adj + Tr, 8:]
+            for j in range(3):
+                o = r + (j - 1) * d
+                if 0 <= o < H:
+                    acc[o] += first @ w[m, 0, j].t() + second @ w[m, 1, j].t()
+    return acc
+
+
 def test_weight_packing_row_stationary():
     """packing.pack_res_rs / _pairs / _fold against F.conv2d through a torch emulation of the kernel's GEMM schedule."""
     import torch.nn.functional as F
     from timbre_trap_b200.framework import packing as P
     torch.manual_seed(0)
     H, T = 7, 24
-    for C, d, mode in ((16, 2, 'planar'), (32, 1, 'planar'), (4, 1, 'fold4'), (3, 3, 'fold4'), (8, 2, 'fold2'), (5, 3, 'fold2'),
-                       (4, 3, 'pairs'), (8, 1, 'planar8')):
+    for C, d, mode in ((16, 2, 'planar'), (32, 1, 'planar'), (4, 1, 'fold4'), (2, 2, 'fold4'), (3, 3, 'fold4'), (7, 1, 'fold2'), (8, 2, 'fold2'),
+                       (5, 3, 'fold2'), (4, 3, 'pairs'), (8, 1, 'planar8')):
         x = torch.randn(1, C, H, T).to(torch.bfloat16).float()
         w1, b1 = torch.randn(C, C, 3, 3).to(torch.bfloat16).float(), torch.randn(C)
         w2, b2 = torch.randn(C, C, 1, 1).to(torch.bfloat16).float(), torch.randn(C)
@@ -205,11 +225,13 @@ def test_weight_packing_row_stationary():
         if mode.startswith('fold'):
             fold = int(mode[-1]); Cw = 16 // fold
             w1p, w2p, bias = P.pack_res_rs_fold(w1, b1, w2, b2, d, fold)
-            hp = (d + 1) // 2 if fold == 2 else 1
-            assert tuple(w1p.shape) == (2 * (2 * hp + 1), 48, 8) and tuple(w2p.shape) == (2, 16, 8) and tuple(bias.shape) == (2, 16)
+            mmas = P.res_rs_fold_mmas(d, fold)
+            # two MMAs per input row where the taps' frames fit four 16-byte halves, three otherwise (never the 5 whole-row shifts of d = 3)
+            assert len(mmas) == (2 if (fold == 4 and d <= 2) or (fold == 2 and d == 1) else 3)
+            assert tuple(w1p.shape) == (2 * len(mmas), 48, 8) and tuple(w2p.shape) == (2, 16, 8) and tuple(bias.shape) == (2, 16)
             rows = torch.zeros(H, T // fold, fold, Cw)
             rows[..., :C] = x[0].permute(1, 2, 0).reshape(H, T // fold, fold, C)
-            acc = _emulate_rs(rows.reshape(H, T // fold, 16), w1p, bias, d, 2 * hp + 1, 1, hp, 16)
+            acc = _emulate_rs_fold(rows.reshape(H, T // fold, 16), w1p, bias, d, mmas, 16)
             got = acc.reshape(H, T // fold, fold, Cw)[..., :C].reshape(H, T, C).permute(2, 0, 1)
         elif mode == 'pairs':
             w1p, w2p, bias = P.pack_res_rs_pairs(w1, b1, w2, b2, d)

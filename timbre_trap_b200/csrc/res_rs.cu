@@ -76,7 +76,19 @@ struct RsPlan {
     static constexpr int kHalo = (P4 || MODE == kRsFold2) ? (D + 1) / 2 : (MODE == kRsFold4 ? 1 : D);   // column halo in GEMM rows (16-byte units)
     static constexpr int kColStep = (P4 || kFolded) ? 1 : D;         // distance between the horizontal taps / K groups of a row, 16-byte units
     static constexpr int kG = P4 ? 2 * kHalo + 1 : 3;                // K groups per row (CG = 1)
-    static constexpr int kShifts = kFolded ? 2 * kHalo + 1 : 3;      // horizontal taps (CG >= 2)
+    // Folded rows: the frames a row's 3 horizontal taps touch are picked K GROUP by K GROUP (a 16-byte half of a GEMM row), not row
+    // by row: MMA kx reads the first half of row i + s and the second half of row i + s - adj (adj = 1: LBO is one row short of the
+    // plane distance).  fold 4, d <= 2 and fold 2, d = 1: frames -2..5 / -1..2 of the row = 2 MMAs, not 3 whole-row shifts;
+    // fold 2, d = 3: frames {-3,-2, 0,1, 3,4} = 3 MMAs, not 5.
+    static constexpr bool kTwoMma = (MODE == kRsFold4 && D <= 2) || (MODE == kRsFold2 && D == 1);
+    static constexpr bool kSparse3 = MODE == kRsFold2 && D == 3;
+    static constexpr int kShifts = kFolded ? (kTwoMma ? 2 : 3) : 3;  // MMAs per input row and channel-group pair (CG >= 2)
+    static constexpr int fold_s(int kx) { return kTwoMma ? kx : (kSparse3 ? (kx == 2 ? 2 : kx - 1) : kx - 1); }
+    static constexpr int fold_adj(int kx) { return kTwoMma ? 1 : (kSparse3 ? (kx == 1 ? 0 : 1) : 0); }
+    // A-descriptor offset of MMA kx (low word: start address in 16-byte units, LBO in bits 16..29)
+    static constexpr uint32_t a_off(int kx) {
+        return kFolded ? (uint32_t)(fold_s(kx) + kHalo) - ((uint32_t)fold_adj(kx) << 16) : (uint32_t)(kx * kColStep);
+    }
     static constexpr int kRing = CG == 1 ? 32 : (CG == 2 ? 14 : 16);
     static constexpr int NC = CG >= 4 ? 32 : 16;                     // accumulator columns per output row (padded)
     static constexpr int N3 = 3 * NC;
@@ -291,7 +303,7 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
                         for (int kx = 0; kx < S_::kShifts; ++kx) {
 #pragma unroll
                             for (int q = 0; q < CG / 2; ++q) {
-                                if (issuer) umma::mma_bf16(acc, desc64(row_lo + (uint32_t)(kx * S_::kColStep) + (uint32_t)(2 * q) * (plane >> 4)), desc64(b_lo), idesc, true);
+                                if (issuer) umma::mma_bf16(acc, desc64(row_lo + S_::a_off(kx) + (uint32_t)(2 * q) * (plane >> 4)), desc64(b_lo), idesc, true);
                                 b_lo += b_step;
                             }
                         }

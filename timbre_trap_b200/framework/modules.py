@@ -563,7 +563,7 @@ class TimbreTrap(nn.Module):
         chunks = audio.unfold(-1, L, hop)[:, :, :n_chunks]                 # (B, 1, n_chunks, L) view
         return chunks.reshape(audio.size(0) * n_chunks, 1, L), n_chunks
 
-    def _chunked(self, audio, want_transcription, want_reconstruction, activations=True, prepadded=False):
+    def _chunked(self, audio, want_transcription, want_reconstruction, activations=True, prepadded=False, on_activations=None):
         """
         Batched form of chunked_inference (modules.py:204-269) for one or both switch settings with a shared
         encoder pass.  Returns (transcription, reconstruction) coefficient tensors (B, F, T, 2) interleaved - or the
@@ -572,6 +572,10 @@ class TimbreTrap(nn.Module):
         The last decoder stage of every chunk goes into one (B * n_chunks, F, M, 4) bf16 buffer per output; `convout`, the Hann
         cross-fade, the trim and (for activations) tanh|.| then run as ONE kernel over it (tt_conv_out_crossfade): the
         per-chunk fp32 coefficients of the reference's loop never exist.
+
+        `on_activations(lo, hi, activations[lo:hi])` (fused path only): called as soon as the clips [lo, hi) have all their chunks
+        through the decoder - their activations are produced right then, while the remaining chunk batches still compute, so a
+        caller that streams results off the device (framework.HostPipeline) can start copying early.
         """
         _lib.require_cuda(audio, 'audio')
         with torch.no_grad():
@@ -586,6 +590,10 @@ class TimbreTrap(nn.Module):
             else:
                 stages = [torch.empty((B * n_chunks, F, M, 2), dtype=torch.float32, device=audio.device) if w else None for w in wants]
             step = self.MAX_CHUNKS_PER_BATCH
+            early = on_activations is not None and fused and want_transcription and activations
+            if early:
+                act_early = torch.empty((B, F, n_out), dtype=torch.float32, device=audio.device)
+                emitted = 0
             for c0 in range(0, B * n_chunks, step):
                 lat, skips = self._codes(chunks[c0:c0 + step])
                 for stage, reconstruct in zip(stages, (False, True)):
@@ -600,11 +608,20 @@ class TimbreTrap(nn.Module):
                             # (modules.py:244, 259-263): broadcast, i.e. both channels carry the head's output
                             y = _channel0(y, self.HEAD_MODE).unsqueeze(-1).expand(-1, -1, -1, 2)
                         stage[c0:c0 + step] = y
+                if early:
+                    done = min(B, (c0 + step) // n_chunks)            # clips whose chunks have all been decoded
+                    if done > emitted:
+                        self._convout_crossfade(stages[0], emitted, done, n_chunks, window, None, act_early)
+                        on_activations(emitted, done, act_early[emitted:done])
+                        emitted = done
             _, _, w_out, b_out = self.decoder._packed()
             results = []
             for stage, want_act in zip(stages, (activations, False)):
                 if stage is None:
                     results.append(None)
+                    continue
+                if early and want_act:
+                    results.append(act_early)
                     continue
                 as_act = want_act and self.HEAD_MODE is None         # the fused tanh|.| is the BASE model's to_activations
                 if as_act:
@@ -626,6 +643,19 @@ class TimbreTrap(nn.Module):
                     res = self.to_activations(res.permute(0, 3, 1, 2))       # a variant's own activation function
                 results.append(res)
             return results
+
+    def _convout_crossfade(self, stage, lo, hi, n_chunks, window, out_coeffs, out_act):
+        """tt_conv_out_crossfade over the clips [lo, hi) of a (B * n_chunks, F, M, 4) stage buffer."""
+        F, M = self.sliCQ.n_bins, self.sliCQ.max_window_length
+        _, _, w_out, b_out = self.decoder._packed()
+        sub = stage[lo * n_chunks: hi * n_chunks]
+        with torch.cuda.device(stage.device):
+            _lib.check(_lib.lib().tt_conv_out_crossfade(ctypes.c_void_p(sub.data_ptr()), ctypes.c_void_p(window.data_ptr()),
+                                                        ctypes.c_void_p(w_out.data_ptr()), ctypes.c_void_p(b_out.data_ptr()),
+                                                        hi - lo, n_chunks, self.decoder.channels[4], F, M,
+                                                        None if out_coeffs is None else ctypes.c_void_p(out_coeffs[lo:hi].data_ptr()),
+                                                        None if out_act is None else ctypes.c_void_p(out_act[lo:hi].data_ptr()),
+                                                        ctypes.c_void_p(torch.cuda.current_stream(stage.device).cuda_stream)))
 
     def chunked_inference(self, audio, transcribe=False):
         """modules.py:204-269: (B, 1, N) -> (B, 2, F, T) cross-faded coefficients."""
@@ -666,9 +696,10 @@ class TimbreTrap(nn.Module):
         """modules.py:315-336: (B, 1, N) -> audio (B, 1, N') in [-1, 1].  `group`: see _decode_shared_peak."""
         return self._decode_shared_peak(self._chunked(audio_in, False, True)[1].permute(0, 3, 1, 2), group)
 
-    def transcribe_and_reconstruct(self, audio, group=None):
-        """Both outputs of transcribe() and reconstruct() from ONE encoder pass (not in the reference, which runs two)."""
-        act, rec = self._chunked(audio, True, True)
+    def transcribe_and_reconstruct(self, audio, group=None, on_activations=None):
+        """Both outputs of transcribe() and reconstruct() from ONE encoder pass (not in the reference, which runs two).
+        `on_activations`: see _chunked (early hand-over of finished clips' activations; the returned tensors are the same)."""
+        act, rec = self._chunked(audio, True, True, on_activations=on_activations)
         return act, self._decode_shared_peak(rec.permute(0, 3, 1, 2), group)
 
     # ---- one long clip over several GPUs (BASELINE.json configs[4]) ---------------------------------------------------

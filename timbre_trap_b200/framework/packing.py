@@ -290,35 +290,51 @@ def pack_res_rs_pairs(w1, b1, w2, b2, dilation):
     return w1p, w2p, bias
 
 
+def res_rs_fold_mmas(dilation, fold):
+    """The MMAs of one folded input row (csrc/res_rs.cu, RsPlan::fold_s / fold_adj): (s, adj) = first half of GEMM row i + s and second
+    half of row i + s - adj."""
+    d = int(dilation)
+    if (fold == 4 and d <= 2) or (fold == 2 and d == 1):
+        return [(0, 1), (1, 1)]
+    if fold == 2 and d == 3:
+        return [(-1, 1), (0, 0), (2, 1)]
+    return [(-1, 0), (0, 0), (1, 0)]
+
+
 def pack_res_rs_fold(w1, b1, w2, b2, dilation, fold):
     """
     pack_res_rs for FOLDED rows (csrc/res_rs.cu layouts 2 and 4): a GEMM row is `fold` consecutive frames x Cw = 16 / fold
     channels (fold = 2: C <= 8 in C8 planar; fold = 4: C <= 4 in the packed layout), i.e. always 16 values = two K groups
-    (halves).  The horizontal tap (kx - 1) * d becomes row offsets o in [-hp, hp] with fold * o + e_in - e_out = (kx - 1) * d
-    (Toeplitz expansion over the frames of a row); hp = ceil((d+1)/2) for fold = 2, 1 for fold = 4.
-    W1 -> (2 (2 hp + 1), 48, 8): K groups (o, half); rows n = j * 16 + e_out * Cw + co with j <-> vertical tap ky = 2 - j.
+    (halves).  The 3x3 kernel is Toeplitz-expanded over the frames of a row: a K group holding input frame f_in (relative to the
+    first frame of the output row) meets output frame e_out through the horizontal tap kx with (kx - 1) * d = f_in - e_out.  Which
+    halves of which neighbouring rows form the K = 16 of one MMA is `res_rs_fold_mmas` (only the halves some tap touches are read).
+    W1 -> (2 n_mma, 48, 8): K groups (mma, half); rows n = j * 16 + e_out * Cw + co with j <-> vertical tap ky = 2 - j.
     W2 -> (2, 16, 8) block-diagonal over the frames; bias -> (2, 16).
     """
     Co, Ci = w1.shape[:2]
     Cw = 16 // fold
     assert fold in (2, 4) and Co <= Cw and Ci <= Cw
     d = int(dilation)
-    hp = (d + 1) // 2 if fold == 2 else 1
     dev = w1.device
     w = w1.detach().float()
     per_half = fold // 2                                       # frames per 16-byte half
-    groups = []
-    for o in range(-hp, hp + 1):
-        g = torch.zeros((3, 16, 16), dtype=torch.float32, device=dev)          # [j][n][k over the whole row]
-        for e_out in range(fold):
-            for e_in in range(fold):
-                s_ = fold * o + e_in - e_out
-                for kx in range(3):
-                    if (kx - 1) * d == s_:
-                        for j in range(3):
-                            g[j, e_out * Cw: e_out * Cw + Co, e_in * Cw: e_in * Cw + Ci] = w[:, :, 2 - j, kx]
-        g = g.reshape(48, 16)
-        groups += [g[:, :8], g[:, 8:]]
+    assert per_half * Cw == 8
+    groups, seen = [], set()
+    for s_row, adj in res_rs_fold_mmas(d, fold):
+        for half in range(2):
+            first = fold * (s_row - adj * half) + per_half * half          # input frame of the half's first value
+            g = torch.zeros((3, 16, 8), dtype=torch.float32, device=dev)   # [j][n][k within the half]
+            for e_in in range(per_half):
+                f_in = first + e_in
+                assert f_in not in seen
+                seen.add(f_in)
+                for e_out in range(fold):
+                    for kx in range(3):
+                        if (kx - 1) * d == f_in - e_out:
+                            for j in range(3):
+                                g[j, e_out * Cw: e_out * Cw + Co, e_in * Cw: e_in * Cw + Ci] = w[:, :, 2 - j, kx]
+            groups.append(g.reshape(48, 8))
+    assert all(e_out + (kx - 1) * d in seen for e_out in range(fold) for kx in range(3))
     w1p = torch.stack(groups, dim=0).contiguous().to(torch.bfloat16)
     g2 = torch.zeros((16, 16), dtype=torch.float32, device=dev)
     bias = torch.zeros((2, 16), dtype=torch.float32, device=dev)
@@ -327,7 +343,6 @@ def pack_res_rs_fold(w1, b1, w2, b2, dilation, fold):
         bias[0, e * Cw: e * Cw + Co] = b1.detach().float()
         bias[1, e * Cw: e * Cw + Co] = b2.detach().float()
     w2p = torch.stack([g2[:, :8], g2[:, 8:]], dim=0).contiguous().to(torch.bfloat16)
-    assert per_half * Cw == 8
     return w1p, w2p, bias
 
 

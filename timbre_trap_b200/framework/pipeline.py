@@ -7,14 +7,63 @@ compute stream, the device-to-host read of step k (0.63 GB for 256 blocks) delay
 ranks' reads contend for host memory at the same moment.  `HostPipeline` keeps three streams - copy-in, compute, copy-out - and
 `depth` sets of pinned output buffers, so the read-back of step k overlaps the compute of step k+1:
 
-    pipe = HostPipeline(model, depth=2)
+    pipe = HostPipeline(model, depth=3)
     tickets = [pipe.submit(batch) for batch in pinned_batches]      # returns immediately (blocks only when `depth` are in flight)
     activations, audio = pipe.collect(ticket)                       # pinned host tensors, valid until the slot is reused
+
+Two details matter once eight ranks share one host (measured, profiles/r02_e2e_readback_check_n8.txt: a rank's 0.63 GB read-back takes
+11 ms alone and 35-55 ms when all eight copy at once):
+  * `early`: the model hands over the activations of the clips whose chunks are through the decoder after every chunk batch
+    (TimbreTrap.transcribe_and_reconstruct(on_activations=...)); they start their way to the host while the next chunk batch
+    computes, so only the last batch's share and the audio are left to copy when the step's last kernel ends - the drain of the
+    pipeline after the final step shrinks from the whole read-back to about a third of it;
+  * keep TWO submissions in flight (depth >= 3, collect ticket k - 2 after submitting k): the host then never waits for a
+    read-back before it may enqueue the next step's ~2000 launches, and the GPU never runs dry.
 """
+
+import contextlib
+import os
 
 import torch
 
-__all__ = ['HostPipeline']
+__all__ = ['HostPipeline', 'gpu_local_cpus', 'near_gpu']
+
+
+def gpu_local_cpus(device):
+    """The CPUs of the NUMA node the GPU's PCIe root port hangs off (sysfs `local_cpulist`), or None when the kernel does not say."""
+    try:
+        p = torch.cuda.get_device_properties(device)
+        path = f'/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/local_cpulist'
+        with open(path) as f:
+            text = f.read().strip()
+    except (OSError, AttributeError, RuntimeError):
+        return None
+    cpus = set()
+    for part in filter(None, text.split(',')):
+        lo, _, hi = part.partition('-')
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus or None
+
+
+@contextlib.contextmanager
+def near_gpu(device):
+    """Run the body on the GPU-local CPUs, so that pinned host memory allocated inside lands on the GPU's own NUMA node (first-touch
+    policy).  With one process per GPU and every rank reading back 0.63 GB per step, buffers that all sit on the node the launcher
+    happened to start on send half of the ranks' traffic across the socket interconnect.  A no-op where sysfs gives no answer."""
+    if not hasattr(os, 'sched_getaffinity'):
+        yield False
+        return
+    before = os.sched_getaffinity(0)
+    local = gpu_local_cpus(device)
+    want = (local & before) if local else None
+    if not want or want == before:
+        yield False
+        return
+    os.sched_setaffinity(0, want)
+    try:
+        yield True
+    finally:
+        os.sched_setaffinity(0, before)
 
 
 class _Slot:
@@ -29,8 +78,10 @@ class _Slot:
 
 
 class HostPipeline:
-    def __init__(self, model, device=None, depth=2, group=None):
+    def __init__(self, model, device=None, depth=3, group=None, numa_local=True, early=True):
         self.model = model
+        self.numa_local = numa_local
+        self.early = bool(early)
         self.device = torch.device(device) if device is not None else next(model.parameters()).device
         if self.device.type != 'cuda':
             raise ValueError('HostPipeline needs the model on a CUDA device')
@@ -58,20 +109,46 @@ class HostPipeline:
                 slot.dev_in.copy_(host_audio, non_blocking=True)
                 slot.in_done.record(self.s_in)
             comp.wait_event(slot.in_done)
-            act, wav = self.model.transcribe_and_reconstruct(slot.dev_in, group=self.group)
-            slot.comp_done.record(comp)
-            if slot.host_act is None or slot.host_act.shape != act.shape or slot.host_wav.shape != wav.shape:
-                slot.host_act = torch.empty(act.shape, dtype=act.dtype).pin_memory()
-                slot.host_wav = torch.empty(wav.shape, dtype=wav.dtype).pin_memory()
-            with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(slot.comp_done)
-                slot.host_act.copy_(act, non_blocking=True)
-                slot.host_wav.copy_(wav, non_blocking=True)
-                slot.out_done.record(self.s_out)
-            # the results are read on another stream: keep the allocator from handing their memory to the next step early
-            act.record_stream(self.s_out)
-            wav.record_stream(self.s_out)
+            self._run(slot, comp)
         return k
+
+    def _host_buffers(self, slot, act_shape, wav_shape, dtype):
+        if slot.host_act is None or tuple(slot.host_act.shape) != tuple(act_shape) or tuple(slot.host_wav.shape) != tuple(wav_shape):
+            slot.host_act = self.pinned_empty(act_shape, dtype)
+            slot.host_wav = self.pinned_empty(wav_shape, dtype)
+
+    def _run(self, slot, comp):
+        B = slot.dev_in.size(0)
+        sent = []                                          # clip ranges whose activations are already on their way
+
+        def on_activations(lo, hi, act):
+            if slot.host_act is None or tuple(slot.host_act.shape) != (B,) + tuple(act.shape[1:]):
+                return                                     # first use of this slot / new shape: everything goes at the end
+            ready = torch.cuda.Event()
+            ready.record(comp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(ready)
+                slot.host_act[lo:hi].copy_(act, non_blocking=True)
+            sent.append((lo, hi))
+
+        act, wav = self.model.transcribe_and_reconstruct(slot.dev_in, group=self.group, on_activations=on_activations if self.early else None)
+        slot.comp_done.record(comp)
+        self._host_buffers(slot, act.shape, wav.shape, act.dtype)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(slot.comp_done)
+            done = sent[-1][1] if sent else 0              # the hook is called with consecutive ranges starting at clip 0
+            if done < B:
+                slot.host_act[done:].copy_(act[done:], non_blocking=True)
+            slot.host_wav.copy_(wav, non_blocking=True)
+            slot.out_done.record(self.s_out)
+        # the results are read on another stream: keep the allocator from handing their memory to the next step early
+        act.record_stream(self.s_out)
+        wav.record_stream(self.s_out)
+
+    def pinned_empty(self, shape, dtype=torch.float32):
+        """A pinned host tensor on the GPU's NUMA node (for the caller's input batches as well)."""
+        with near_gpu(self.device) if self.numa_local else contextlib.nullcontext():
+            return torch.empty(tuple(shape), dtype=dtype, pin_memory=True)
 
     def collect(self, ticket):
         """Blocks until the results of `ticket` are on the host; returns (activations (B, F, T), audio (B, 1, N')) pinned tensors
