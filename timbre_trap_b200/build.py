@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libtimbretrap_b200.so')
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC']
+              '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC'] + os.environ.get('TT_NVCC_EXTRA', '').split()   # e.g. -D switches of A/B builds
 
 
 def sources():

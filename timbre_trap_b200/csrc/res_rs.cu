@@ -48,6 +48,9 @@ constexpr int kRsEpiWarps = 16;
 // warps: 16 epilogue + TMA producer + scout + 3x3 issuer + 1x1 issuer (the last four use one thread each)
 constexpr int kRsThreads = (kRsEpiWarps + 4) * 32;
 constexpr int kRsSlots = 16;       // TMEM accumulator slots (3x3 rings + 1x1 slots)
+#ifndef TT_RS_EPI_SLEEP
+#define TT_RS_EPI_SLEEP 40
+#endif
 constexpr int kRsCmdSlots = 32;    // >= the deepest input-row ring: the scout can never be further ahead of the issuer than that
 
 struct ResRsParams {
@@ -89,7 +92,15 @@ struct RsPlan {
     static constexpr uint32_t a_off(int kx) {
         return kFolded ? (uint32_t)(fold_s(kx) + kHalo) - ((uint32_t)fold_adj(kx) << 16) : (uint32_t)(kx * kColStep);
     }
-    static constexpr int kRing = CG == 1 ? 32 : (CG == 2 ? 14 : 16);
+#ifndef TT_RS_RING2
+#define TT_RS_RING2 17
+#endif
+#ifndef TT_RS_RING4
+#define TT_RS_RING4 20
+#endif
+    // input-row ring: a row stays until the epilogue of ITS output row has read it as the residual (~4-7 row periods after its MMAs),
+    // and the producer throttles on ring_free (measured: 280-320 cycles per row at 14 / 16 slots) - as deep as shared memory allows
+    static constexpr int kRing = CG == 1 ? 32 : (CG == 2 ? TT_RS_RING2 : TT_RS_RING4);
     static constexpr int NC = CG >= 4 ? 32 : 16;                     // accumulator columns per output row (padded)
     static constexpr int N3 = 3 * NC;
     static constexpr int KG1 = CG == 1 ? kG + 1 : kShifts * CG;
@@ -111,6 +122,8 @@ struct RsPlan {
     static constexpr int kCmd = kZero + 2048;                        // per-row issue commands, written by the scout (kRsCmdSlots x 32 bytes)
     static constexpr int kTotal = kCmd + kRsCmdSlots * 32;
     static_assert(SR >= 3 && D * SR + A2 <= kRsSlots, "TMEM slot plan");
+    static_assert(kRing <= kRsCmdSlots, "one command slot per ring slot at least");
+    static_assert(kTotal <= (CG <= 2 ? 115712 : 232448), "shared memory: two CTAs per SM for CG <= 2, one for CG = 4");
 };
 
 template <int NV>
@@ -222,6 +235,7 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
             const uint32_t ring0 = umma::smem_u32(sRing);
             const uint32_t b_base = desc_lo(umma::smem_u32(sW1), N3 * 16u);
             uint4* cmds = reinterpret_cast<uint4*>(smem + S_::kCmd);
+            TT_PROF(long long t_plan = 0, t_free = 0, t_tma = 0, tp = clock64();)
             for (int ri = ri_first; ri <= ri_last; ++ri) {
                 const int idx = ri - ri_first, slot = idx % kRing;
                 // target blocks j = 0, 1, 2 <-> output rows ri - D, ri, ri + D (vertical taps ky = 2, 1, 0)
@@ -240,12 +254,19 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
                 c1.y = nb <= 0 ? 0u : (nb == 3 ? idesc3 : (nb == 2 ? idesc2 : idesc1));
                 c1.z = b_base + (uint32_t)((j0 + na) * NC);
                 c1.w = ri - D >= 0 ? umma::smem_u32(&acc1_full[slot_of(ri - D)]) : 0u;                // barrier of the row this one completes
+                TT_PROF(t_plan += clock64() - tp; tp = clock64();)
                 if (idx >= kRing) umma::mbar_wait(&ring_free[slot], (uint32_t)((idx / kRing - 1) & 1));
+                TT_PROF(t_free += clock64() - tp; tp = clock64();)
                 cmds[2 * (idx % kRsCmdSlots)] = c0;
                 cmds[2 * (idx % kRsCmdSlots) + 1] = c1;
                 mbar_expect_tx(&ring_full[slot], bytes);
                 tma_load_5d(sRing + (size_t)slot * slot_bytes, &tmap_x, &ring_full[slot], 0, t0 - halo, h_start + ri, 0, b);
+                TT_PROF(t_tma += clock64() - tp; tp = clock64();)
             }
+            TT_PROF(if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+                        const int nr = ri_last - ri_first + 1;
+                        printf("rs producer: cycles/row: plan %lld, ring_free wait %lld, command + tma %lld\n", t_plan / nr, t_free / nr, t_tma / nr);
+                    })
         }
     } else if (warp == kRsEpiWarps + 1) {
         // =================================== scout ===================================
@@ -253,16 +274,23 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
         // (the other two targets were acquired with earlier rows).  A barrier probe costs ~100 cycles even when it succeeds; the issuer
         // only reads one counter.
         if (lane == 0) {
+            TT_PROF(long long t_full = 0, t_acc = 0, tp = clock64();)
             for (int ri = ri_first; ri <= ri_last; ++ri) {
                 const int idx = ri - ri_first;
                 umma::mbar_wait(&ring_full[idx % kRing], (uint32_t)((idx / kRing) & 1));
+                TT_PROF(t_full += clock64() - tp; tp = clock64();)
                 const int it_new = ri + D;
                 if (it_new < n_out) {
                     const int u = (it_new / D) / SR;
                     if (u > 0) umma::mbar_wait(&acc1_free[slot_of(it_new)], (uint32_t)((u - 1) & 1));
                 }
                 asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(umma::smem_u32(rows_ready)), "r"((uint32_t)idx + 1u) : "memory");
+                TT_PROF(t_acc += clock64() - tp; tp = clock64();)
             }
+            TT_PROF(if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+                        const int nr = ri_last - ri_first + 1;
+                        printf("rs scout: cycles/row: row landed %lld, accumulator free + publish %lld\n", t_full / nr, t_acc / nr);
+                    })
         }
     } else if (warp == kRsEpiWarps + 2) {
         // =================================== 3x3 MMA issuer: one thread, input rows in order ===================================
@@ -367,7 +395,7 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
         auto epi1 = [&](int it) {
             const int sl = slot_of(it), a = it % A2;
             TT_PROF(tp = clock64();)
-            umma::mbar_wait(&acc1_full[sl], (uint32_t)(((it / D) / SR) & 1));
+            umma::mbar_wait_ns(&acc1_full[sl], (uint32_t)(((it / D) / SR) & 1), TT_RS_EPI_SLEEP);
             umma::fence_after_sync();
             TT_PROF(t_w1 += clock64() - tp; tp = clock64();)
             uint8_t* mid = sMid + (size_t)a * S_::kMidSlot + (size_t)j * 16u;
@@ -411,7 +439,7 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
         auto epi2 = [&](int it) {
             const int u = it / A2, a = it % A2;
             TT_PROF(tp = clock64();)
-            umma::mbar_wait(&acc2_full[a], (uint32_t)(u & 1));
+            umma::mbar_wait_ns(&acc2_full[a], (uint32_t)(u & 1), TT_RS_EPI_SLEEP);
             umma::fence_after_sync();
             TT_PROF(t_w2 += clock64() - tp; tp = clock64();)
             const int ridx = it - ri_first;                            // ring index of row h
@@ -461,9 +489,20 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
             TT_PROF(t_e2 += clock64() - tp;)
         };
         if constexpr (A2 >= 2 * kRsGroups) {
-            // two slot sets per group: the 1x1 round trip of a row overlaps the first epilogue of the group's next row
+            // two slot sets per group: the 1x1 round trip of a row overlaps the first epilogue of the group's next row - unless that
+            // row's accumulator is not there yet (measured: ~1000 cycles of waiting per row): then the pending second epilogue goes
+            // first, which hands its input-row slot back to the producer and its accumulator to the 1x1 issuer that much earlier
             int prev = -1;
             for (int it = g; it < n_out; it += kRsGroups) {
+#ifndef TT_RS_STATIC_ORDER
+                if (prev >= 0) {
+                    const bool there = umma::mbar_try(&acc1_full[slot_of(it)], (uint32_t)(((it / D) / SR) & 1));
+                    if (!__all_sync(0xffffffffu, there)) {
+                        epi2(prev);
+                        prev = -1;
+                    }
+                }
+#endif
                 epi1(it);
                 if (prev >= 0) epi2(prev);
                 prev = it;

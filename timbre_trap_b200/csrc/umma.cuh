@@ -140,6 +140,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// the same with the caller's back-off: warps with slack in their schedule (the epilogue groups of res_rs.cu) can sleep longer
+// between probes than the threads on the kernel's critical path
+__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+    if (mbar_try(bar, parity)) return;
+    while (!mbar_try(bar, parity)) __nanosleep(sleep_ns);
+}
+
 // warp-collective wait: one lane polls (32x less traffic on the shared-memory pipe than every lane spinning), the rest of
 // the warp is released by __syncwarp(), which also orders memory among the lanes
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
