@@ -41,6 +41,34 @@ def test_forward_matches_oracle(cfg, batch, blocks):
             assert e < 5 * TOL, (k, e)
 
 
+# other geometries the wrapper can be constructed with: max_window_length 32 ... 4096 (the generic shared-memory per-bin transform;
+# 1024 is the tuned register one), an ODD block length (33075), block lengths with every allowed prime factor
+SWEEP = [(5, 12, 8000, 0.25), (7, 36, 44100, 1.0), (4, 24, 16000, 0.3), (9, 60, 22050, 1.5), (6, 48, 11025, 2.0), (3, 12, 8000, 0.064),
+         (8, 12, 48000, 0.5), (10, 24, 44100, 2.0)]
+
+
+@pytest.mark.parametrize('cfg', SWEEP)
+def test_other_geometries_match_oracle(cfg):
+    cqt, ref = _mods(cfg)
+    assert (cqt.block_length, cqt.max_window_length, cqt.n_bins) == (ref.block_length, ref.max_window_length, ref.n_bins)
+    batch, blocks = 2, 2
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy(rng.uniform(-1, 1, (batch, 1, blocks * ref.block_length)).astype(np.float32))
+    got, want = cqt(x.cuda()), ref(x)
+    assert got.shape == want.shape
+    emax, el2 = rel_err(got.cpu().numpy(), want.numpy())
+    assert emax < TOL and el2 < TOL, ('forward', emax, el2)
+    c = torch.from_numpy(rng.standard_normal(tuple(want.shape)).astype(np.float32))
+    raw, peak = cqt.decode_raw(c.cuda())
+    want_raw = ref.decode_raw(c)
+    emax, el2 = rel_err(raw.cpu().numpy(), want_raw.numpy())
+    assert emax < TOL and el2 < TOL, ('inverse', emax, el2)
+    assert abs(float(peak) - float(want_raw.abs().max())) <= TOL * float(want_raw.abs().max())
+    # block independence: a block's coefficients do not depend on its neighbours or its position in the batch, bit for bit
+    solo = cqt(x[1:, :, ref.block_length:].contiguous().cuda())
+    assert torch.equal(solo, got[1:, :, :, ref.max_window_length:])
+
+
 def test_encode_complex_and_layout_helpers():
     cqt, ref = _mods(SMALL)
     x = tonal_clip(2 * ref.block_length, SMALL[2], seed=3, n_batch=2)
