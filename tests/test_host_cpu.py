@@ -146,6 +146,12 @@ def test_unsupported_channel_plans_fail_at_construction():
         TimbreTrap(22050, 9, 60, 3, model_complexity=3)
     TimbreTrap(22050, 9, 60, 3, model_complexity=1)
     TimbreTrap(22050, 9, 60, 3, latent_size=128, model_complexity=2)
+    # latent sizes: padded to the GEMM widths the (H, 1)-kernel layers are built for, the state_dict keeps the reference's shapes
+    for latent, pad in ((1, 16), (16, 16), (24, 32), (40, 64), (100, 128), (129, 256), (256, 256)):
+        m = TimbreTrap(8000, 6, 12, 0.5, latent_size=latent)
+        assert m.encoder.latent_pad == m.decoder.latent_pad == pad and m.encoder.convlat.weight.size(0) == latent
+    with pytest.raises(ValueError, match='latent_size'):
+        TimbreTrap(8000, 6, 12, 0.5, latent_size=257)
 
 
 def test_cpu_tensors_are_rejected_loudly():

@@ -84,6 +84,30 @@ def test_small_model_vs_oracle_and_golden(golden_dir, tag, complexity, latent, s
     assert torch.equal(act2, act) and torch.equal(wav2, wav)
 
 
+@pytest.mark.parametrize('cfg,latent,complexity,skip', [
+    (dict(sample_rate=8000, n_octaves=5, bins_per_octave=12, secs_per_block=0.25), None, 1, False),     # F = 60: 60 -> 29 -> 13 -> 5 -> 1 rows, M = 128
+    (dict(sample_rate=16000, n_octaves=4, bins_per_octave=24, secs_per_block=0.3), 16, 2, True),        # F = 96: 47, 22, 10, 4 rows, M = 256, skips
+    (dict(sample_rate=44100, n_octaves=7, bins_per_octave=36, secs_per_block=1.0), 40, 1, False),       # F = 252: 125, 61, 29, 13 rows, latent not a multiple of 16
+])
+def test_other_geometries_vs_oracle(cfg, latent, complexity, skip):
+    """Row counts, window lengths and latent sizes other than the two the golden vectors hold: every conv stage sees odd and even
+    heights down to a single row, the decoder's output paddings follow the encoder's sizes (modules.py:486-531)."""
+    from oracle import model_ref as R
+    model, sd, c = _build(cfg, latent, complexity, skip, seed=4)
+    audio = tonal_clip(int(2.3 * c.block_length), cfg['sample_rate'], seed=6, n_batch=2)
+    whole = c.pad_to_block_length(audio)
+    rec, lat, trn, _, _, _ = model(whole.cuda())
+    want = R.forward_ref(whole, sd, c)
+    for name, a, b in (('rec', rec, want[0]), ('latents', lat, want[1]), ('trn', trn, want[2])):
+        assert a.shape == b.shape
+        _check_logits(a.cpu().numpy(), b.numpy(), name)
+    act = model.transcribe(audio.cuda())
+    act_ref = R.transcribe_ref(audio, sd, c)
+    assert act.shape == act_ref.shape and float((act.cpu() - act_ref).abs().max()) <= 1e-2
+    act2, wav = model.transcribe_and_reconstruct(audio.cuda())
+    assert torch.equal(act2, act) and wav.shape == (2, 1, whole.size(-1)) and abs(float(wav.abs().max()) - 1.0) < 1e-5
+
+
 def test_base_model_one_chunk_vs_oracle_and_golden(golden_dir):
     """BASELINE.json configs[0]: base model, one synthetic 3 s clip."""
     from oracle import model_ref as R

@@ -64,11 +64,11 @@ def test_transposed_roles(Cin, Cout, KH, sh, op, H):
     assert torch.allclose(TR._channel_sum(gyc).cpu(), gy.sum(dim=(0, 2, 3)), atol=1e-3, rtol=1e-4)
 
 
-def _setup(skip=False):
+def _setup(skip=False, latent=None):
     from oracle import model_ref as R
     from timbre_trap_b200.framework import TimbreTrap
-    model = TimbreTrap(latent_size=None, model_complexity=1, skip_connections=skip, **SMALL)
-    sd = R.init_state_dict(model.sliCQ.n_bins, None, 1, seed=3)
+    model = TimbreTrap(latent_size=latent, model_complexity=1, skip_connections=skip, **SMALL)
+    sd = R.init_state_dict(model.sliCQ.n_bins, latent, 1, seed=3)
     if skip:
         sd['skip_weights'] = torch.tensor([0.9, 1.1, 0.8, 1.2, 0.7])
     model.load_state_dict(sd)
@@ -96,14 +96,14 @@ def _oracle_grads(R, sd, c, audio, gt):
     return {k: v.grad for k, v in sd.items()}, losses, float(total.detach())
 
 
-@pytest.mark.parametrize('skip', [False, True])
-def test_step_gradients_match_oracle_autograd(skip):
+@pytest.mark.parametrize('skip,latent', [(False, None), (True, None), (False, 40)])     # 40 latent channels: padded to 64 in the kernels
+def test_step_gradients_match_oracle_autograd(skip, latent):
     from timbre_trap_b200.framework.train import TrainStep
-    R, model, sd, c, audio, gt = _setup(skip)
+    R, model, sd, c, audio, gt = _setup(skip, latent)
     want, want_losses, want_total = _oracle_grads(R, sd, c, audio, gt)
     ts = TrainStep(model)
     out = ts.losses(audio.cuda(), gt.cuda())
-    np.testing.assert_allclose(float(out['total']), want_total, rtol=3e-2)
+    np.testing.assert_allclose(float(out['total'].detach()), want_total, rtol=3e-2)
     ts.backward(out['total'])
     got = {k: p.grad.detach().cpu() for k, p in model.named_parameters()}
     assert set(got) == set(want)

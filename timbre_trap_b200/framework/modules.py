@@ -204,7 +204,7 @@ class Encoder(nn.Module):
         self.convlat = nn.Conv2d(channels[4], latent_size, kernel_size=(embedding_size, 1))
         self.channels = channels
         self.latent_size = latent_size
-        self.latent_pad = (latent_size + 15) // 16 * 16
+        self.latent_pad = _latent_pad(latent_size)
         # first stage in the packed 4-channel layout (8 B per frame instead of the 16 B of channel-padded C8 planar)
         self.packed4 = channels[0] <= 4 and channels[1] <= 8
         self.block1.set_packed4(self.packed4)
@@ -264,7 +264,7 @@ class Decoder(nn.Module):
         self.convout = nn.Conv2d(channels[4], 2, kernel_size=3, padding='same')
         self.channels = channels
         self.latent_size = latent_size
-        self.latent_pad = (latent_size + 15) // 16 * 16
+        self.latent_pad = _latent_pad(latent_size)
         self.embedding_size = embedding_size
         self.packed4 = channels[4] <= 4 and channels[3] <= 8
         self.block4.set_packed4(self.packed4)
@@ -400,6 +400,14 @@ def _unit_skips(embeddings_internal):
     """Already-weighted embeddings (the API form of Decoder.forward / TimbreTrap.decode) as (weight 1, embedding) pairs."""
     one = torch.ones((), dtype=torch.float32, device=embeddings_internal[0].device)
     return [(one, e) for e in embeddings_internal]
+
+
+def _latent_pad(latent_size):
+    """Latent channels as the (H, 1)-kernel layers see them: zero-padded to the next GEMM width the kernels are built for."""
+    for n in (16, 32, 64, 128, 256):
+        if latent_size <= n:
+            return n
+    raise ValueError(f'latent_size {latent_size} is not supported (at most 256)')
 
 
 def _latents_to_c8(latents, latent_pad):
