@@ -202,7 +202,7 @@ def run_reference(args, rank):
                                   sample=f'{args.steps} steps x {n_blocks} block(s) of 3 s; oracle/model_ref.py convs + a torch.fft NSGT on the oracle tables (the '
                                          'reference is pure Python with an un-vendored CQT dependency; /root/reference is absent on the GPU box)'),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -485,10 +485,33 @@ def run_ours(args, rank, world, local_rank):
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on rank 0's stdout.  Libraries print there too (NCCL's version banner on process-group creation,
+    for one): from here on file descriptor 1 is stderr for everything but emit()."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        os.write(1, data)
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)
