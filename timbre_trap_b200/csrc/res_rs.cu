@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
             for (int it = g; it < n_out; it += kRsGroups) {
 #ifndef TT_RS_STATIC_ORDER
                 if (prev >= 0) {
-                    const bool there = umma::mbar_try(&acc1_full[slot_of(it)], (uint32_t)(((it / D) / SR) & 1));
+                    const bool there = umma::mbar_test(&acc1_full[slot_of(it)], (uint32_t)(((it / D) / SR) & 1));
                     if (!__all_sync(0xffffffffu, there)) {
                         epi2(prev);
                         prev = -1;
