@@ -14,6 +14,8 @@
 // ones operand and yields db.  A CTA walks a strip of image rows of one 128-pixel column tile (X rows live in a ring, every row is
 // fetched once per strip, out-of-image rows arrive as zeros from the TMA), then writes its accumulators to a partial buffer; a
 // second kernel sums the partials in a fixed order (deterministic) into the PyTorch weight layout (co, ci, kh, kw).
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "../../include/timbre_trap_b200.h"
@@ -193,6 +195,205 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     umma::fence_before_sync();
     __syncthreads();
     if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------------
+// 3x3 'same' layers, row-stationary form.  The kernel above issues one MMA per tap and K step (9 + 1 for the bias), and its single
+// issuing thread - ~45 cycles per tcgen05.mma whatever its size - is what bounds it.  Here a B-side (X) row rho meets ALL THREE
+// vertical taps at once: the A operand spans the dZ rows rho - d, rho, rho + d, which lie next to each other in shared memory (a
+// strip's dZ rows are all resident, stored residue class by residue class mod d), i.e. the TMEM lanes are (j, co) with j = 0, 1, 2
+// <-> ky = 2, 1, 0; the horizontal taps are the N groups of the same MMA (one B-side channel group: column kx * 8 + ci) or three
+// MMAs (more groups: columns kx * NK + ci).  1 or 3 MMAs per K step instead of 4 or 10; the bias gradient is summed from the
+// resident dZ rows by the two otherwise idle warps.  Partials: per CTA (3 CGO 8 lanes) x NCOL columns + CGO 8 bias sums.
+// ------------------------------------------------------------------------------------------------------------------------------------
+constexpr int kWg3MaxRows = 112;       // dZ rows a strip may hold (its own + 2 d halo rows): one mbarrier each
+
+struct Wgrad3Params {
+    float* partial;
+    int B, T, H;
+    int d;
+    int rows_per_strip;
+    int xring;
+    int per_cta;                       // floats of one CTA's partial block
+};
+
+template <int CGO, int CGI>
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
+                                                               const Wgrad3Params p) {
+    constexpr int NK = CGI == 1 ? 32 : (CGI == 2 ? 16 : 32);          // N of one MMA
+    constexpr int NMMA = CGI == 1 ? 1 : 3;                             // MMAs per K step
+    constexpr int NCOL = NK * NMMA;                                    // accumulator columns
+    constexpr uint32_t ncols = NCOL <= 32 ? 32 : (NCOL <= 64 ? 64 : 128);
+    constexpr int MREAL = 3 * CGO * 8;                                 // lanes (j, co)
+    constexpr uint32_t z_slot = (uint32_t)CGO * kStripTileT * 16u;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int d = p.d;
+    const int TW = kStripTileT + 2 * d;
+    const uint32_t x_plane = (uint32_t)TW * 16u;
+    const uint32_t x_slot = ((uint32_t)CGI * x_plane + 127u) & ~127u;
+    const int xring = p.xring;
+    uint64_t* z_full = reinterpret_cast<uint64_t*>(smem);             // [kWg3MaxRows]
+    uint64_t* x_full = z_full + kWg3MaxRows;                           // [xring <= 8]
+    uint64_t* x_empty = x_full + 8;
+    uint64_t* done = x_empty + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    float* sBias = reinterpret_cast<float*>(smem + 1280);              // [2 warps][CGO * 8]
+    uint8_t* sX = smem + 2048;
+    uint8_t* sZ = sX + (size_t)xring * x_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * kStripTileT;
+    const int h0 = blockIdx.y * p.rows_per_strip, h1 = min(p.H, h0 + p.rows_per_strip);
+    const int b = blockIdx.z;
+    const int n_rows = h1 - h0;                                        // X rows of the strip
+    const int nz = n_rows + 2 * d;                                     // dZ rows h0 - d .. h1 + d - 1 (out-of-image rows arrive as zeros)
+    const int sd = (nz + d - 1) / d;                                   // positions per residue class
+    auto zpos = [&](int i) { return (i % d) * sd + i / d; };           // i = dZ row - (h0 - d)
+
+    if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
+    if (tid == 32) {
+        for (int i = 0; i < nz; ++i) umma::mbar_init(&z_full[i], 1);
+        for (int i = 0; i < xring; ++i) { umma::mbar_init(&x_full[i], 1); umma::mbar_init(&x_empty[i], 1); }
+        umma::mbar_init(done, 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ================= producer: dZ rows in the order the X rows need them, X rows through a small ring =================
+        auto load_z = [&](int i) {
+            mbar_expect_tx(&z_full[i], z_slot);
+            tma_load_5d(sZ + (size_t)zpos(i) * z_slot, &tmap_z, &z_full[i], 0, t0, h0 - d + i, 0, b);
+        };
+        for (int i = 0; i < min(nz, 2 * d + 1); ++i) load_z(i);
+        for (int r = 0; r < n_rows; ++r) {
+            const int slot = r % xring;
+            if (r >= xring) umma::mbar_wait(&x_empty[slot], (uint32_t)((r / xring - 1) & 1));
+            mbar_expect_tx(&x_full[slot], (uint32_t)CGI * x_plane);
+            tma_load_5d(sX + (size_t)slot * x_slot, &tmap_x, &x_full[slot], 0, t0 - d, h0 + r, 0, b);
+            if (r + 2 * d + 1 < nz) load_z(r + 2 * d + 1);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = umma::make_idesc_bf16(128, NK) | (1u << 15) | (1u << 16);       // both operands MN-major
+        constexpr uint32_t lbo_field = (128u >> 4) << 16;
+        const uint32_t hi_a = ((uint32_t)(kStripTileT * 16) >> 4) | (1u << 14);
+        const uint32_t hi_b = ((CGI == 1 ? (uint32_t)d * 16u : x_plane) >> 4) | (1u << 14);
+        const uint32_t z0 = umma::smem_u32(sZ), x0 = umma::smem_u32(sX);
+        auto d64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+        for (int r = 0; r < n_rows; ++r) {
+            // dZ rows r, r + d, r + 2 d (relative to h0 - d): the first two were awaited with earlier X rows once r >= d
+            if (r < d) {
+                umma::mbar_wait(&z_full[r], 0);
+                umma::mbar_wait(&z_full[r + d], 0);
+            }
+            umma::mbar_wait(&z_full[r + 2 * d], 0);
+            umma::mbar_wait(&x_full[r % xring], (uint32_t)((r / xring) & 1));
+            umma::fence_after_sync();
+            const uint32_t lo_a = (((z0 + (uint32_t)zpos(r) * z_slot) >> 4) & 0x3FFFu) | lbo_field;
+            const uint32_t lo_b = (((x0 + (uint32_t)(r % xring) * x_slot) >> 4) & 0x3FFFu) | lbo_field;
+#pragma unroll
+            for (int s = 0; s < kStripTileT / 16; ++s) {
+                const bool acc = !(r == 0 && s == 0);
+                const uint64_t da = d64(hi_a, lo_a + (uint32_t)s * 16u);
+#pragma unroll
+                for (int kx = 0; kx < NMMA; ++kx)
+                    umma::mma_bf16(tmem + (uint32_t)(kx * NK), da, d64(hi_b, lo_b + (uint32_t)(kx * d) + (uint32_t)s * 16u), idesc, acc);
+            }
+            umma::commit(&x_empty[r % xring]);
+        }
+        umma::commit(done);
+    } else if (warp >= 2) {
+        // ================= bias gradient: pixel sums of the strip's OWN dZ rows, from shared memory =================
+        float acc[CGO * 8];
+#pragma unroll
+        for (int k = 0; k < CGO * 8; ++k) acc[k] = 0.f;
+        for (int r = warp - 2; r < n_rows; r += 2) {
+            const int i = r + d;                                        // dZ row h0 + r
+            umma::mbar_wait(&z_full[i], 0);
+            const uint8_t* row = sZ + (size_t)zpos(i) * z_slot;
+#pragma unroll
+            for (int q = 0; q < kStripTileT / 32; ++q) {
+#pragma unroll
+                for (int cg = 0; cg < CGO; ++cg) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(row + ((size_t)cg * kStripTileT + q * 32 + lane) * 16u);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(h[e]);
+                        acc[cg * 8 + 2 * e] += f.x;
+                        acc[cg * 8 + 2 * e + 1] += f.y;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CGO * 8; ++k) {
+            float v = acc[k];
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if (lane == 0) sBias[(warp - 2) * CGO * 8 + k] = v;
+        }
+    }
+    __syncthreads();
+    // ================= epilogue: accumulators and bias sums -> the CTA's partial block =================
+    const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    float* dst = p.partial + cta * (size_t)p.per_cta;
+    if (tid < CGO * 8) dst[(size_t)MREAL * NCOL + tid] = sBias[tid] + sBias[CGO * 8 + tid];
+    if (warp * 32 < MREAL) {
+        umma::mbar_wait_warp(done, 0);
+        umma::fence_after_sync();
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const int m = warp * 32 + lane;
+#pragma unroll
+        for (int c0 = 0; c0 < NCOL; c0 += 16) {
+            float v[16];
+            umma::tmem_ld16(lane_addr + (uint32_t)c0, v);
+            umma::tmem_ld_wait();
+            if (m < MREAL) {
+                float4* o = reinterpret_cast<float4*>(dst + (size_t)m * NCOL + c0);
+                o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                o[2] = make_float4(v[8], v[9], v[10], v[11]);
+                o[3] = make_float4(v[12], v[13], v[14], v[15]);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+// dw (co, ci, 3, 3) and db (co) += fixed-order sums over the CTAs' partial blocks of wgrad3_kernel: one warp per output element
+__global__ void __launch_bounds__(256) wgrad3_reduce_kernel(const float* __restrict__ partial, int n_ctas, int per_cta, int cgo, int ncol, int nk,
+                                                            int kx_in_n, int m_real, int n_real, float* __restrict__ dw, float* __restrict__ db) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // over (tap in [0, 9], co, ci); tap 9 = bias
+    const int lane = threadIdx.x & 31;
+    const int total = 10 * m_real * n_real;
+    if (i >= total) return;
+    const int tap = i / (m_real * n_real), rem = i - tap * m_real * n_real;
+    const int o = rem / n_real, c = rem - o * n_real;
+    if (tap == 9 && (c != 0 || db == nullptr)) return;
+    size_t off;
+    if (tap == 9) {
+        off = (size_t)3 * cgo * 8 * ncol + o;
+    } else {
+        const int ky = tap / 3, kx = tap - 3 * ky;
+        const int m = (2 - ky) * cgo * 8 + o;
+        const int col = kx_in_n ? kx * 8 + c : kx * nk + c;
+        off = (size_t)m * ncol + col;
+    }
+    float acc = 0.f;
+    for (int k = lane; k < n_ctas; k += 32) acc += partial[(size_t)k * per_cta + off];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
+    if (lane == 0) {
+        if (tap == 9) db[o] += acc;
+        else dw[((size_t)o * n_real + c) * 9 + tap] += acc;
+    }
 }
 
 // dW (m, n, taps) and db (m) += fixed-order sums of the per-CTA partials (m = A-side channel, n = B-side channel: (co, ci, kh, kw) for a
@@ -420,6 +621,32 @@ static long long wgrad_strips(int B, int Hz, int T) {
     return std::max<long long>(1, std::min<long long>((6 * 148 + tiles - 1) / tiles, std::max(1, Hz / 8)));
 }
 
+// ---- row-stationary 3x3: strip geometry (shared by the launch and the scratch bound) ----
+struct Wg3Plan {
+    int rows, strips, xring, per_cta;
+    size_t smem;
+};
+
+static Wg3Plan wg3_plan(int B, int CGi, int CGo, int H, int T, int d) {
+    Wg3Plan g;
+    const size_t z_slot = (size_t)CGo * kStripTileT * 16, x_slot = ((size_t)CGi * (kStripTileT + 2 * d) * 16 + 127) & ~(size_t)127;
+    g.xring = 4;
+    // everything a strip touches of dZ stays resident: rows + 2 d slots, and the A operand reads 32 KB from its first slot
+    const size_t budget = 226 * 1024 - 2048 - g.xring * x_slot - 32 * 1024;
+    int max_rows = (int)std::min<size_t>(budget / z_slot, (size_t)kWg3MaxRows) - (3 * d - 1);      // the residue-class layout rounds the row count up to a multiple of d
+    max_rows = std::max(max_rows, 1);
+    const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
+    // at least ~4 CTAs per SM in total (one is resident at a time), never more rows than shared memory holds
+    long long strips = std::max<long long>((H + max_rows - 1) / max_rows, std::min<long long>((4 * 148 + tiles - 1) / tiles, std::max(1, H / 4)));
+    g.rows = (int)((H + strips - 1) / strips);
+    g.strips = (H + g.rows - 1) / g.rows;
+    const int nk = CGi == 1 ? 32 : (CGi == 2 ? 16 : 32), ncol = nk * (CGi == 1 ? 1 : 3);
+    g.per_cta = 3 * CGo * 8 * ncol + CGo * 8;
+    const size_t nzpos = (size_t)d * ((g.rows + 2 * d + d - 1) / d);
+    g.smem = 2048 + g.xring * x_slot + std::max(nzpos * z_slot, (nzpos - 3) * z_slot + 32 * 1024) + 1024;
+    return g;
+}
+
 }  // namespace tt
 
 using namespace tt;
@@ -427,7 +654,15 @@ using namespace tt;
 extern "C" int64_t tt_wgrad_scratch_floats(int B, int H, int T) {
     // upper bound over the strip splits the weight-gradient entry points choose (H = rows of the A-side tensor)
     const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
-    return tiles * (wgrad_strips(B, H, T) + 1) * kWgMaxTaps * kWgMaxM * 32;
+    long long need = tiles * (wgrad_strips(B, H, T) + 1) * kWgMaxTaps * kWgMaxM * 32;
+    // the row-stationary 3x3 kernel: its strips are bounded by shared memory, its partial blocks are smaller
+    for (int cgi = 1; cgi <= 4; cgi *= 2)
+        for (int cgo = 1; cgo <= 4; cgo *= 2)
+            for (int d = 1; d <= 3; ++d) {
+                const Wg3Plan g = wg3_plan(B, cgi, cgo, H, T, d);
+                need = std::max(need, tiles * g.strips * (long long)g.per_cta);
+            }
+    return need;
 }
 
 // common launch: A side `a` (channels Ca, rows Ha), B side `bsrc` (channels Cb, rows Hb)
@@ -471,6 +706,43 @@ static int wgrad_any(const void* bsrc, const void* a, float* dw, float* db, int 
     return TT_OK;
 }
 
+template <int CGO, int CGI>
+static int launch_wgrad3(const void* x, const void* dz, float* dw, float* db, int B, int cin_real, int cout_real, int H, int T, int d,
+                         float* scratch, cudaStream_t stream) {
+    const Wg3Plan g = wg3_plan(B, CGI, CGO, H, T, d);
+    TT_REQUIRE(g.smem <= 227 * 1024 && g.rows + 2 * d <= kWg3MaxRows, "wgrad3: %zu bytes of shared memory, %d rows", g.smem, g.rows);
+    static size_t configured = 0;
+    if (g.smem > configured) {
+        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad3_kernel<CGO, CGI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        configured = g.smem;
+    }
+    CUtensorMap mx, mz;
+    int rc = make_row_map(&mx, x, B, CGI, H, T, kStripTileT + 2 * d);
+    if (rc) return rc;
+    rc = make_row_map(&mz, dz, B, CGO, H, T, kStripTileT);
+    if (rc) return rc;
+    Wgrad3Params p;
+    p.partial = scratch; p.B = B; p.T = T; p.H = H; p.d = d; p.rows_per_strip = g.rows; p.xring = g.xring; p.per_cta = g.per_cta;
+    dim3 grid((T + kStripTileT - 1) / kStripTileT, g.strips, B);
+    wgrad3_kernel<CGO, CGI><<<grid, kWgThreads, g.smem, stream>>>(mx, mz, p);
+    TT_CUDA_CHECK(cudaGetLastError());
+    const int n_ctas = (int)(grid.x * grid.y * grid.z);
+    constexpr int NK = CGI == 1 ? 32 : (CGI == 2 ? 16 : 32), NCOL = NK * (CGI == 1 ? 1 : 3);
+    const int total = 10 * cout_real * cin_real;
+    wgrad3_reduce_kernel<<<(total + 7) / 8, 256, 0, stream>>>(scratch, n_ctas, g.per_cta, CGO, NCOL, NK, CGI == 1, cout_real, cin_real, dw, db);
+    tt_count_launches(2);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
+static int wgrad3_dispatch(const void* x, const void* dz, float* dw, float* db, int B, int Cin, int Cout, int cin_real, int cout_real, int H, int T,
+                           int d, float* scratch, cudaStream_t stream) {
+#define TT_WG3(CO, CI) if (Cout == CO * 8 && Cin == CI * 8) return launch_wgrad3<CO, CI>(x, dz, dw, db, B, cin_real, cout_real, H, T, d, scratch, stream);
+    TT_WG3(1, 1) TT_WG3(2, 2) TT_WG3(4, 4) TT_WG3(1, 2) TT_WG3(2, 1) TT_WG3(2, 4) TT_WG3(4, 2) TT_WG3(1, 4) TT_WG3(4, 1)
+#undef TT_WG3
+    return TT_ERR_UNSUPPORTED;
+}
+
 extern "C" int tt_conv_wgrad_same(const void* x, const void* dz, float* dw, float* db, int B, int Cin, int Cout, int cin_real, int cout_real,
                                   int H, int T, int k, int dilation, float* scratch, void* stream_) {
     TT_REQUIRE(x && dz && dw && scratch, "null argument");
@@ -479,7 +751,11 @@ extern "C" int tt_conv_wgrad_same(const void* x, const void* dz, float* dw, floa
     TT_REQUIRE((k == 3 && dilation >= 1 && dilation <= 3) || k == 1, "wgrad: 3x3 (dilation 1..3) or 1x1");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    if (k == 3) return wgrad_any<3, 3, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, dilation, scratch, stream);
+    if (k == 3) {
+        static const bool legacy = getenv("TT_WGRAD_LEGACY") != nullptr;       // A/B switch: the one-MMA-per-tap kernel
+        if (!legacy) return wgrad3_dispatch(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, T, dilation, scratch, stream);
+        return wgrad_any<3, 3, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, dilation, scratch, stream);
+    }
     return wgrad_any<1, 1, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, 1, scratch, stream);
 }
 
