@@ -54,6 +54,8 @@ template <int NPAD, int KH, int KW, int RS, int MW, bool KXN = false>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
                                                               const WgradParams p) {
     static_assert(!KXN || (KH == 3 && KW == 3 && NPAD == 32), "KXN is the 3x3 single-group form");
+    // 1x1 layers: the "ones" MMA would be every second MMA; instead warps 2-3 (idle otherwise) sum the A-side rows from shared memory
+    constexpr bool BIASW = KH == 1 && KW == 1 && RS == 1;
     constexpr int TAPS = KXN ? KH : KH * KW;
     constexpr uint32_t need = (TAPS + 1) * NPAD;
     constexpr uint32_t ncols = need <= 32 ? 32 : (need <= 64 ? 64 : (need <= 128 ? 128 : (need <= 256 ? 256 : 512)));
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
     if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
     if (tid == 32) {
-        for (int i = 0; i < kWgZSlots; ++i) { umma::mbar_init(&z_full[i], 1); umma::mbar_init(&z_empty[i], 1); }
+        for (int i = 0; i < kWgZSlots; ++i) { umma::mbar_init(&z_full[i], 1); umma::mbar_init(&z_empty[i], BIASW ? 2 : 1); }
         for (int i = 0; i < xring; ++i) { umma::mbar_init(&x_full[i], 1); umma::mbar_init(&x_empty[i], 1); }
         umma::mbar_init(done, 1);
         umma::mbar_fence_init();
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                             umma::mma_bf16(tmem + (uint32_t)((ky * KW + kx) * NPAD), da, d64(hi_b, lo_b[ky] + (uint32_t)(kx * d) + (uint32_t)s * 16u), idesc, acc);
                     }
                 }
-                umma::mma_bf16(tmem + (uint32_t)(TAPS * NPAD), da, d64(hi_a, lo_ones + (uint32_t)s * 16u), idesc, acc);
+                if constexpr (!BIASW) umma::mma_bf16(tmem + (uint32_t)(TAPS * NPAD), da, d64(hi_a, lo_ones + (uint32_t)s * 16u), idesc, acc);
             }
             first = false;
             umma::commit(&z_empty[zs]);
@@ -167,7 +169,44 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             for (int k = 0; k < RS; ++k) umma::commit(&x_empty[(r * RS + k) % xring]);
         }
         umma::commit(done);
+    } else if (BIASW && warp >= 2) {
+        // ================= bias gradient of the 1x1 layers: pixel sums of the A-side rows, from the ring =================
+        float bsum[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) bsum[k] = 0.f;
+        for (int r = warp - 2; r < n_rows; r += 2) {
+            const int zs = r % zslots;
+            umma::mbar_wait(&z_full[zs], (uint32_t)((r / zslots) & 1));
+            const uint8_t* row = sZ + (size_t)zs * z_slot;
+#pragma unroll
+            for (int cg = 0; cg < 4; ++cg) {
+                if (cg < p.CGo) {
+#pragma unroll
+                    for (int q = 0; q < kStripTileT / 32; ++q) {
+                        const uint4 v = *reinterpret_cast<const uint4*>(row + ((size_t)cg * kStripTileT + q * 32 + lane) * 16u);
+                        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 f = __bfloat1622float2(h[e]);
+                            bsum[cg * 8 + 2 * e] += f.x;
+                            bsum[cg * 8 + 2 * e + 1] += f.y;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&z_empty[zs]);
+        }
+        float* sB = reinterpret_cast<float*>(smem + 640);               // [2 warps][32]
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+            float v = bsum[k];
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+            if (lane == 0) sB[(warp - 2) * 32 + k] = v;
+        }
     }
+    if constexpr (BIASW) __syncthreads();
     __syncwarp();
     // ================= epilogue: accumulators -> partial buffer (TMEM lane = A-side channel; NPAD columns per tap) =================
     if (warp < MW) {
@@ -177,8 +216,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
         float* dst = p.partial + (cta * kWgMaxTaps * MROWS + warp * 32 + lane) * NPAD;
         const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        if constexpr (BIASW) {
+            // the reduction reads the bias of channel o at [TAPS][o][0]
+            const float* sB = reinterpret_cast<const float*>(smem + 640);
+            const int o = warp * 32 + lane;
+            if (o < 32) dst[(size_t)TAPS * MROWS * NPAD] = sB[o] + sB[32 + o];       // dst already points at this thread's channel row
+        }
 #pragma unroll 1
-        for (int tap = 0; tap <= TAPS; ++tap) {
+        for (int tap = 0; tap < TAPS + (BIASW ? 0 : 1); ++tap) {
 #pragma unroll
             for (int c0 = 0; c0 < NPAD; c0 += 16) {
                 float v[16];
@@ -217,18 +262,22 @@ struct Wgrad3Params {
     int per_cta;                       // floats of one CTA's partial block
 };
 
-template <int CGO, int CGI>
+// KH = 1: the 1x1 layers through the same kernel - one dZ row per X row, no taps: one MMA per K step (the kernel above: two, the
+// second one for the bias), N = the B-side channel groups.
+template <int CGO, int CGI, int KH>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
                                                                const Wgrad3Params p) {
-    constexpr int NK = CGI == 1 ? 32 : (CGI == 2 ? 16 : 32);          // N of one MMA
-    constexpr int NMMA = CGI == 1 ? 1 : 3;                             // MMAs per K step
+    static_assert(KH == 3 || KH == 1, "3x3 or 1x1");
+    constexpr int NK = KH == 1 ? (CGI <= 2 ? 16 : 32) : (CGI == 1 ? 32 : (CGI == 2 ? 16 : 32));   // N of one MMA
+    constexpr int NMMA = KH == 1 ? 1 : (CGI == 1 ? 1 : 3);             // MMAs per K step
     constexpr int NCOL = NK * NMMA;                                    // accumulator columns
     constexpr uint32_t ncols = NCOL <= 32 ? 32 : (NCOL <= 64 ? 64 : 128);
-    constexpr int MREAL = 3 * CGO * 8;                                 // lanes (j, co)
+    constexpr int MREAL = KH * CGO * 8;                                // lanes (j, co)
     constexpr uint32_t z_slot = (uint32_t)CGO * kStripTileT * 16u;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int d = p.d;
-    const int TW = kStripTileT + 2 * d;
+    const int d = KH == 3 ? p.d : 1;                                   // row distance of the vertical taps (1x1: residue layout degenerates)
+    const int hz = KH == 3 ? d : 0;                                    // dZ halo rows on either side / column halo of the X rows
+    const int TW = kStripTileT + 2 * hz;
     const uint32_t x_plane = (uint32_t)TW * 16u;
     const uint32_t x_slot = ((uint32_t)CGI * x_plane + 127u) & ~127u;
     const int xring = p.xring;
@@ -246,7 +295,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_cons
     const int h0 = blockIdx.y * p.rows_per_strip, h1 = min(p.H, h0 + p.rows_per_strip);
     const int b = blockIdx.z;
     const int n_rows = h1 - h0;                                        // X rows of the strip
-    const int nz = n_rows + 2 * d;                                     // dZ rows h0 - d .. h1 + d - 1 (out-of-image rows arrive as zeros)
+    const int nz = n_rows + 2 * hz;                                    // dZ rows h0 - d .. h1 + d - 1 (out-of-image rows arrive as zeros)
     const int sd = (nz + d - 1) / d;                                   // positions per residue class
     auto zpos = [&](int i) { return (i % d) * sd + i / d; };           // i = dZ row - (h0 - d)
 
@@ -266,31 +315,31 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_cons
         // ================= producer: dZ rows in the order the X rows need them, X rows through a small ring =================
         auto load_z = [&](int i) {
             mbar_expect_tx(&z_full[i], z_slot);
-            tma_load_5d(sZ + (size_t)zpos(i) * z_slot, &tmap_z, &z_full[i], 0, t0, h0 - d + i, 0, b);
+            tma_load_5d(sZ + (size_t)zpos(i) * z_slot, &tmap_z, &z_full[i], 0, t0, h0 - hz + i, 0, b);
         };
-        for (int i = 0; i < min(nz, 2 * d + 1); ++i) load_z(i);
+        for (int i = 0; i < min(nz, 2 * hz + 1); ++i) load_z(i);
         for (int r = 0; r < n_rows; ++r) {
             const int slot = r % xring;
             if (r >= xring) umma::mbar_wait(&x_empty[slot], (uint32_t)((r / xring - 1) & 1));
             mbar_expect_tx(&x_full[slot], (uint32_t)CGI * x_plane);
-            tma_load_5d(sX + (size_t)slot * x_slot, &tmap_x, &x_full[slot], 0, t0 - d, h0 + r, 0, b);
-            if (r + 2 * d + 1 < nz) load_z(r + 2 * d + 1);
+            tma_load_5d(sX + (size_t)slot * x_slot, &tmap_x, &x_full[slot], 0, t0 - hz, h0 + r, 0, b);
+            if (r + 2 * hz + 1 < nz) load_z(r + 2 * hz + 1);
         }
     } else if (warp == 1 && lane == 0) {
         // ================= MMA issuer =================
         constexpr uint32_t idesc = umma::make_idesc_bf16(128, NK) | (1u << 15) | (1u << 16);       // both operands MN-major
         constexpr uint32_t lbo_field = (128u >> 4) << 16;
         const uint32_t hi_a = ((uint32_t)(kStripTileT * 16) >> 4) | (1u << 14);
-        const uint32_t hi_b = ((CGI == 1 ? (uint32_t)d * 16u : x_plane) >> 4) | (1u << 14);
+        const uint32_t hi_b = (((KH == 3 && CGI == 1) ? (uint32_t)d * 16u : x_plane) >> 4) | (1u << 14);
         const uint32_t z0 = umma::smem_u32(sZ), x0 = umma::smem_u32(sX);
         auto d64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
         for (int r = 0; r < n_rows; ++r) {
             // dZ rows r, r + d, r + 2 d (relative to h0 - d): the first two were awaited with earlier X rows once r >= d
-            if (r < d) {
+            if (KH == 3 && r < d) {
                 umma::mbar_wait(&z_full[r], 0);
                 umma::mbar_wait(&z_full[r + d], 0);
             }
-            umma::mbar_wait(&z_full[r + 2 * d], 0);
+            umma::mbar_wait(&z_full[r + 2 * hz], 0);
             umma::mbar_wait(&x_full[r % xring], (uint32_t)((r / xring) & 1));
             umma::fence_after_sync();
             const uint32_t lo_a = (((z0 + (uint32_t)zpos(r) * z_slot) >> 4) & 0x3FFFu) | lbo_field;
@@ -312,7 +361,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_cons
 #pragma unroll
         for (int k = 0; k < CGO * 8; ++k) acc[k] = 0.f;
         for (int r = warp - 2; r < n_rows; r += 2) {
-            const int i = r + d;                                        // dZ row h0 + r
+            const int i = r + hz;                                       // dZ row h0 + r
             umma::mbar_wait(&z_full[i], 0);
             const uint8_t* row = sZ + (size_t)zpos(i) * z_slot;
 #pragma unroll
@@ -369,20 +418,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_cons
 
 // dw (co, ci, 3, 3) and db (co) += fixed-order sums over the CTAs' partial blocks of wgrad3_kernel: one warp per output element
 __global__ void __launch_bounds__(256) wgrad3_reduce_kernel(const float* __restrict__ partial, int n_ctas, int per_cta, int cgo, int ncol, int nk,
-                                                            int kx_in_n, int m_real, int n_real, float* __restrict__ dw, float* __restrict__ db) {
-    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // over (tap in [0, 9], co, ci); tap 9 = bias
+                                                            int kx_in_n, int kh, int m_real, int n_real, float* __restrict__ dw, float* __restrict__ db) {
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // over (tap in [0, taps], co, ci); tap == taps: bias
     const int lane = threadIdx.x & 31;
-    const int total = 10 * m_real * n_real;
+    const int taps = kh * kh;
+    const int total = (taps + 1) * m_real * n_real;
     if (i >= total) return;
     const int tap = i / (m_real * n_real), rem = i - tap * m_real * n_real;
     const int o = rem / n_real, c = rem - o * n_real;
-    if (tap == 9 && (c != 0 || db == nullptr)) return;
+    if (tap == taps && (c != 0 || db == nullptr)) return;
     size_t off;
-    if (tap == 9) {
-        off = (size_t)3 * cgo * 8 * ncol + o;
+    if (tap == taps) {
+        off = (size_t)kh * cgo * 8 * ncol + o;
     } else {
-        const int ky = tap / 3, kx = tap - 3 * ky;
-        const int m = (2 - ky) * cgo * 8 + o;
+        const int ky = tap / kh, kx = tap - kh * ky;
+        const int m = (kh - 1 - ky) * cgo * 8 + o;
         const int col = kx_in_n ? kx * 8 + c : kx * nk + c;
         off = (size_t)m * ncol + col;
     }
@@ -391,8 +441,8 @@ __global__ void __launch_bounds__(256) wgrad3_reduce_kernel(const float* __restr
 #pragma unroll
     for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, s);
     if (lane == 0) {
-        if (tap == 9) db[o] += acc;
-        else dw[((size_t)o * n_real + c) * 9 + tap] += acc;
+        if (tap == taps) db[o] += acc;
+        else dw[((size_t)o * n_real + c) * taps + tap] += acc;
     }
 }
 
@@ -627,23 +677,24 @@ struct Wg3Plan {
     size_t smem;
 };
 
-static Wg3Plan wg3_plan(int B, int CGi, int CGo, int H, int T, int d) {
+static Wg3Plan wg3_plan(int B, int CGi, int CGo, int H, int T, int d, int kh = 3) {
     Wg3Plan g;
+    if (kh == 1) d = 0;
     const size_t z_slot = (size_t)CGo * kStripTileT * 16, x_slot = ((size_t)CGi * (kStripTileT + 2 * d) * 16 + 127) & ~(size_t)127;
     g.xring = 4;
     // everything a strip touches of dZ stays resident: rows + 2 d slots, and the A operand reads 32 KB from its first slot
     const size_t budget = 226 * 1024 - 2048 - g.xring * x_slot - 32 * 1024;
-    int max_rows = (int)std::min<size_t>(budget / z_slot, (size_t)kWg3MaxRows) - (3 * d - 1);      // the residue-class layout rounds the row count up to a multiple of d
+    int max_rows = (int)std::min<size_t>(budget / z_slot, (size_t)kWg3MaxRows) - (kh == 1 ? 0 : 3 * d - 1);   // the residue-class layout rounds the row count up to a multiple of d
     max_rows = std::max(max_rows, 1);
     const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
     // at least ~4 CTAs per SM in total (one is resident at a time), never more rows than shared memory holds
     long long strips = std::max<long long>((H + max_rows - 1) / max_rows, std::min<long long>((4 * 148 + tiles - 1) / tiles, std::max(1, H / 4)));
     g.rows = (int)((H + strips - 1) / strips);
     g.strips = (H + g.rows - 1) / g.rows;
-    const int nk = CGi == 1 ? 32 : (CGi == 2 ? 16 : 32), ncol = nk * (CGi == 1 ? 1 : 3);
-    g.per_cta = 3 * CGo * 8 * ncol + CGo * 8;
-    const size_t nzpos = (size_t)d * ((g.rows + 2 * d + d - 1) / d);
-    g.smem = 2048 + g.xring * x_slot + std::max(nzpos * z_slot, (nzpos - 3) * z_slot + 32 * 1024) + 1024;
+    const int nk = kh == 1 ? (CGi <= 2 ? 16 : 32) : (CGi == 1 ? 32 : (CGi == 2 ? 16 : 32)), ncol = nk * ((kh == 1 || CGi == 1) ? 1 : 3);
+    g.per_cta = kh * CGo * 8 * ncol + CGo * 8;
+    const size_t nzpos = kh == 1 ? (size_t)g.rows : (size_t)d * ((g.rows + 2 * d + d - 1) / d);
+    g.smem = 2048 + g.xring * x_slot + std::max(nzpos * z_slot, (nzpos - std::min<size_t>(nzpos, kh)) * z_slot + 32 * 1024) + 1024;
     return g;
 }
 
@@ -659,8 +710,8 @@ extern "C" int64_t tt_wgrad_scratch_floats(int B, int H, int T) {
     for (int cgi = 1; cgi <= 4; cgi *= 2)
         for (int cgo = 1; cgo <= 4; cgo *= 2)
             for (int d = 1; d <= 3; ++d) {
-                const Wg3Plan g = wg3_plan(B, cgi, cgo, H, T, d);
-                need = std::max(need, tiles * g.strips * (long long)g.per_cta);
+                const Wg3Plan g = wg3_plan(B, cgi, cgo, H, T, d), g1 = wg3_plan(B, cgi, cgo, H, T, 1, 1);
+                need = std::max(need, std::max(tiles * g.strips * (long long)g.per_cta, tiles * g1.strips * (long long)g1.per_cta));
             }
     return need;
 }
@@ -706,14 +757,15 @@ static int wgrad_any(const void* bsrc, const void* a, float* dw, float* db, int 
     return TT_OK;
 }
 
-template <int CGO, int CGI>
+template <int CGO, int CGI, int KH>
 static int launch_wgrad3(const void* x, const void* dz, float* dw, float* db, int B, int cin_real, int cout_real, int H, int T, int d,
                          float* scratch, cudaStream_t stream) {
-    const Wg3Plan g = wg3_plan(B, CGI, CGO, H, T, d);
+    if (KH == 1) d = 0;
+    const Wg3Plan g = wg3_plan(B, CGI, CGO, H, T, d, KH);
     TT_REQUIRE(g.smem <= 227 * 1024 && g.rows + 2 * d <= kWg3MaxRows, "wgrad3: %zu bytes of shared memory, %d rows", g.smem, g.rows);
     static size_t configured = 0;
     if (g.smem > configured) {
-        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad3_kernel<CGO, CGI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad3_kernel<CGO, CGI, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
         configured = g.smem;
     }
     CUtensorMap mx, mz;
@@ -724,20 +776,21 @@ static int launch_wgrad3(const void* x, const void* dz, float* dw, float* db, in
     Wgrad3Params p;
     p.partial = scratch; p.B = B; p.T = T; p.H = H; p.d = d; p.rows_per_strip = g.rows; p.xring = g.xring; p.per_cta = g.per_cta;
     dim3 grid((T + kStripTileT - 1) / kStripTileT, g.strips, B);
-    wgrad3_kernel<CGO, CGI><<<grid, kWgThreads, g.smem, stream>>>(mx, mz, p);
+    wgrad3_kernel<CGO, CGI, KH><<<grid, kWgThreads, g.smem, stream>>>(mx, mz, p);
     TT_CUDA_CHECK(cudaGetLastError());
     const int n_ctas = (int)(grid.x * grid.y * grid.z);
-    constexpr int NK = CGI == 1 ? 32 : (CGI == 2 ? 16 : 32), NCOL = NK * (CGI == 1 ? 1 : 3);
-    const int total = 10 * cout_real * cin_real;
-    wgrad3_reduce_kernel<<<(total + 7) / 8, 256, 0, stream>>>(scratch, n_ctas, g.per_cta, CGO, NCOL, NK, CGI == 1, cout_real, cin_real, dw, db);
+    constexpr int NK = KH == 1 ? (CGI <= 2 ? 16 : 32) : (CGI == 1 ? 32 : (CGI == 2 ? 16 : 32)), NCOL = NK * ((KH == 1 || CGI == 1) ? 1 : 3);
+    const int total = (KH * KH + 1) * cout_real * cin_real;
+    wgrad3_reduce_kernel<<<(total + 7) / 8, 256, 0, stream>>>(scratch, n_ctas, g.per_cta, CGO, NCOL, NK, KH == 3 && CGI == 1, KH, cout_real, cin_real, dw, db);
     tt_count_launches(2);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }
 
+template <int KH>
 static int wgrad3_dispatch(const void* x, const void* dz, float* dw, float* db, int B, int Cin, int Cout, int cin_real, int cout_real, int H, int T,
                            int d, float* scratch, cudaStream_t stream) {
-#define TT_WG3(CO, CI) if (Cout == CO * 8 && Cin == CI * 8) return launch_wgrad3<CO, CI>(x, dz, dw, db, B, cin_real, cout_real, H, T, d, scratch, stream);
+#define TT_WG3(CO, CI) if (Cout == CO * 8 && Cin == CI * 8) return launch_wgrad3<CO, CI, KH>(x, dz, dw, db, B, cin_real, cout_real, H, T, d, scratch, stream);
     TT_WG3(1, 1) TT_WG3(2, 2) TT_WG3(4, 4) TT_WG3(1, 2) TT_WG3(2, 1) TT_WG3(2, 4) TT_WG3(4, 2) TT_WG3(1, 4) TT_WG3(4, 1)
 #undef TT_WG3
     return TT_ERR_UNSUPPORTED;
@@ -753,9 +806,11 @@ extern "C" int tt_conv_wgrad_same(const void* x, const void* dz, float* dw, floa
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k == 3) {
         static const bool legacy = getenv("TT_WGRAD_LEGACY") != nullptr;       // A/B switch: the one-MMA-per-tap kernel
-        if (!legacy) return wgrad3_dispatch(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, T, dilation, scratch, stream);
+        if (!legacy) return wgrad3_dispatch<3>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, T, dilation, scratch, stream);
         return wgrad_any<3, 3, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, dilation, scratch, stream);
     }
+    // (the resident-strip kernel also runs 1x1 layers - wgrad3_dispatch<1> - but one CTA per SM hides less latency than the ring kernel's
+    // co-resident CTAs: measured equal; the ring kernel without its "ones" MMA is the faster one)
     return wgrad_any<1, 1, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, 1, scratch, stream);
 }
 
