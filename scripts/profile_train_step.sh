@@ -1,6 +1,6 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r02_train_launches5.csv python scripts/train_step_bench.py 8 1 > gpurun_out/r02_train_ncu5.log 2>&1; tail -1 gpurun_out/r02_train_ncu5.log; python - <<PY
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r02_train_launches6.csv python scripts/train_step_bench.py 8 1 > gpurun_out/r02_train_ncu6.log 2>&1; tail -1 gpurun_out/r02_train_ncu6.log; python - <<PY
 import csv, collections
-rows = list(csv.reader(open("gpurun_out/r02_train_launches5.csv")))
+rows = list(csv.reader(open("gpurun_out/r02_train_launches6.csv")))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
 H = rows[hdr]; ki = H.index("Kernel Name"); vi = H.index("Metric Value")
 agg = collections.OrderedDict()
