@@ -142,6 +142,10 @@ int tt_multipitch_counts(const unsigned char* est, const unsigned char* ref, int
  * w1 (KG1, 3 NC, 8), w2 (KG2, NC, 8) bf16 and bias (2, NC) fp32 with NC = accumulator columns per row (16, or 32 for C = 32). */
 int tt_res_block_rs(const void* x, void* y, const void* w1, const void* w2, const float* bias, int B, int C, int c_real,
                     int H, int T, int dilation, int layout, void* stream);
+/* The same launch, additionally writing the block's inner activation ELU(W1 * x + b1) to `mid` (layout and size of y; NULL = none):
+   the loss step keeps it for the backward pass (the 3x3 data / weight gradients need ELU'(z1)) instead of recomputing the conv. */
+int tt_res_block_rs_mid(const void* x, void* y, void* mid, const void* w1, const void* w2, const float* bias, int B, int C, int c_real,
+                        int H, int T, int dilation, int layout, void* stream);
 /* One 3x3 dilated 'same' conv (k = 3, weights packing.pack_res3x3) or 1x1 conv (k = 1, packing.pack_res1x1), optional ELU, on C8
  * planar tensors: building block of the backward pass (recompute + data gradients as convs with transformed weights) */
 int tt_conv_same(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,

@@ -226,3 +226,38 @@ def test_res_block_rs_folded(C, H, T, d, B, fold, strip_rows, force_strip_rows):
     pad = y[..., C:] if fold == 4 else y.float().permute(0, 1, 4, 2, 3).reshape(B, -1, H, T)[:, C:]
     if pad.numel():
         assert float(pad.float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('C,H,T,d,mode', [(4, 23, 256, 1, 'fold4'), (3, 17, 130, 2, 'pairs'), (8, 19, 256, 3, 'fold2'), (8, 9, 131, 1, 'planar'),
+                                          (16, 21, 200, 2, 'planar'), (32, 11, 128, 3, 'planar')])
+def test_res_block_inner_activation_output(C, H, T, d, mode):
+    """tt_res_block_rs_mid: the block's output is unchanged (bit for bit) and `mid` holds ELU(conv3x3(x) + b1) as the kernel stages it
+    for its 1x1 conv (bf16) - what the loss step keeps for its backward pass."""
+    import torch.nn.functional as F
+    from timbre_trap_b200.framework import ops, packing as P
+    g = torch.Generator().manual_seed(C * 10 + d)
+    x = torch.randn((2, C, H, T), generator=g)
+    w1, b1 = torch.randn((C, C, 3, 3), generator=g) * 0.2, torch.randn(C, generator=g) * 0.1
+    w2, b2 = torch.randn((C, C, 1, 1), generator=g) * 0.3, torch.randn(C, generator=g) * 0.1
+    packed = mode in ('fold4', 'pairs')
+    xin = (P.to_p4(x) if packed else P.to_c8(x)).cuda()
+    if mode == 'fold4':
+        pk = P.pack_res_rs_fold(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), d, 4)
+    elif mode == 'fold2':
+        pk = P.pack_res_rs_fold(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), d, 2)
+    elif mode == 'pairs':
+        pk = P.pack_res_rs_pairs(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda(), d)
+    else:
+        pk = P.pack_res_rs(w1.cuda(), b1.cuda(), w2.cuda(), b2.cuda())
+    fold = mode.startswith('fold')
+    y0 = ops.res_block_rs(xin, *pk, C, d, fold=fold)
+    mid = torch.full_like(xin, float('nan'))
+    y1 = ops.res_block_rs(xin, *pk, C, d, fold=fold, mid_out=mid)
+    assert torch.equal(y0, y1)
+    got = (P.from_p4(mid, C) if packed else P.from_c8(mid, C)).cpu()
+    xb = x.to(torch.bfloat16).float()
+    want = F.elu(F.conv2d(xb, w1.to(torch.bfloat16).float(), b1, padding=d, dilation=d))
+    assert torch.isfinite(got).all()
+    assert float((got - want).abs().max()) <= 2e-2 * max(1.0, float(want.abs().max()))
+    with pytest.raises(ValueError):
+        ops.res_block_rs(xin, *pk, C, d, fold=fold, mid_out=mid[:1])

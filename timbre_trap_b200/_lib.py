@@ -33,6 +33,7 @@ SIGNATURES = {
     'tt_magnitude': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     'tt_chunk_crossfade': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     'tt_res_block_rs': (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    'tt_res_block_rs_mid': (c_int, [c_void_p] * 6 + [c_int] * 7 + [c_void_p]),
     'tt_set_strip_rows': (c_int, [c_int]),
     'tt_conv_down_strip': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     'tt_conv_up_strip': (c_int, [c_void_p] * 3 + [c_int] * 8 + [c_void_p]),

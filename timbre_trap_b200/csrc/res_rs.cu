@@ -55,6 +55,7 @@ constexpr int kRsCmdSlots = 32;    // >= the deepest input-row ring: the scout c
 
 struct ResRsParams {
     __nv_bfloat16* y;
+    __nv_bfloat16* mid;        // optional (training): the inner activation ELU(W1 * x + b1), in the layout of y
     const __nv_bfloat16* w1;   // packed (KG1, 3 NC, 8), see packing.pack_res_rs
     const __nv_bfloat16* w2;   // packed (KG2, NC, 8)
     const float* bias;         // (2, NC): accumulator-column biases of the 3x3 and the 1x1 conv
@@ -142,7 +143,7 @@ __device__ __forceinline__ void tmem_store(uint32_t taddr, const float* v) {
 }
 __device__ __forceinline__ void tmem_store_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int CG, int NREAL, int D, int MODE>
+template <int CG, int NREAL, int D, int MODE, bool MID>
 __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(const __grid_constant__ CUtensorMap tmap_x, const ResRsParams p) {
     using S_ = RsPlan<CG, D, MODE>;
     constexpr int NC = S_::NC, N3 = S_::N3, SR = S_::SR, A2 = S_::A2;
@@ -414,6 +415,14 @@ __global__ void __launch_bounds__(kRsThreads, CG <= 2 ? 2 : 1) res_rs_kernel(con
                     if constexpr (NV >= 8) { o.z = pack2(v[k + 4], v[k + 5]); o.w = pack2(v[k + 6], v[k + 7]); }
                     else { o.z = 0u; o.w = 0u; }
                     *reinterpret_cast<uint4*>(mid + (size_t)((c0 + k) >> 3) * 2048u) = o;
+                    if constexpr (MID) if (t_ok) {
+                        // the loss step keeps the inner activation (its backward needs it) instead of recomputing the 3x3 conv
+                        uint4* gm = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.mid) +
+                                                             (reinterpret_cast<const uint8_t*>(y_thread) - reinterpret_cast<const uint8_t*>(p.y)));
+                        const int cg = (c0 + k) >> 3;
+                        if constexpr (S_::kFolded) gm[(size_t)it * (2 * p.T) + cg] = o;
+                        else gm[(size_t)cg * p.H * p.T + (size_t)it * p.T] = o;
+                    }
                     if constexpr (NV < 8) break;
                 }
             }
@@ -547,14 +556,17 @@ static int launch_rs(const void* x, ResRsParams p, cudaStream_t stream) {
     using S_ = RsPlan<CG, D, MODE>;
     static bool configured = false;
     if (!configured) {
-        TT_CUDA_CHECK(cudaFuncSetAttribute(res_rs_kernel<CG, NREAL, D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::kTotal));
+        TT_CUDA_CHECK(cudaFuncSetAttribute(res_rs_kernel<CG, NREAL, D, MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::kTotal));
+        TT_CUDA_CHECK(cudaFuncSetAttribute(res_rs_kernel<CG, NREAL, D, MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_::kTotal));
         configured = true;
     }
     CUtensorMap map;
     const int rc = S_::kFolded ? make_folded_row_map(&map, x, p.B, p.H, p.T, S_::TW) : make_row_map(&map, x, p.B, CG, p.H, p.T, S_::TW);
     if (rc) return rc;
     dim3 grid((p.T + kStripTileT - 1) / kStripTileT, (p.H + p.rows_per_strip - 1) / p.rows_per_strip, p.B);
-    res_rs_kernel<CG, NREAL, D, MODE><<<grid, kRsThreads, S_::kTotal, stream>>>(map, p);
+    // the variant that also writes the inner activation is a separate instantiation: the inference kernel keeps its register budget
+    if (p.mid != nullptr) res_rs_kernel<CG, NREAL, D, MODE, true><<<grid, kRsThreads, S_::kTotal, stream>>>(map, p);
+    else res_rs_kernel<CG, NREAL, D, MODE, false><<<grid, kRsThreads, S_::kTotal, stream>>>(map, p);
     TT_CUDA_CHECK(cudaGetLastError());
     tt_count_launches(1);
     return TT_OK;
@@ -582,6 +594,11 @@ extern "C" int tt_set_strip_rows(int rows) {
 
 extern "C" int tt_res_block_rs(const void* x, void* y, const void* w1, const void* w2, const float* bias, int B, int C, int c_real,
                                int H, int T, int dilation, int layout, void* stream) {
+    return tt_res_block_rs_mid(x, y, nullptr, w1, w2, bias, B, C, c_real, H, T, dilation, layout, stream);
+}
+
+extern "C" int tt_res_block_rs_mid(const void* x, void* y, void* mid, const void* w1, const void* w2, const float* bias, int B, int C, int c_real,
+                                   int H, int T, int dilation, int layout, void* stream) {
     TT_REQUIRE(x && y && w1 && w2 && bias, "null argument");
     TT_REQUIRE(C == 8 || C == 16 || C == 32, "res block: padded channel count must be 8, 16 or 32 (got %d)", C);
     TT_REQUIRE(layout == kRsPlanar || layout == kRsPairs8 || layout == kRsFold2 || layout == kRsFold4, "unknown layout mode %d", layout);
@@ -593,7 +610,7 @@ extern "C" int tt_res_block_rs(const void* x, void* y, const void* w1, const voi
     TT_REQUIRE(c_real >= 1 && c_real <= C, "bad real channel count");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
     ResRsParams p;
-    p.y = (__nv_bfloat16*)y; p.w1 = (const __nv_bfloat16*)w1; p.w2 = (const __nv_bfloat16*)w2; p.bias = bias;
+    p.y = (__nv_bfloat16*)y; p.mid = (__nv_bfloat16*)mid; p.w1 = (const __nv_bfloat16*)w1; p.w2 = (const __nv_bfloat16*)w2; p.bias = bias;
     // the kernel's T counts GEMM rows: frames, frame pairs or frame quads
     if (layout == kRsPairs8 || layout == kRsFold2) T /= 2;
     if (layout == kRsFold4) T /= 4;

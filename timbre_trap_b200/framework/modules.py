@@ -76,7 +76,7 @@ class ResidualConv2dBlock(nn.Module):
                  'planar': lambda: P.pack_res_rs(*args)}[mode]
         return self._caches.setdefault(mode, _PackedCache()).get(args, build)
 
-    def forward_c8(self, x, out=None):
+    def forward_c8(self, x, out=None, mid_out=None):
         # rows of C <= 8 tensors are folded to 16 values (4 or 2 frames per GEMM row) when T allows
         T = x.size(-2)
         if self.packed4:
@@ -84,7 +84,7 @@ class ResidualConv2dBlock(nn.Module):
         else:
             mode = 'fold2' if (self.channels <= 8 and T % 2 == 0) else 'planar'
         w1, w2, bias = self._packed(mode)
-        return ops.res_block_rs(x, w1, w2, bias, self.channels, self.dilation, out=out, fold=mode.startswith('fold'))
+        return ops.res_block_rs(x, w1, w2, bias, self.channels, self.dilation, out=out, fold=mode.startswith('fold'), mid_out=mid_out)
 
     def forward(self, x):
         """(B, C, H, W) -> (B, C, H, W) fp32 (API parity; the fast paths stay in the internal layouts)."""

@@ -74,7 +74,7 @@ def _check_p4(x, name='x'):
         raise ValueError(f'{name} must be a contiguous packed 4-channel bf16 tensor (B, H, T, 4) with even T, got {tuple(x.shape)} {x.dtype}')
 
 
-def res_block_rs(x, w1, w2, bias, c_real, dilation, out=None, fold=False):
+def res_block_rs(x, w1, w2, bias, c_real, dilation, out=None, fold=False, mid_out=None):
     """Row-stationary fused residual block (csrc/res_rs.cu).  x C8 planar: weights from packing.pack_res_rs, or with fold=True
     (C <= 8, even T) packing.pack_res_rs_fold(..., fold=2); x packed 4-channel (B, H, T, 4): packing.pack_res_rs_pairs, or with
     fold=True (T % 4 == 0) packing.pack_res_rs_fold(..., fold=4)."""
@@ -92,7 +92,13 @@ def res_block_rs(x, w1, w2, bias, c_real, dilation, out=None, fold=False):
     _lib.require_cuda(bias, 'bias')
     y = torch.empty_like(x) if out is None else out
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_res_block_rs(_p(x), _p(y), _p(w1), _p(w2), _p(bias), B, C, c_real, H, T, dilation, layout, _s(x)))
+        if mid_out is None:
+            _lib.check(_lib.lib().tt_res_block_rs(_p(x), _p(y), _p(w1), _p(w2), _p(bias), B, C, c_real, H, T, dilation, layout, _s(x)))
+        else:
+            # the inner activation ELU(W1 * x + b1) as well, in the layout of y (kept by the loss step for its backward pass)
+            if mid_out.shape != y.shape or mid_out.dtype != y.dtype or not mid_out.is_contiguous():
+                raise ValueError('mid_out must be a contiguous tensor of the shape and dtype of the output')
+            _lib.check(_lib.lib().tt_res_block_rs_mid(_p(x), _p(y), _p(mid_out), _p(w1), _p(w2), _p(bias), B, C, c_real, H, T, dilation, layout, _s(x)))
     return y
 
 

@@ -268,29 +268,29 @@ def _wgrad_same(x8, dz8, cin, cout, k, d):
 
 
 class _ResFn(torch.autograd.Function):
-    """ResidualConv2dBlock: fused forward kernel; the backward stays in bf16 C8 planar end to end - recompute of the inner activation
-    and both data-gradient convolutions through the tile kernel (tt_conv_same), both weight gradients through the MN-major tcgen05
-    kernel (tt_conv_wgrad_same), the ELU derivatives / residual add as one-pass element-wise kernels.  No NCHW fp32 round trips."""
+    """ResidualConv2dBlock: fused forward kernel, which also writes the inner activation ELU(W1 * x + b1) it stages in shared memory
+    (tt_res_block_rs_mid) - the backward needs it and a recompute costs a whole 3x3 conv launch per block; the backward stays in bf16
+    C8 planar end to end - both data-gradient convolutions through the tile kernel (tt_conv_same), both weight gradients through the
+    MN-major tcgen05 kernels (tt_conv_wgrad_same), the ELU derivatives / residual add as one-pass element-wise kernels."""
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2, run, c, d):
-        y = run(x)
-        ctx.save_for_backward(x, y, w1, b1, w2)
+        a1 = torch.empty_like(x)
+        y = run(x, a1)
+        ctx.save_for_backward(x, y, a1, w1, b1, w2)
         ctx.meta = (c, d)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, y, w1, b1, w2 = ctx.saved_tensors
+        x, y, a1, w1, b1, w2 = ctx.saved_tensors
         c, d = ctx.meta
-        n = max(16, P.pad8(c))
-        w1_fwd, b1_pad = _bw_pack(w1, 'res3x3', lambda: (P.pack_res3x3(w1.detach().float()), P.pad_vec(b1, n)))
         w2_t = _bw_pack(w2, 'res1x1T', lambda: P.pack_res1x1(w2.detach().float().transpose(0, 1).contiguous()))
         w1_t = _bw_pack(w1, 'res3x3T', lambda: P.pack_res3x3(w1.detach().float().transpose(0, 1).flip(2, 3).contiguous()))
         gy = gy.contiguous()
         dz2 = _as_c8(_ew('tt_res_out_bwd_bf16', gy, y, x))                       # gy * ELU'(z2), activated 1x1 output = y - x
         x8 = _as_c8(x)
-        a1 = ops.conv_same(x8, w1_fwd, b1_pad, 3, d, act=True)                   # the inner activation, as the forward staged it
+        a1 = _as_c8(a1)                                                          # the inner activation, as the forward staged it
         dw2, db2 = _wgrad_same(a1, dz2, c, c, 1, 1)
         da1 = ops.conv_same(dz2, w2_t, None, 1, 1)
         dz1 = _ew('tt_elu_bwd_bf16', da1, a1)
@@ -557,7 +557,7 @@ class _TrnLossFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------------------------------------------
 def _res(blk, x):
     c1, c2 = blk.conv1[0], blk.conv2[0]
-    return _ResFn.apply(x, c1.weight, c1.bias, c2.weight, c2.bias, lambda t: blk.forward_c8(t), blk.channels, blk.dilation)
+    return _ResFn.apply(x, c1.weight, c1.bias, c2.weight, c2.bias, lambda t, mid: blk.forward_c8(t, mid_out=mid), blk.channels, blk.dilation)
 
 
 def _encoder(enc, coeffs):
