@@ -150,6 +150,10 @@ int tt_res_block_rs_mid(const void* x, void* y, void* mid, const void* w1, const
  * planar tensors: building block of the backward pass (recompute + data gradients as convs with transformed weights) */
 int tt_conv_same(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,
                  int act_elu, void* stream);
+/* The same conv with one of the element-wise passes of the residual blocks' backward fused into its epilogue, on a tensor `e` of the
+   output's shape and layout: post = 1: y = conv(x) * ELU'(e), e the ACTIVATED value (e > 0 ? 1 : e + 1); post = 2: y = conv(x) + e. */
+int tt_conv_same_post(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,
+                      int act_elu, int post, const void* e, void* stream);
 /* EncoderBlock.sconv + ELU (modules.py:626-629): Conv2d(Cin, Cout, (4,1), stride (2,1)); Hout = (Hin-4)/2 + 1, and
  * DecoderBlock.tconv + ELU (modules.py:685-688): ConvTranspose2d(Cin, Cout, (4,1), stride (2,1), output_padding);
  * Hout = 2 Hin + 2 + out_pad - row-pipelined kernels (csrc/updown_strip.cu); weights from packing.pack_down_strip / pack_up_strip

@@ -261,3 +261,23 @@ def test_res_block_inner_activation_output(C, H, T, d, mode):
     assert float((got - want).abs().max()) <= 2e-2 * max(1.0, float(want.abs().max()))
     with pytest.raises(ValueError):
         ops.res_block_rs(xin, *pk, C, d, fold=fold, mid_out=mid[:1])
+
+
+@pytest.mark.parametrize('C,H,T,k,d', [(8, 13, 200, 1, 1), (16, 21, 128, 3, 2), (32, 9, 256, 3, 3), (5, 7, 131, 3, 1)])
+def test_conv_same_fused_epilogues(C, H, T, k, d):
+    """tt_conv_same_post: the element-wise passes of the residual blocks' backward in the conv's epilogue - times ELU'(.) given the
+    activated tensor (the 1x1 data gradient), plus a tensor (the residual add of the 3x3 data gradient)."""
+    from timbre_trap_b200.framework import ops, packing as P
+    B = 2
+    x = _bf(_rand((B, C, H, T), 1))
+    w = _bf(_rand((C, C, k, k), 2, 0.3))
+    e = _bf(_rand((B, C, H, T), 7))
+    conv = F.conv2d(x, w, None, padding=d if k == 3 else 0, dilation=d if k == 3 else 1)
+    wp = P.pack_res3x3(w.cuda()) if k == 3 else P.pack_res1x1(w.cuda())
+    x8, e8 = P.to_c8(x.cuda()), P.to_c8(e.cuda())
+    got = ops.conv_same(x8, wp, None, k, d, times_elu_grad_of=e8)
+    _assert_close(P.from_c8(got, C).cpu(), conv * torch.where(e > 0, torch.ones_like(e), e + 1))
+    got = ops.conv_same(x8, wp, None, k, d, plus=e8)
+    _assert_close(P.from_c8(got, C).cpu(), conv + e)
+    with pytest.raises(ValueError):
+        ops.conv_same(x8, wp, None, k, d, plus=e8[:1])

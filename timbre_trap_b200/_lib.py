@@ -38,6 +38,7 @@ SIGNATURES = {
     'tt_conv_down_strip': (c_int, [c_void_p] * 3 + [c_int] * 7 + [c_void_p]),
     'tt_conv_up_strip': (c_int, [c_void_p] * 3 + [c_int] * 8 + [c_void_p]),
     'tt_conv_same': (c_int, [c_void_p] * 4 + [c_int] * 7 + [c_void_p]),
+    'tt_conv_same_post': (c_int, [c_void_p] * 4 + [c_int] * 8 + [c_void_p] * 2),
     'tt_conv_lat': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),
     'tt_deconv_in': (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     'tt_conv_in': (c_int, [c_void_p] * 4 + [c_int] * 5 + [c_void_p]),

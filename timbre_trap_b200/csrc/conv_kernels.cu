@@ -50,6 +50,9 @@ struct ConvRowsParams {
     int n_mma1, kg1;       // MMAs per group, K groups of 8 in the packed weights
     int out_mode;          // 0: N channels -> one output row;  1: two output rows of N/2 channels
     int act;               // ELU on the output
+    int post;              // after that, with the tensor `e` (layout of y): 1 = times ELU'(e) as a function of the ACTIVATED value e
+                           // (e > 0 ? 1 : e + 1), 2 = plus e  - the element-wise passes of the residual blocks' backward, fused
+    const __nv_bfloat16* e;
     int w_group_stride;    // bytes between the packed weights of consecutive row groups (0: shared)
     int b_group_stride;    // floats between the biases of consecutive row groups (0: shared)
     uint32_t tap_off[kMaxTaps];
@@ -193,8 +196,19 @@ __global__ void __launch_bounds__(kConvThreads) conv_rows_kernel(const __grid_co
                     int ho, cg;
                     if (p.out_mode == 0) { ho = g0 + i; cg = c >> 3; }
                     else { ho = 2 * (g0 + i) + (c >= N1 / 2 ? 1 : 0); cg = (c % (N1 / 2)) >> 3; }
-                    if (cg < p.CGout && ho < p.Hout)
-                        reinterpret_cast<uint4*>(p.y)[(((size_t)b * p.CGout + cg) * p.Hout + ho) * p.T + t0 + j] = pack8(v + 8 * hh);
+                    if (cg < p.CGout && ho < p.Hout) {
+                        const size_t at = (((size_t)b * p.CGout + cg) * p.Hout + ho) * p.T + t0 + j;
+                        if (p.post) {
+                            float ev[8];
+                            unpack8(__ldg(reinterpret_cast<const uint4*>(p.e) + at), ev);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                if (p.post == 1) v[8 * hh + k] *= ev[k] > 0.f ? 1.f : ev[k] + 1.f;
+                                else v[8 * hh + k] += ev[k];
+                            }
+                        }
+                        reinterpret_cast<uint4*>(p.y)[at] = pack8(v + 8 * hh);
+                    }
                 }
             }
         }
@@ -257,7 +271,13 @@ static int dispatch_n1(const ConvRowsParams& p, int n1, cudaStream_t s) {
 //   k = 3: weights from packing.pack_res3x3 (K order tap-major);  k = 1: packing.pack_res1x1.  bias may be NULL (zeros).
 extern "C" int tt_conv_same(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,
                             int act_elu, void* stream) {
+    return tt_conv_same_post(x, y, w, bias, B, C, H, T, k, dilation, act_elu, 0, nullptr, stream);
+}
+
+extern "C" int tt_conv_same_post(const void* x, void* y, const void* w, const float* bias, int B, int C, int H, int T, int k, int dilation,
+                                 int act_elu, int post, const void* e, void* stream) {
     TT_REQUIRE(x && y && w, "null argument");
+    TT_REQUIRE(post >= 0 && post <= 2 && (post == 0 || e != nullptr), "conv_same: post-op 0, 1 (times ELU'(e)) or 2 (plus e) with its tensor");
     TT_REQUIRE(C == 8 || C == 16 || C == 32, "conv_same: padded channel count must be 8, 16 or 32 (got %d)", C);
     TT_REQUIRE((k == 3 && dilation >= 1 && dilation <= 4) || k == 1, "conv_same: 3x3 (dilation 1..4) or 1x1");
     if (B <= 0 || H <= 0 || T <= 0) return TT_OK;
@@ -275,7 +295,7 @@ extern "C" int tt_conv_same(const void* x, void* y, const void* w, const float* 
     p.groups = H;
     p.R = std::min(C == 8 ? 16 : (C == 16 ? 8 : 4), kMaxRows);
     p.sh = 1; p.row_lo = -d; p.in_rows = p.R + 2 * d; p.padT = d;
-    p.out_mode = 0; p.act = act_elu;
+    p.out_mode = 0; p.act = act_elu; p.post = post; p.e = (const __nv_bfloat16*)e;
     const uint32_t TW = kTileT + 2 * d, row_bytes = TW * 16, plane = (uint32_t)p.in_rows * row_bytes;
     int m = 0;
     if (k == 3) {

@@ -129,12 +129,16 @@ def conv_up_strip(x, w, cout_pad, out_pad, packed4_out=False, act=True):
     return y
 
 
-def conv_same(x, w, bias, k, dilation=1, act=False):
-    """3x3 dilated 'same' conv (k = 3) or 1x1 conv (k = 1) on a C8 planar tensor, optional ELU (tile kernel, tensor cores)."""
+def conv_same(x, w, bias, k, dilation=1, act=False, times_elu_grad_of=None, plus=None):
+    """3x3 dilated 'same' conv (k = 3) or 1x1 conv (k = 1) on a C8 planar tensor, optional ELU (tile kernel, tensor cores).  Fused
+    epilogues of the residual blocks' backward: `times_elu_grad_of=a` multiplies by ELU'(.) given the activated tensor a, `plus=g` adds g."""
     _check_c8(x)
     B, CG, H, T, _ = x.shape
     y = torch.empty_like(x)
+    post, e = (1, times_elu_grad_of) if times_elu_grad_of is not None else ((2, plus) if plus is not None else (0, None))
+    if e is not None and (e.shape != x.shape or e.dtype != x.dtype or not e.is_contiguous()):
+        raise ValueError('the post-op tensor must have the shape, dtype and (contiguous) layout of the output')
     with torch.cuda.device(x.device):
-        _lib.check(_lib.lib().tt_conv_same(_p(x), _p(y), _p(w), _p(bias) if bias is not None else None, B, CG * 8, H, T, k, dilation,
-                                           int(act), _s(x)))
+        _lib.check(_lib.lib().tt_conv_same_post(_p(x), _p(y), _p(w), _p(bias) if bias is not None else None, B, CG * 8, H, T, k, dilation,
+                                                int(act), post, _p(e) if e is not None else None, _s(x)))
     return y

@@ -292,13 +292,14 @@ class _ResFn(torch.autograd.Function):
         x8 = _as_c8(x)
         a1 = _as_c8(a1)                                                          # the inner activation, as the forward staged it
         dw2, db2 = _wgrad_same(a1, dz2, c, c, 1, 1)
-        da1 = ops.conv_same(dz2, w2_t, None, 1, 1)
-        dz1 = _ew('tt_elu_bwd_bf16', da1, a1)
+        dz1 = ops.conv_same(dz2, w2_t, None, 1, 1, times_elu_grad_of=a1)         # W2^T dz2, times ELU'(z1): one launch
         dw1, db1 = _wgrad_same(x8, dz1, c, c, 3, d)
-        gx8 = ops.conv_same(dz1, w1_t, None, 3, d)
-        gx = _to_layout_of(gx8, x)
-        one = torch.ones((), dtype=torch.float32, device=gx.device)
-        _lib.check(_lib.lib().tt_add_scaled_bf16(_p(gy), _p(gx), _p(one.reshape(1)), _p(gx), gx.numel(), _s(gx)))     # gx = gy + gx
+        if gy.dim() == 5:
+            gx = ops.conv_same(dz1, w1_t, None, 3, d, plus=gy)                   # gx = gy + W1^T (*) dz1: the residual add in the epilogue
+        else:
+            gx = _to_layout_of(ops.conv_same(dz1, w1_t, None, 3, d), x)          # packed 4-channel stage: re-layout, then add
+            one = torch.ones((), dtype=torch.float32, device=gx.device)
+            _lib.check(_lib.lib().tt_add_scaled_bf16(_p(gy), _p(gx), _p(one.reshape(1)), _p(gx), gx.numel(), _s(gx)))
         return gx, dw1, db1, dw2, db2, None, None, None
 
 
