@@ -683,7 +683,12 @@ static Wg3Plan wg3_plan(int B, int CGi, int CGo, int H, int T, int d, int kh = 3
     const size_t z_slot = (size_t)CGo * kStripTileT * 16, x_slot = ((size_t)CGi * (kStripTileT + 2 * d) * 16 + 127) & ~(size_t)127;
     g.xring = 4;
     // everything a strip touches of dZ stays resident: rows + 2 d slots, and the A operand reads 32 KB from its first slot
-    const size_t budget = 226 * 1024 - 2048 - g.xring * x_slot - 32 * 1024;
+    // one resident strip per SM leaves the tensor pipe idle while the strip's first rows are in flight: with small rows (C <= 16) take
+    // half of the shared memory, so that two CTAs share an SM and one computes while the other loads
+    static const int cap_kb = getenv("TT_WG3_SMEM_KB") ? atoi(getenv("TT_WG3_SMEM_KB")) : 112;
+    static const int cap_cgo = getenv("TT_WG3_CAP_CGO") ? atoi(getenv("TT_WG3_CAP_CGO")) : 2;
+    const size_t cap = (size_t)(cap_kb > 0 && CGo <= cap_cgo ? cap_kb : 226) * 1024;
+    const size_t budget = cap - 2048 - g.xring * x_slot - 32 * 1024;
     int max_rows = (int)std::min<size_t>(budget / z_slot, (size_t)kWg3MaxRows) - (kh == 1 ? 0 : 3 * d - 1);   // the residue-class layout rounds the row count up to a multiple of d
     max_rows = std::max(max_rows, 1);
     const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
