@@ -466,6 +466,195 @@ __global__ void __launch_bounds__(32 * kWg3RedSeg) wgrad3_reduce_kernel(const fl
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------------
+// (4,1) stride-(2,1) layers (EncoderBlock.sconv; DecoderBlock.tconv with the sides swapped), row-stationary form.
+//     dW[cc][cf][kh] = sum over (b, q, t) of  coarse[b, cc, q, t] * fine[b, cf, 2 q + kh, t]
+// A fine row rho meets the coarse rows q0 - 1 and q0 = rho / 2 (taps kh = rho % 2 + 2 and rho % 2): the strip's coarse rows are
+// resident and consecutive, so the two are stacked in the MMA's M (TMEM lanes (j, cc), j = 0 <-> q0 - 1), and the row parity selects
+// the accumulator columns: ONE MMA per fine row and K step - two per coarse row where the kernel above needs 4 + 1.  The bias
+// gradient of the strided layer (pixel sums of the coarse tensor) comes from the resident rows through the idle warps.
+// ------------------------------------------------------------------------------------------------------------------------------------
+struct WgradUdParams {
+    float* partial;
+    int B, T, Hc;                      // coarse rows; fine rows 0 .. 2 Hc + 1 are used
+    int rows_per_strip;                // values of q0 per strip (q0 in [0, Hc]: the last one pairs the zero row Hc with row Hc - 1)
+    int xring;
+    int per_cta;
+};
+
+template <int CGC, int CGF>
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_ud_kernel(const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_c,
+                                                                 const WgradUdParams p) {
+    constexpr int NK = CGF <= 2 ? 16 : 32;                             // N of one MMA (fine-side channels, padded)
+    constexpr int NCOL = 2 * NK;                                       // accumulator columns: (row parity, cf)
+    constexpr uint32_t ncols = NCOL <= 32 ? 32 : 64;
+    constexpr int MREAL = 2 * CGC * 8;                                 // lanes (j, cc)
+    static_assert(MREAL <= 128, "two coarse rows of up to 64 channels");
+    constexpr uint32_t c_slot = (uint32_t)CGC * kStripTileT * 16u;
+    constexpr uint32_t f_plane = (uint32_t)kStripTileT * 16u;
+    constexpr uint32_t f_slot = (uint32_t)CGF * f_plane;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int xring = p.xring;
+    uint64_t* c_full = reinterpret_cast<uint64_t*>(smem);             // [kWg3MaxRows]
+    uint64_t* f_full = c_full + kWg3MaxRows;                           // [xring <= 8]
+    uint64_t* f_empty = f_full + 8;
+    uint64_t* done = f_empty + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+    float* sBias = reinterpret_cast<float*>(smem + 1280);              // [2 warps][CGC * 8]
+    uint8_t* sF = smem + 2048;
+    uint8_t* sC = sF + (size_t)xring * f_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int t0 = blockIdx.x * kStripTileT;
+    const int q_lo = blockIdx.y * p.rows_per_strip, q_hi = min(p.Hc + 1, q_lo + p.rows_per_strip);     // values of q0
+    const int b = blockIdx.z;
+    const int n_q = q_hi - q_lo;
+    const int n_frows = 2 * n_q;                                       // fine rows 2 q_lo .. 2 q_hi - 1
+    const int nc = n_q + 1;                                            // coarse rows q_lo - 1 .. q_hi - 1 (rows -1 and Hc arrive as zeros)
+
+    if (warp == 0) umma::tmem_alloc(tmem_slot, ncols);
+    if (tid == 32) {
+        for (int i = 0; i < nc; ++i) umma::mbar_init(&c_full[i], 1);
+        for (int i = 0; i < xring; ++i) { umma::mbar_init(&f_full[i], 1); umma::mbar_init(&f_empty[i], 1); }
+        umma::mbar_init(done, 1);
+        umma::mbar_fence_init();
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0 && lane == 0) {
+        // ================= producer =================
+        auto load_c = [&](int i) {
+            mbar_expect_tx(&c_full[i], c_slot);
+            tma_load_5d(sC + (size_t)i * c_slot, &tmap_c, &c_full[i], 0, t0, q_lo - 1 + i, 0, b);
+        };
+        load_c(0);
+        if (nc > 1) load_c(1);
+        for (int r = 0; r < n_frows; ++r) {
+            const int slot = r % xring;
+            if (r >= xring) umma::mbar_wait(&f_empty[slot], (uint32_t)((r / xring - 1) & 1));
+            mbar_expect_tx(&f_full[slot], f_slot);
+            tma_load_5d(sF + (size_t)slot * f_slot, &tmap_f, &f_full[slot], 0, t0, 2 * q_lo + r, 0, b);
+            if ((r & 1) && (r >> 1) + 2 < nc) load_c((r >> 1) + 2);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc = umma::make_idesc_bf16(128, NK) | (1u << 15) | (1u << 16);       // both operands MN-major
+        constexpr uint32_t lbo_field = (128u >> 4) << 16;
+        const uint32_t hi_a = ((uint32_t)(kStripTileT * 16) >> 4) | (1u << 14);
+        const uint32_t hi_b = (f_plane >> 4) | (1u << 14);
+        const uint32_t c0 = umma::smem_u32(sC), f0 = umma::smem_u32(sF);
+        auto d64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
+        for (int r = 0; r < n_frows; ++r) {
+            const int qi = r >> 1;                                     // coarse rows qi (= q0 - 1) and qi + 1 (= q0) of the strip's buffer
+            if (r == 0) umma::mbar_wait(&c_full[0], 0);
+            if ((r & 1) == 0) umma::mbar_wait(&c_full[qi + 1], 0);
+            umma::mbar_wait(&f_full[r % xring], (uint32_t)((r / xring) & 1));
+            umma::fence_after_sync();
+            const uint32_t lo_a = (((c0 + (uint32_t)qi * c_slot) >> 4) & 0x3FFFu) | lbo_field;
+            const uint32_t lo_b = (((f0 + (uint32_t)(r % xring) * f_slot) >> 4) & 0x3FFFu) | lbo_field;
+            const uint32_t acc_col = tmem + (uint32_t)((r & 1) * NK);
+#pragma unroll
+            for (int s = 0; s < kStripTileT / 16; ++s)
+                umma::mma_bf16(acc_col, d64(hi_a, lo_a + (uint32_t)s * 16u), d64(hi_b, lo_b + (uint32_t)s * 16u), idesc, !(r < 2 && s == 0));
+            umma::commit(&f_empty[r % xring]);
+        }
+        umma::commit(done);
+    } else if (warp >= 2) {
+        // ================= pixel sums of the strip's own coarse rows q_lo .. min(q_hi, Hc) - 1 (the strided layer's bias gradient) =================
+        float acc[CGC * 8];
+#pragma unroll
+        for (int k = 0; k < CGC * 8; ++k) acc[k] = 0.f;
+        const int own = min(q_hi, p.Hc) - q_lo;
+        for (int r = warp - 2; r < own; r += 2) {
+            const int i = r + 1;                                        // buffer row of coarse row q_lo + r
+            umma::mbar_wait(&c_full[i], 0);
+            const uint8_t* row = sC + (size_t)i * c_slot;
+#pragma unroll
+            for (int q = 0; q < kStripTileT / 32; ++q) {
+#pragma unroll
+                for (int cg = 0; cg < CGC; ++cg) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(row + ((size_t)cg * kStripTileT + q * 32 + lane) * 16u);
+                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 f = __bfloat1622float2(h[e]);
+                        acc[cg * 8 + 2 * e] += f.x;
+                        acc[cg * 8 + 2 * e + 1] += f.y;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CGC * 8; ++k) {
+            float v = acc[k];
+#pragma unroll
+            for (int sft = 16; sft > 0; sft >>= 1) v += __shfl_xor_sync(0xffffffffu, v, sft);
+            if (lane == 0) sBias[(warp - 2) * CGC * 8 + k] = v;
+        }
+    }
+    __syncthreads();
+    const size_t cta = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    float* dst = p.partial + cta * (size_t)p.per_cta;
+    if (tid < CGC * 8) dst[(size_t)MREAL * NCOL + tid] = sBias[tid] + sBias[CGC * 8 + tid];
+    if (warp * 32 < MREAL) {
+        umma::mbar_wait_warp(done, 0);
+        umma::fence_after_sync();
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const int m = warp * 32 + lane;
+#pragma unroll
+        for (int c0 = 0; c0 < NCOL; c0 += 16) {
+            float v[16];
+            umma::tmem_ld16(lane_addr + (uint32_t)c0, v);
+            umma::tmem_ld_wait();
+            if (m < MREAL) {
+                float4* o = reinterpret_cast<float4*>(dst + (size_t)m * NCOL + c0);
+                o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+                o[2] = make_float4(v[8], v[9], v[10], v[11]);
+                o[3] = make_float4(v[12], v[13], v[14], v[15]);
+            }
+        }
+    }
+    umma::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) umma::tmem_dealloc(tmem, ncols);
+}
+
+// dw (cc, cf, 4, 1) and db (cc) += fixed-order sums over the partial blocks of wgrad_ud_kernel (same scheme as wgrad3_reduce_kernel)
+__global__ void __launch_bounds__(32 * kWg3RedSeg) wgrad_ud_reduce_kernel(const float* __restrict__ partial, int n_ctas, int per_cta, int cgc, int nk,
+                                                                         int m_real, int n_real, float* __restrict__ dw, float* __restrict__ db) {
+    __shared__ float part[kWg3RedSeg][32];
+    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;                                  // over (kh in [0, 4], cc, cf); kh == 4: bias
+    const int total = 5 * m_real * n_real;
+    const int kh = i / (m_real * n_real), rem = i - kh * m_real * n_real;
+    const int o = rem / n_real, c = rem - o * n_real;
+    const bool live = i < total && !(kh == 4 && (c != 0 || db == nullptr));
+    float acc = 0.f;
+    if (live) {
+        const int ncol = 2 * nk;
+        size_t off;
+        if (kh == 4) off = (size_t)2 * cgc * 8 * ncol + o;
+        else off = (size_t)((kh < 2 ? 1 : 0) * cgc * 8 + o) * ncol + (size_t)(kh & 1) * nk + c;      // kh = parity + 2 (1 - j)
+        const int per_seg = (n_ctas + kWg3RedSeg - 1) / kWg3RedSeg;
+        const int k0 = seg * per_seg, k1 = min(n_ctas, k0 + per_seg);
+        const float* src = partial + off;
+        for (int k = k0; k < k1; ++k) acc += src[(size_t)k * per_cta];
+    }
+    part[seg][lane] = acc;
+    __syncthreads();
+    if (seg == 0 && live) {
+        float v = part[0][lane];
+#pragma unroll
+        for (int q = 1; q < kWg3RedSeg; ++q) v += part[q][lane];
+        if (kh == 4) db[o] += v;
+        else dw[((size_t)o * n_real + c) * 4 + kh] += v;
+    }
+}
+
 // dW (m, n, taps) and db (m) += fixed-order sums of the per-CTA partials (m = A-side channel, n = B-side channel: (co, ci, kh, kw) for a
 // regular conv, (ci, co, kh, kw) - the ConvTranspose2d weight layout - when the two sides are swapped)
 // kxn: the partials hold 3 vertical taps of [kx][8 channels] columns (see KXN above); taps stays 9 for the output layout.
@@ -723,6 +912,31 @@ static Wg3Plan wg3_plan(int B, int CGi, int CGo, int H, int T, int d, int kh = 3
     return g;
 }
 
+struct WgUdPlan {
+    int rows, strips, xring, per_cta;
+    size_t smem;
+};
+
+static WgUdPlan wgud_plan(int B, int CGf, int CGc, int Hc, int T) {
+    WgUdPlan g;
+    const size_t c_slot = (size_t)CGc * kStripTileT * 16, f_slot = (size_t)CGf * kStripTileT * 16;
+    g.xring = 4;
+    const size_t cap = (size_t)(CGc <= 2 ? 112 : 226) * 1024;          // small rows: two strips per SM (see wg3_plan)
+    const size_t budget = cap - 2048 - g.xring * f_slot - 32 * 1024;
+    int max_rows = (int)std::min<size_t>(budget / c_slot, (size_t)kWg3MaxRows) - 1;     // values of q0 per strip (+ 1 coarse row)
+    max_rows = std::max(max_rows, 1);
+    const int nq = Hc + 1;
+    const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
+    long long strips = std::max<long long>((nq + max_rows - 1) / max_rows, std::min<long long>((4 * 148 + tiles - 1) / tiles, std::max(1, nq / 4)));
+    g.rows = (int)((nq + strips - 1) / strips);
+    g.strips = (nq + g.rows - 1) / g.rows;
+    const int nk = CGf <= 2 ? 16 : 32;
+    g.per_cta = 2 * CGc * 8 * 2 * nk + CGc * 8;
+    const size_t nrows = (size_t)g.rows + 1;
+    g.smem = 2048 + g.xring * f_slot + std::max(nrows * c_slot, (nrows - 2) * c_slot + 32 * 1024) + 1024;
+    return g;
+}
+
 }  // namespace tt
 
 using namespace tt;
@@ -738,6 +952,10 @@ extern "C" int64_t tt_wgrad_scratch_floats(int B, int H, int T) {
                 const Wg3Plan g = wg3_plan(B, cgi, cgo, H, T, d), g1 = wg3_plan(B, cgi, cgo, H, T, 1, 1);
                 need = std::max(need, std::max(tiles * g.strips * (long long)g.per_cta, tiles * g1.strips * (long long)g1.per_cta));
             }
+    for (int cgc = 1; cgc <= 8; cgc *= 2) {
+        const WgUdPlan g = wgud_plan(B, std::max(1, cgc / 2), cgc, H, T);
+        need = std::max(need, tiles * g.strips * (long long)g.per_cta);
+    }
     return need;
 }
 
@@ -839,6 +1057,34 @@ extern "C" int tt_conv_wgrad_same(const void* x, const void* dz, float* dw, floa
     return wgrad_any<1, 1, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, 1, scratch, stream);
 }
 
+template <int CGC, int CGF>
+static int launch_wgrad_ud(const void* fine, const void* coarse, float* dw, float* db, int B, int cfine_real, int ccoarse_real, int Hfine, int Hcoarse,
+                           int T, float* scratch, cudaStream_t stream) {
+    const WgUdPlan g = wgud_plan(B, CGF, CGC, Hcoarse, T);
+    TT_REQUIRE(g.smem <= 227 * 1024 && g.rows + 1 <= kWg3MaxRows, "wgrad_ud: %zu bytes of shared memory, %d rows", g.smem, g.rows);
+    static size_t configured = 0;
+    if (g.smem > configured) {
+        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad_ud_kernel<CGC, CGF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        configured = g.smem;
+    }
+    CUtensorMap mf, mc;
+    int rc = make_row_map(&mf, fine, B, CGF, Hfine, T, kStripTileT);
+    if (rc) return rc;
+    rc = make_row_map(&mc, coarse, B, CGC, Hcoarse, T, kStripTileT);
+    if (rc) return rc;
+    WgradUdParams p;
+    p.partial = scratch; p.B = B; p.T = T; p.Hc = Hcoarse; p.rows_per_strip = g.rows; p.xring = g.xring; p.per_cta = g.per_cta;
+    dim3 grid((T + kStripTileT - 1) / kStripTileT, g.strips, B);
+    wgrad_ud_kernel<CGC, CGF><<<grid, kWgThreads, g.smem, stream>>>(mf, mc, p);
+    TT_CUDA_CHECK(cudaGetLastError());
+    const int n_ctas = (int)(grid.x * grid.y * grid.z);
+    const int total = 5 * ccoarse_real * cfine_real;
+    wgrad_ud_reduce_kernel<<<(total + 31) / 32, 32 * kWg3RedSeg, 0, stream>>>(scratch, n_ctas, g.per_cta, CGC, CGF <= 2 ? 16 : 32, ccoarse_real, cfine_real, dw, db);
+    tt_count_launches(2);
+    TT_CUDA_CHECK(cudaGetLastError());
+    return TT_OK;
+}
+
 extern "C" int tt_conv_wgrad_updown(const void* fine, const void* coarse, float* dw, float* db, int B, int Cfine, int Ccoarse, int cfine_real,
                                     int ccoarse_real, int Hfine, int Hcoarse, int T, int transposed, float* scratch, void* stream_) {
     TT_REQUIRE(fine && coarse && dw && scratch, "null argument");
@@ -848,8 +1094,16 @@ extern "C" int tt_conv_wgrad_updown(const void* fine, const void* coarse, float*
     if (B <= 0 || T <= 0 || Hcoarse <= 0) return TT_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
     // the coarse tensor (sconv: the output gradient; tconv: the layer input) is the A side, the fine one (rows 2q + kh) the B side
-    const int rc = wgrad_any<4, 1, 2>(fine, coarse, dw, transposed ? nullptr : db, B, Cfine, Ccoarse, cfine_real, ccoarse_real, Hfine, Hcoarse, T, 1,
-                                      scratch, stream);
+    static const bool legacy = getenv("TT_WGRAD_LEGACY") != nullptr;
+    int rc = TT_ERR_UNSUPPORTED;
+    float* dbc = transposed ? nullptr : db;
+    if (!legacy) {
+#define TT_WGUD(CC, CF) if (Ccoarse == CC * 8 && Cfine == CF * 8) rc = launch_wgrad_ud<CC, CF>(fine, coarse, dw, dbc, B, cfine_real, ccoarse_real, Hfine, Hcoarse, T, scratch, stream);
+        TT_WGUD(1, 1) TT_WGUD(2, 1) TT_WGUD(4, 2) TT_WGUD(8, 4)
+#undef TT_WGUD
+    }
+    if (rc == TT_ERR_UNSUPPORTED)
+        rc = wgrad_any<4, 1, 2>(fine, coarse, dw, dbc, B, Cfine, Ccoarse, cfine_real, ccoarse_real, Hfine, Hcoarse, T, 1, scratch, stream);
     if (rc || !transposed || !db) return rc;
     // ConvTranspose2d bias: sum of the FINE tensor (the output gradient) over all pixels
     const int CG = Cfine / 8, chunks = 64;
