@@ -262,21 +262,19 @@ struct Wgrad3Params {
     int per_cta;                       // floats of one CTA's partial block
 };
 
-// KH = 1: the 1x1 layers through the same kernel - one dZ row per X row, no taps: one MMA per K step (the kernel above: two, the
-// second one for the bias), N = the B-side channel groups.
-template <int CGO, int CGI, int KH>
+template <int CGO, int CGI>
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_z,
                                                                const Wgrad3Params p) {
-    static_assert(KH == 3 || KH == 1, "3x3 or 1x1");
-    constexpr int NK = KH == 1 ? (CGI <= 2 ? 16 : 32) : (CGI == 1 ? 32 : (CGI == 2 ? 16 : 32));   // N of one MMA
-    constexpr int NMMA = KH == 1 ? 1 : (CGI == 1 ? 1 : 3);             // MMAs per K step
+    constexpr int KH = 3;
+    constexpr int NK = CGI == 1 ? 32 : (CGI == 2 ? 16 : 32);          // N of one MMA
+    constexpr int NMMA = CGI == 1 ? 1 : 3;                             // MMAs per K step
     constexpr int NCOL = NK * NMMA;                                    // accumulator columns
     constexpr uint32_t ncols = NCOL <= 32 ? 32 : (NCOL <= 64 ? 64 : 128);
     constexpr int MREAL = KH * CGO * 8;                                // lanes (j, co)
     constexpr uint32_t z_slot = (uint32_t)CGO * kStripTileT * 16u;
     extern __shared__ __align__(1024) uint8_t smem[];
-    const int d = KH == 3 ? p.d : 1;                                   // row distance of the vertical taps (1x1: residue layout degenerates)
-    const int hz = KH == 3 ? d : 0;                                    // dZ halo rows on either side / column halo of the X rows
+    const int d = p.d;                                                 // row distance of the vertical taps
+    const int hz = d;                                                  // dZ halo rows on either side / column halo of the X rows
     const int TW = kStripTileT + 2 * hz;
     const uint32_t x_plane = (uint32_t)TW * 16u;
     const uint32_t x_slot = ((uint32_t)CGI * x_plane + 127u) & ~127u;
@@ -330,12 +328,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad3_kernel(const __grid_cons
         constexpr uint32_t idesc = umma::make_idesc_bf16(128, NK) | (1u << 15) | (1u << 16);       // both operands MN-major
         constexpr uint32_t lbo_field = (128u >> 4) << 16;
         const uint32_t hi_a = ((uint32_t)(kStripTileT * 16) >> 4) | (1u << 14);
-        const uint32_t hi_b = (((KH == 3 && CGI == 1) ? (uint32_t)d * 16u : x_plane) >> 4) | (1u << 14);
+        const uint32_t hi_b = ((CGI == 1 ? (uint32_t)d * 16u : x_plane) >> 4) | (1u << 14);
         const uint32_t z0 = umma::smem_u32(sZ), x0 = umma::smem_u32(sX);
         auto d64 = [](uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; };
         for (int r = 0; r < n_rows; ++r) {
             // dZ rows r, r + d, r + 2 d (relative to h0 - d): the first two were awaited with earlier X rows once r >= d
-            if (KH == 3 && r < d) {
+            if (r < d) {
                 umma::mbar_wait(&z_full[r], 0);
                 umma::mbar_wait(&z_full[r + d], 0);
             }
@@ -886,9 +884,8 @@ struct Wg3Plan {
     size_t smem;
 };
 
-static Wg3Plan wg3_plan(int B, int CGi, int CGo, int H, int T, int d, int kh = 3) {
+static Wg3Plan wg3_plan(int B, int CGi, int CGo, int H, int T, int d) {
     Wg3Plan g;
-    if (kh == 1) d = 0;
     const size_t z_slot = (size_t)CGo * kStripTileT * 16, x_slot = ((size_t)CGi * (kStripTileT + 2 * d) * 16 + 127) & ~(size_t)127;
     g.xring = 4;
     // everything a strip touches of dZ stays resident: rows + 2 d slots, and the A operand reads 32 KB from its first slot
@@ -898,17 +895,17 @@ static Wg3Plan wg3_plan(int B, int CGi, int CGo, int H, int T, int d, int kh = 3
     static const int cap_cgo = getenv("TT_WG3_CAP_CGO") ? atoi(getenv("TT_WG3_CAP_CGO")) : 2;
     const size_t cap = (size_t)(cap_kb > 0 && CGo <= cap_cgo ? cap_kb : 226) * 1024;
     const size_t budget = cap - 2048 - g.xring * x_slot - 32 * 1024;
-    int max_rows = (int)std::min<size_t>(budget / z_slot, (size_t)kWg3MaxRows) - (kh == 1 ? 0 : 3 * d - 1);   // the residue-class layout rounds the row count up to a multiple of d
+    int max_rows = (int)std::min<size_t>(budget / z_slot, (size_t)kWg3MaxRows) - (3 * d - 1);   // the residue-class layout rounds the row count up to a multiple of d
     max_rows = std::max(max_rows, 1);
     const long long tiles = (long long)B * ((T + kStripTileT - 1) / kStripTileT);
     // at least ~4 CTAs per SM in total (one is resident at a time), never more rows than shared memory holds
     long long strips = std::max<long long>((H + max_rows - 1) / max_rows, std::min<long long>((4 * 148 + tiles - 1) / tiles, std::max(1, H / 4)));
     g.rows = (int)((H + strips - 1) / strips);
     g.strips = (H + g.rows - 1) / g.rows;
-    const int nk = kh == 1 ? (CGi <= 2 ? 16 : 32) : (CGi == 1 ? 32 : (CGi == 2 ? 16 : 32)), ncol = nk * ((kh == 1 || CGi == 1) ? 1 : 3);
-    g.per_cta = kh * CGo * 8 * ncol + CGo * 8;
-    const size_t nzpos = kh == 1 ? (size_t)g.rows : (size_t)d * ((g.rows + 2 * d + d - 1) / d);
-    g.smem = 2048 + g.xring * x_slot + std::max(nzpos * z_slot, (nzpos - std::min<size_t>(nzpos, kh)) * z_slot + 32 * 1024) + 1024;
+    const int nk = CGi == 1 ? 32 : (CGi == 2 ? 16 : 32), ncol = nk * (CGi == 1 ? 1 : 3);
+    g.per_cta = 3 * CGo * 8 * ncol + CGo * 8;
+    const size_t nzpos = (size_t)d * ((g.rows + 2 * d + d - 1) / d);
+    g.smem = 2048 + g.xring * x_slot + std::max(nzpos * z_slot, (nzpos - 3) * z_slot + 32 * 1024) + 1024;
     return g;
 }
 
@@ -949,8 +946,8 @@ extern "C" int64_t tt_wgrad_scratch_floats(int B, int H, int T) {
     for (int cgi = 1; cgi <= 4; cgi *= 2)
         for (int cgo = 1; cgo <= 4; cgo *= 2)
             for (int d = 1; d <= 3; ++d) {
-                const Wg3Plan g = wg3_plan(B, cgi, cgo, H, T, d), g1 = wg3_plan(B, cgi, cgo, H, T, 1, 1);
-                need = std::max(need, std::max(tiles * g.strips * (long long)g.per_cta, tiles * g1.strips * (long long)g1.per_cta));
+                const Wg3Plan g = wg3_plan(B, cgi, cgo, H, T, d);
+                need = std::max(need, tiles * g.strips * (long long)g.per_cta);
             }
     for (int cgc = 1; cgc <= 8; cgc *= 2) {
         const WgUdPlan g = wgud_plan(B, std::max(1, cgc / 2), cgc, H, T);
@@ -1000,15 +997,15 @@ static int wgrad_any(const void* bsrc, const void* a, float* dw, float* db, int 
     return TT_OK;
 }
 
-template <int CGO, int CGI, int KH>
+template <int CGO, int CGI>
 static int launch_wgrad3(const void* x, const void* dz, float* dw, float* db, int B, int cin_real, int cout_real, int H, int T, int d,
                          float* scratch, cudaStream_t stream) {
-    if (KH == 1) d = 0;
-    const Wg3Plan g = wg3_plan(B, CGI, CGO, H, T, d, KH);
+    constexpr int KH = 3;
+    const Wg3Plan g = wg3_plan(B, CGI, CGO, H, T, d);
     TT_REQUIRE(g.smem <= 227 * 1024 && g.rows + 2 * d <= kWg3MaxRows, "wgrad3: %zu bytes of shared memory, %d rows", g.smem, g.rows);
     static size_t configured = 0;
     if (g.smem > configured) {
-        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad3_kernel<CGO, CGI, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+        TT_CUDA_CHECK(cudaFuncSetAttribute(wgrad3_kernel<CGO, CGI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
         configured = g.smem;
     }
     CUtensorMap mx, mz;
@@ -1019,21 +1016,20 @@ static int launch_wgrad3(const void* x, const void* dz, float* dw, float* db, in
     Wgrad3Params p;
     p.partial = scratch; p.B = B; p.T = T; p.H = H; p.d = d; p.rows_per_strip = g.rows; p.xring = g.xring; p.per_cta = g.per_cta;
     dim3 grid((T + kStripTileT - 1) / kStripTileT, g.strips, B);
-    wgrad3_kernel<CGO, CGI, KH><<<grid, kWgThreads, g.smem, stream>>>(mx, mz, p);
+    wgrad3_kernel<CGO, CGI><<<grid, kWgThreads, g.smem, stream>>>(mx, mz, p);
     TT_CUDA_CHECK(cudaGetLastError());
     const int n_ctas = (int)(grid.x * grid.y * grid.z);
-    constexpr int NK = KH == 1 ? (CGI <= 2 ? 16 : 32) : (CGI == 1 ? 32 : (CGI == 2 ? 16 : 32)), NCOL = NK * ((KH == 1 || CGI == 1) ? 1 : 3);
+    constexpr int NK = CGI == 1 ? 32 : (CGI == 2 ? 16 : 32), NCOL = NK * (CGI == 1 ? 1 : 3);
     const int total = (KH * KH + 1) * cout_real * cin_real;
-    wgrad3_reduce_kernel<<<(total + 31) / 32, 32 * kWg3RedSeg, 0, stream>>>(scratch, n_ctas, g.per_cta, CGO, NCOL, NK, KH == 3 && CGI == 1, KH, cout_real, cin_real, dw, db);
+    wgrad3_reduce_kernel<<<(total + 31) / 32, 32 * kWg3RedSeg, 0, stream>>>(scratch, n_ctas, g.per_cta, CGO, NCOL, NK, CGI == 1, KH, cout_real, cin_real, dw, db);
     tt_count_launches(2);
     TT_CUDA_CHECK(cudaGetLastError());
     return TT_OK;
 }
 
-template <int KH>
 static int wgrad3_dispatch(const void* x, const void* dz, float* dw, float* db, int B, int Cin, int Cout, int cin_real, int cout_real, int H, int T,
                            int d, float* scratch, cudaStream_t stream) {
-#define TT_WG3(CO, CI) if (Cout == CO * 8 && Cin == CI * 8) return launch_wgrad3<CO, CI, KH>(x, dz, dw, db, B, cin_real, cout_real, H, T, d, scratch, stream);
+#define TT_WG3(CO, CI) if (Cout == CO * 8 && Cin == CI * 8) return launch_wgrad3<CO, CI>(x, dz, dw, db, B, cin_real, cout_real, H, T, d, scratch, stream);
     TT_WG3(1, 1) TT_WG3(2, 2) TT_WG3(4, 4) TT_WG3(1, 2) TT_WG3(2, 1) TT_WG3(2, 4) TT_WG3(4, 2) TT_WG3(1, 4) TT_WG3(4, 1)
 #undef TT_WG3
     return TT_ERR_UNSUPPORTED;
@@ -1049,11 +1045,11 @@ extern "C" int tt_conv_wgrad_same(const void* x, const void* dz, float* dw, floa
     cudaStream_t stream = (cudaStream_t)stream_;
     if (k == 3) {
         static const bool legacy = getenv("TT_WGRAD_LEGACY") != nullptr;       // A/B switch: the one-MMA-per-tap kernel
-        if (!legacy) return wgrad3_dispatch<3>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, T, dilation, scratch, stream);
+        if (!legacy) return wgrad3_dispatch(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, T, dilation, scratch, stream);
         return wgrad_any<3, 3, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, dilation, scratch, stream);
     }
-    // (the resident-strip kernel also runs 1x1 layers - wgrad3_dispatch<1> - but one CTA per SM hides less latency than the ring kernel's
-    // co-resident CTAs: measured equal; the ring kernel without its "ones" MMA is the faster one)
+    // (1x1 layers through resident strips - plain or with four image rows per MMA - were measured slower than the ring kernel with its
+    // co-resident CTAs: 293 vs 205 us at the largest stage; the ring kernel without its "ones" MMA stays)
     return wgrad_any<1, 1, 1>(x, dz, dw, db, B, Cin, Cout, cin_real, cout_real, H, H, T, 1, scratch, stream);
 }
 
