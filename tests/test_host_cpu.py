@@ -363,3 +363,40 @@ def test_weight_packing_strided_transposed_latent():
         latp[:, :D] = lat[0, :, 0].t()
         got = torch.stack([latp @ packed[h].float().permute(1, 0, 2).reshape(packed.shape[2], -1).t()[:, :C0] + tables[ind, h, :C0] for h in range(H4)])
         assert torch.allclose(got.permute(2, 0, 1), want, atol=1e-4)
+
+
+def test_pipeline_numa_helpers(monkeypatch, tmp_path):
+    """framework.pipeline: the GPU-local CPU list is parsed from sysfs; near_gpu narrows the affinity to it and restores it, and is a
+    no-op where the kernel gives no answer (no GPU needed: the device properties and the sysfs path are stubbed)."""
+    import builtins
+    import os
+    from timbre_trap_b200.framework import pipeline as PL
+
+    class Props:
+        pci_domain_id, pci_bus_id, pci_device_id = 0, 0x1b, 0
+
+    monkeypatch.setattr(PL.torch.cuda, 'get_device_properties', lambda d: Props())
+    real_open = builtins.open
+    listing = {'text': '0-1,3\n'}
+
+    def fake_open(path, *a, **k):
+        if str(path).endswith('0000:1b:00.0/local_cpulist'):
+            f = tmp_path / 'cpulist'
+            f.write_text(listing['text'])
+            return real_open(f, *a, **k)
+        return real_open(path, *a, **k)
+
+    monkeypatch.setattr(builtins, 'open', fake_open)
+    assert PL.gpu_local_cpus('cuda:0') == {0, 1, 3}
+    listing['text'] = '\n'
+    assert PL.gpu_local_cpus('cuda:0') is None
+    if hasattr(os, 'sched_getaffinity'):
+        before = os.sched_getaffinity(0)
+        with PL.near_gpu('cuda:0') as moved:                     # no list: nothing changes
+            assert moved is False and os.sched_getaffinity(0) == before
+        listing['text'] = ','.join(str(c) for c in sorted(before)[:1]) + '\n'
+        with PL.near_gpu('cuda:0') as moved:
+            assert os.sched_getaffinity(0) == set(sorted(before)[:1]) and moved == (len(before) > 1)
+        assert os.sched_getaffinity(0) == before
+    monkeypatch.setattr(PL.torch.cuda, 'get_device_properties', lambda d: (_ for _ in ()).throw(RuntimeError('no device')))
+    assert PL.gpu_local_cpus('cuda:0') is None
